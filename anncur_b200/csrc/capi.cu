@@ -1,0 +1,191 @@
+// extern "C" surface of libanncur_b200.so (include/anncur_b200.h): argument checking, workspace
+// carving and dispatch into the kernel translation units.  No torch types, no allocation.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace anncur {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += uint64_t(n); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// rows of the score matrix materialised at once by the FFMA path (scratch = rows x N fp32 <= ~1 GiB)
+static int f32_row_block(int n_queries, int64_t n_items) {
+    int64_t rows = (int64_t(1) << 28) / (n_items > 0 ? n_items : 1);
+    rows = rows / 128 * 128;
+    if (rows < 128) rows = 128;
+    if (rows > n_queries) rows = n_queries;
+    return int(rows);
+}
+
+}  // namespace anncur
+
+using namespace anncur;
+
+extern "C" {
+
+int anncur_abi_version(void) { return ANNCUR_ABI_VERSION; }
+const char* anncur_last_error(void) { return g_err; }
+uint64_t anncur_kernel_launch_count(void) { return g_launches; }
+void anncur_reset_kernel_launch_count(void) { g_launches = 0; }
+
+size_t anncur_pinv_workspace_bytes(int m, int n) { return pinv_workspace_bytes(m, n); }
+
+int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(m >= 0 && n >= 0, "pinv: negative shape %d x %d", m, n);
+    if (m == 0 || n == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(A && out && workspace, "pinv: null pointer");
+    ANNCUR_REQUIRE(lda >= n && ldo >= m, "pinv: lda %d < n %d or ldo %d < m %d", lda, n, ldo, m);
+    return pinv_f32(A, m, n, lda, rcond, out, ldo, cond_out, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
+int anncur_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int m, int n, int k,
+                    void* stream) {
+    ANNCUR_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative shape");
+    if (m == 0 || n == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(C && (k == 0 || (A && B)), "gemm: null pointer");
+    ANNCUR_REQUIRE(ldc >= n && (k == 0 || (lda >= k && ldb >= n)), "gemm: leading dimension too small");
+    return sgemm_rowmajor(A, lda, B, ldb, C, ldc, m, n, k, cudaStream_t(stream));
+}
+
+size_t anncur_packed_items_bytes(int64_t n_items, int k_dim, int kind) { return packed_items_bytes(n_items, k_dim, kind); }
+
+int anncur_pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind, void* packed,
+                      float* e_scale_out, void* stream) {
+    ANNCUR_REQUIRE(n_items >= 0 && k_dim >= 0, "pack_items: negative shape");
+    ANNCUR_REQUIRE(packed && e_scale_out, "pack_items: null pointer");
+    ANNCUR_REQUIRE(n_items == 0 || k_dim == 0 || (E && lde >= n_items), "pack_items: bad E / lde");
+    ANNCUR_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "pack_items: packed must be 256-byte aligned");
+    return pack_items(E, lde, n_items, k_dim, kind, packed, e_scale_out, cudaStream_t(stream));
+}
+
+size_t anncur_score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
+    return score_topk_workspace_bytes(n_queries, n_items, k_dim, k, kind);
+}
+
+int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                      int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
+                      int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim >= 0, "score_topk: negative shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_vals && out_idx, "score_topk: null output");
+    ANNCUR_REQUIRE(n_items == 0 || k_dim == 0 || (Q && packed_items && e_scale && workspace && ldq >= k_dim),
+                   "score_topk: null input or ldq < k_dim");
+    return score_topk_fused(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, k, idx_offset, out_vals,
+                            out_idx, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
+size_t anncur_score_topk_f32_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k) {
+    (void)k_dim; (void)k;
+    if (n_queries <= 0 || n_items <= 0) return 256;
+    return align_up(sizeof(float) * size_t(f32_row_block(n_queries, n_items)) * size_t(n_items), 256);
+}
+
+int anncur_score_topk_f32(const float* Q, int ldq, int n_queries, const float* E, int64_t lde, int64_t n_items,
+                          int k_dim, int k, int64_t idx_offset, float* out_vals, int64_t* out_idx, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim >= 0, "score_topk_f32: negative shape");
+    ANNCUR_REQUIRE(k >= 1 && k <= ANNCUR_MAX_K, "score_topk_f32: k = %d outside [1, %d]", k, ANNCUR_MAX_K);
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_vals && out_idx && workspace, "score_topk_f32: null pointer");
+    ANNCUR_REQUIRE(k_dim == 0 || n_items == 0 || (Q && E && ldq >= k_dim && lde >= n_items), "score_topk_f32: bad input");
+    if (workspace_bytes < anncur_score_topk_f32_workspace_bytes(n_queries, n_items, k_dim, k)) {
+        set_error("score_topk_f32 workspace too small");
+        return ANNCUR_E_WORKSPACE;
+    }
+    cudaStream_t s = cudaStream_t(stream);
+    float* scratch = reinterpret_cast<float*>(workspace);
+    const int rb = f32_row_block(n_queries, n_items > 0 ? n_items : 1);
+    for (int r0 = 0; r0 < n_queries; r0 += rb) {
+        const int rows = n_queries - r0 < rb ? n_queries - r0 : rb;
+        int rc = sgemm_rowmajor(Q + int64_t(r0) * ldq, ldq, E, lde, scratch, n_items, rows, n_items, k_dim, s);
+        if (rc != ANNCUR_OK) return rc;
+        rc = select_topk_dense(scratch, n_items, rows, n_items, k, idx_offset, out_vals + int64_t(r0) * k,
+                               out_idx + int64_t(r0) * k, s);
+        if (rc != ANNCUR_OK) return rc;
+    }
+    return ANNCUR_OK;
+}
+
+int anncur_topk_rows_f32(const float* S, int64_t lds, int n_rows, int64_t n_cols, int k, int64_t idx_offset,
+                         float* out_vals, int64_t* out_idx, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0 && n_cols >= 0, "topk_rows: negative shape");
+    ANNCUR_REQUIRE(k >= 1 && k <= ANNCUR_MAX_K, "topk_rows: k = %d outside [1, %d]", k, ANNCUR_MAX_K);
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_vals && out_idx && (n_cols == 0 || (S && lds >= n_cols)), "topk_rows: bad pointers / lds");
+    ANNCUR_REQUIRE(n_cols < (int64_t(1) << 32) - 1, "topk_rows: n_cols too large");
+    return select_topk_dense(S, lds, n_rows, n_cols, k, idx_offset, out_vals, out_idx, cudaStream_t(stream));
+}
+
+int anncur_merge_topk(const float* cand_vals, const int64_t* cand_idx, int n_rows, int n_cand, int k, float* out_vals,
+                      int64_t* out_idx, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0 && n_cand >= 0, "merge_topk: negative shape");
+    ANNCUR_REQUIRE(k >= 1 && k <= ANNCUR_MAX_K, "merge_topk: k = %d outside [1, %d]", k, ANNCUR_MAX_K);
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_vals && out_idx && (n_cand == 0 || (cand_vals && cand_idx)), "merge_topk: null pointer");
+    return select_topk_pairs(cand_vals, cand_idx, n_rows, n_cand, k, out_vals, out_idx, cudaStream_t(stream));
+}
+
+int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,
+                          int k_retr, const int64_t* exact_idx, int k_max, const int* k_list_host, int n_k,
+                          int64_t* out_rr_idx, float* out_rr_vals, int32_t* out_common, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0, "rerank_overlap: negative n_rows");
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(exact && retr_idx && exact_idx && k_list_host && out_rr_idx && out_rr_vals && out_common,
+                   "rerank_overlap: null pointer");
+    ANNCUR_REQUIRE(lds >= n_cols, "rerank_overlap: lds < n_cols");
+    return rerank_overlap(exact, lds, n_rows, n_cols, retr_idx, k_retr, exact_idx, k_max, k_list_host, n_k,
+                          out_rr_idx, out_rr_vals, out_common, cudaStream_t(stream));
+}
+
+int anncur_recon_error_f32(const float* Q, int ldq, const float* E, int64_t lde, const float* A, int64_t lda,
+                           int n_rows, int64_t n_items, int k_dim, double* out_err2, double* out_norm2,
+                           void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0 && n_items >= 0 && k_dim >= 0, "recon_error: negative shape");
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_err2 && out_norm2, "recon_error: null output");
+    ANNCUR_REQUIRE(n_items == 0 || (A && lda >= n_items && (k_dim == 0 || (Q && E && ldq >= k_dim && lde >= n_items))),
+                   "recon_error: bad input");
+    return recon_error(Q, ldq, E, lde, A, lda, n_rows, n_items, k_dim, out_err2, out_norm2, cudaStream_t(stream));
+}
+
+size_t anncur_adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next) {
+    return adaptive_round_workspace_bytes(n_queries, k_q, m, n_items, n_next);
+}
+
+int anncur_adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const int64_t* anchors,
+                          const float* c, int n_queries, int m, double rcond, int n_next, int64_t* next_idx,
+                          float* next_val, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && k_q > 0 && m > 0 && n_items > 0, "adaptive_round: bad shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(R_anc && anchors && c && next_idx && next_val && workspace, "adaptive_round: null pointer");
+    ANNCUR_REQUIRE(ldr >= n_items, "adaptive_round: ldr < n_items");
+    ANNCUR_REQUIRE(n_next >= 1 && n_next <= ANNCUR_MAX_K, "adaptive_round: n_next = %d outside [1, %d]", n_next, ANNCUR_MAX_K);
+    return adaptive_round(R_anc, ldr, k_q, n_items, anchors, c, n_queries, m, rcond, n_next, next_idx, next_val,
+                          workspace, workspace_bytes, cudaStream_t(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Internal C++ entry points of the kernel translation units (wrapped by capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace anncur {
+
+// select_topk.cu
+int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, int k, int64_t idx_offset,
+                      float* out_vals, int64_t* out_idx, cudaStream_t stream);
+int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
+                         int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
+                         cudaStream_t stream);
+int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
+                      int64_t* out_idx, cudaStream_t stream);
+
+// sgemm.cu
+int sgemm_rowmajor(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int m,
+                   int64_t n, int k, cudaStream_t stream);
+int recon_error(const float* Q, int64_t ldq, const float* E, int64_t lde, const float* A, int64_t lda, int n_rows,
+                int64_t n_items, int k_dim, double* out_err2, double* out_norm2, cudaStream_t stream);
+
+// pinv.cu
+size_t pinv_workspace_bytes(int m, int n);
+int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// rerank.cu
+int rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,
+                   int k_retr, const int64_t* exact_idx, int k_max, const int* k_list_host, int n_k,
+                   int64_t* out_rr_idx, float* out_rr_vals, int32_t* out_common, cudaStream_t stream);
+
+// score_topk_umma.cu (tcgen05 / TMEM / TMA)
+size_t packed_items_bytes(int64_t n_items, int k_dim, int kind);
+int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind, void* packed,
+               float* e_scale_out, cudaStream_t stream);
+size_t score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind);
+int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                     int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
+                     int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// adaptive.cu
+size_t adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next);
+int adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const int64_t* anchors,
+                   const float* c, int n_queries, int m, double rcond, int n_next, int64_t* next_idx,
+                   float* next_val, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace anncur

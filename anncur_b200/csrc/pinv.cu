@@ -1,0 +1,240 @@
+// K1: Moore-Penrose pseudo-inverse of an fp32 matrix, replacing np.linalg.pinv at
+// eval/matrix_approx_zeshel.py:47,49 (LAPACK SVD, singular values <= rcond*s_max dropped).
+//
+// One-sided (Hestenes) Jacobi SVD in fp64 on the tall orientation T (len x p, p = min(m, n)):
+// columns are rotated pairwise until mutually orthogonal, T.V = G, sigma_j = |g_j|, and
+//     pinv(T) = V . diag(1/sigma_j^2 [sigma_j > rcond*sigma_max]) . G^T            (p x len)
+// Columns of G and V are stored contiguously (k-major), one CTA per column pair per round of a
+// round-robin tournament; everything stays on the device and on the caller's stream (a converged
+// flag turns the remaining round launches into no-ops instead of synchronising with the host).
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace anncur {
+
+constexpr int JAC_THREADS = 256;
+constexpr int JAC_MAX_SWEEPS = 30;
+
+struct JacobiState {
+    unsigned long long max_off_bits;   // max |g_i.g_j| / (|g_i||g_j|) seen in this sweep (double bits)
+    int converged;
+    int sweeps_done;
+    double s_max, s_min_kept;
+};
+
+__global__ void jacobi_init_kernel(const float* __restrict__ A, int m, int n, int lda, int len, int p,
+                                   bool tall, double* __restrict__ G, double* __restrict__ V, JacobiState* st) {
+    // G[j][r] = T[r][j];  tall: T = A (len = m, p = n);  wide: T = A^T (len = n, p = m)
+    const int64_t total = int64_t(len) * p;
+    for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+        int j = int(t / len), r = int(t % len);
+        G[t] = tall ? double(A[int64_t(r) * lda + j]) : double(A[int64_t(j) * lda + r]);
+    }
+    const int64_t vt = int64_t(p) * p;
+    for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < vt; t += int64_t(gridDim.x) * blockDim.x)
+        V[t] = (t / p == t % p) ? 1.0 : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->max_off_bits = 0ull; st->converged = 0; st->sweeps_done = 0; st->s_max = 0.0; st->s_min_kept = 0.0;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < JAC_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobi_round_kernel(double* __restrict__ G, double* __restrict__ V, int len, int p, int p_even, int round,
+                    double tol, JacobiState* st) {
+    if (st->converged) return;
+    __shared__ double red[JAC_THREADS / 32];
+    __shared__ double cs[2];
+    // round-robin tournament (circle method): player p_even-1 is fixed, the rest rotate
+    int i, j;
+    const int q = p_even - 1;
+    if (blockIdx.x == 0) { i = q; j = round % q; }
+    else { i = (round + int(blockIdx.x)) % q; j = (round - int(blockIdx.x) + q) % q; }
+    if (i >= p || j >= p) return;                      // bye (odd p)
+    if (i > j) { int t = i; i = j; j = t; }
+    double* gi = G + int64_t(i) * len;
+    double* gj = G + int64_t(j) * len;
+    double a = 0.0, b = 0.0, g = 0.0;
+    for (int r = threadIdx.x; r < len; r += JAC_THREADS) {
+        double x = gi[r], y = gj[r];
+        a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+    }
+    a = block_sum(a, red); b = block_sum(b, red); g = block_sum(g, red);
+    if (threadIdx.x == 0) {
+        double c = 1.0, s = 0.0;
+        if (a > 0.0 && b > 0.0) {
+            double off = fabs(g) / sqrt(a * b);
+            atomicMax(&st->max_off_bits, (unsigned long long)__double_as_longlong(off));
+            if (off > tol) {
+                double zeta = (b - a) / (2.0 * g);
+                double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                c = 1.0 / sqrt(1.0 + t * t);
+                s = c * t;
+            }
+        }
+        cs[0] = c; cs[1] = s;
+    }
+    __syncthreads();
+    const double c = cs[0], s = cs[1];
+    if (s == 0.0) return;
+    for (int r = threadIdx.x; r < len; r += JAC_THREADS) {
+        double x = gi[r], y = gj[r];
+        gi[r] = c * x - s * y;
+        gj[r] = s * x + c * y;
+    }
+    double* vi = V + int64_t(i) * p;
+    double* vj = V + int64_t(j) * p;
+    for (int r = threadIdx.x; r < p; r += JAC_THREADS) {
+        double x = vi[r], y = vj[r];
+        vi[r] = c * x - s * y;
+        vj[r] = s * x + c * y;
+    }
+}
+
+__global__ void jacobi_sweep_end_kernel(JacobiState* st, double tol) {
+    if (st->converged) return;
+    double off = __longlong_as_double((long long)st->max_off_bits);
+    st->sweeps_done += 1;
+    if (off <= tol) st->converged = 1;
+    st->max_off_bits = 0ull;
+}
+
+// sigma_j^2 -> weights 1/sigma_j^2 with numpy's cutoff; one CTA, p threads strided
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobi_weights_kernel(const double* __restrict__ G, int len, int p, double rcond, double* __restrict__ w,
+                      JacobiState* st) {
+    __shared__ double red[JAC_THREADS / 32];
+    __shared__ double smax;
+    // pass 1: squared norms (one column per loop trip, whole CTA reduces)
+    double local_max = 0.0;
+    for (int j = 0; j < p; ++j) {
+        double a = 0.0;
+        const double* g = G + int64_t(j) * len;
+        for (int r = threadIdx.x; r < len; r += JAC_THREADS) a = fma(g[r], g[r], a);
+        a = block_sum(a, red);
+        if (threadIdx.x == 0) w[j] = a;
+        local_max = fmax(local_max, a);
+    }
+    if (threadIdx.x == 0) smax = sqrt(local_max);
+    __syncthreads();
+    const double cutoff = rcond * smax;
+    double min_kept = smax;
+    for (int j = threadIdx.x; j < p; j += JAC_THREADS) {
+        double sig = sqrt(w[j]);
+        bool keep = sig > cutoff && sig > 0.0;
+        w[j] = keep ? 1.0 / w[j] : 0.0;
+        if (keep) min_kept = fmin(min_kept, sig);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) min_kept = fmin(min_kept, __shfl_xor_sync(0xffffffffu, min_kept, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = min_kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mk = red[0];
+        for (int i = 1; i < JAC_THREADS / 32; ++i) mk = fmin(mk, red[i]);
+        st->s_max = smax; st->s_min_kept = mk;
+    }
+}
+
+// P[i][r] = sum_j V[j][i] * w[j] * G[j][r]   (p x len), written as fp32 to out (optionally transposed)
+constexpr int PT = 32;
+__global__ void __launch_bounds__(PT * 8)
+pinv_compose_kernel(const double* __restrict__ V, const double* __restrict__ G, const double* __restrict__ w,
+                    int len, int p, bool transpose_out, float* __restrict__ out, int ldo) {
+    __shared__ double Vs[PT][PT + 1];
+    __shared__ double Gs[PT][PT + 1];
+    const int tx = threadIdx.x % PT, ty = threadIdx.x / PT;       // 32 x 8 threads, 4 rows each
+    const int i0 = blockIdx.y * PT, r0 = blockIdx.x * PT;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j0 = 0; j0 < p; j0 += PT) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int jj = ty + s * 8, j = j0 + jj;
+            Vs[jj][tx] = (j < p && i0 + tx < p) ? V[int64_t(j) * p + i0 + tx] * w[j] : 0.0;
+            Gs[jj][tx] = (j < p && r0 + tx < len) ? G[int64_t(j) * len + r0 + tx] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int jj = 0; jj < PT; ++jj) {
+            double g = Gs[jj][tx];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[s] = fma(Vs[jj][ty + s * 8], g, acc[s]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int i = i0 + ty + s * 8, r = r0 + tx;
+        if (i < p && r < len) {
+            if (transpose_out) out[int64_t(r) * ldo + i] = float(acc[s]);
+            else out[int64_t(i) * ldo + r] = float(acc[s]);
+        }
+    }
+}
+
+__global__ void pinv_export_cond_kernel(const JacobiState* st, double* cond_out) {
+    cond_out[0] = st->s_max;
+    cond_out[1] = st->s_min_kept;
+}
+
+size_t pinv_workspace_bytes(int m, int n) {
+    if (m <= 0 || n <= 0) return 256;
+    size_t len = size_t(m > n ? m : n), p = size_t(m > n ? n : m);
+    return align_up(sizeof(double) * (len * p + p * p + p), 256) + 256;
+}
+
+int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return ANNCUR_OK;   // empty anchor set: pinv is the empty n x m matrix
+    if (workspace_bytes < pinv_workspace_bytes(m, n)) {
+        set_error("pinv workspace too small: %zu < %zu", workspace_bytes, pinv_workspace_bytes(m, n));
+        return ANNCUR_E_WORKSPACE;
+    }
+    const bool tall = m >= n;
+    const int len = tall ? m : n, p = tall ? n : m;
+    JacobiState* st = reinterpret_cast<JacobiState*>(workspace);
+    double* G = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+    double* V = G + size_t(len) * p;
+    double* w = V + size_t(p) * p;
+
+    jacobi_init_kernel<<<sm_count() * 4, 256, 0, stream>>>(A, m, n, lda, len, p, tall, G, V, st);
+    ANNCUR_LAUNCH_OK("jacobi_init_kernel");
+    const double tol = fmax(1e-15, 4.0 * sqrt(double(len)) * 1.1102230246251565e-16);
+    if (p > 1) {
+        const int p_even = (p + 1) & ~1;
+        for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+            for (int round = 0; round < p_even - 1; ++round) {
+                jacobi_round_kernel<<<p_even / 2, JAC_THREADS, 0, stream>>>(G, V, len, p, p_even, round, tol, st);
+                ANNCUR_LAUNCH_OK("jacobi_round_kernel");
+            }
+            jacobi_sweep_end_kernel<<<1, 1, 0, stream>>>(st, tol);
+            ANNCUR_LAUNCH_OK("jacobi_sweep_end_kernel");
+        }
+    }
+    jacobi_weights_kernel<<<1, JAC_THREADS, 0, stream>>>(G, len, p, rcond, w, st);
+    ANNCUR_LAUNCH_OK("jacobi_weights_kernel");
+    dim3 grid((len + PT - 1) / PT, (p + PT - 1) / PT);
+    // tall: pinv(A) = P (n x m = p x len);  wide: pinv(A) = P^T (n x m = len x p)
+    pinv_compose_kernel<<<grid, PT * 8, 0, stream>>>(V, G, w, len, p, !tall, out, ldo);
+    ANNCUR_LAUNCH_OK("pinv_compose_kernel");
+    if (cond_out) {
+        pinv_export_cond_kernel<<<1, 1, 0, stream>>>(st, cond_out);
+        ANNCUR_LAUNCH_OK("pinv_export_cond_kernel");
+    }
+    return ANNCUR_OK;
+}
+
+}  // namespace anncur

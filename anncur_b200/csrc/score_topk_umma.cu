@@ -1,0 +1,728 @@
+// K3 + K4: fused approximate-score GEMM and streaming per-row top-k on tcgen05 / TMEM / TMA.
+//
+//   scores = Q (B x K) . E (K x N)            eval/matrix_approx_zeshel.py:109-119 (get_complete_row)
+//   torch.topk(scores, k, dim=1)               eval/matrix_approx_zeshel.py:121-126 (topk_in_row)
+// without ever writing the B x N score matrix.
+//
+// Precision kinds
+//   F32X3 : every fp32 operand x (scaled by a power of two into fp16 range) is split into two
+//           fp16 terms x = h + l (22-23 significant bits).  Three tcgen05 kind::f16 passes
+//           h.h + h.l + l.h accumulate in one fp32 TMEM tile -- fp32-grade scores at 1/3 of the
+//           f16 tensor rate, and each operand still costs 4 bytes per element like plain fp32.
+//   BF16  : single bf16 pass.
+//
+// Layout in HBM (built once per index by pack_items, per batch for Q by pack_queries):
+//   plane[kb][row][32]  16-bit elements, kb = k / 32; a TMA box {32, rows, 1} is one contiguous
+//   rows*64-byte span and lands in shared memory in the canonical K-major SWIZZLE_64B layout.
+//
+// Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
+//   warp 0      TMA producer  (4-stage ring: Q tile 128 x 32 and E tile 256 x 32 per plane)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator 128 x 256 fp32,
+//               double-buffered in the 512 TMEM columns
+//   warps 2-5   epilogue: thread = one query row; tcgen05.ld 32 columns at a time, compare with
+//               the row's running threshold (k-th best so far), push the rare survivors as 64-bit
+//               keys to the row's candidate list (L2-resident), and when a list fills up the warp
+//               radix-selects it back to k entries and tightens the threshold.  Thresholds are
+//               shared between the item chunks of a row through global memory.
+// Work item = (chunk of item tiles, 128-query tile), ordered chunk-major so that co-resident CTAs
+// stream the same slice of E and it is read from HBM once.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace anncur {
+
+// ------------------------------------------------------------------------------------------------
+constexpr int BLOCK_M = 128;           // queries per tile (TMEM lanes)
+constexpr int BLOCK_N = 256;           // items per tile (TMEM columns per accumulator buffer)
+constexpr int BLOCK_K = 32;            // 16-bit elements per k-block = 64 bytes = one SWIZZLE_64B row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 8 KB
+constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int FUSED_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
+
+template <int PASSES> struct StageCfg {
+    static constexpr int kStageBytes = PASSES == 3 ? 2 * (A_PLANE_BYTES + B_PLANE_BYTES) : (A_PLANE_BYTES + B_PLANE_BYTES);
+    static constexpr int kStages = PASSES == 3 ? 4 : 8;
+};
+
+struct FusedParams {
+    int n_queries;
+    int n_items;
+    int num_kb;
+    int k;
+    int m_tiles;
+    int n_tiles;
+    int n_chunks;
+    uint64_t* cand;          // [n_queries][n_chunks][cap]
+    uint32_t* counts;        // [n_queries][n_chunks]
+    uint32_t* thr_shared;    // [n_queries] ordered-uint lower bound (exclusive) on useful scores
+    int* error_flag;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+            if (error_flag) atomicExch(error_flag, 1);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_64B canonical layout: rows of 64 bytes, 8-row groups 512 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3fffu);        // start address
+    d |= uint64_t(1) << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t(512 >> 4) << 32;                // stride byte offset: 8 rows x 64 B
+    d |= uint64_t(1) << 46;                       // descriptor version (sm_100)
+    d |= uint64_t(4) << 61;                       // layout type SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- warp-cooperative compaction of one row's candidate list back to its best k -----------------
+// Called by all 32 lanes.  list: n (> k) keys in global memory.  Returns the k-th best key.
+template <int CPL>
+__device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, uint32_t n, uint32_t k, uint32_t* hist) {
+    const uint32_t lane = lane_id();
+    uint64_t key[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        uint32_t t = uint32_t(i) * 32u + lane;
+        key[i] = t < n ? __ldcg(list + t) : 0ull;
+    }
+    uint64_t prefix = 0, mask = 0;
+    uint32_t need = k;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+            if (key[i] != 0ull && (key[i] & mask) == prefix) atomicAdd(&hist[uint32_t(key[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        uint32_t c[8], lane_sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+        uint32_t incl = lane_sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_down_sync(0xffffffffu, incl, off);
+            if (lane + off < 32) incl += t;
+        }
+        uint32_t running = incl - lane_sum;
+        bool found = false;
+        uint32_t d = 0, new_need = 0, bucket = 0;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+            if (!found && running + c[b] >= need) { found = true; d = lane * 8 + b; new_need = need - running; bucket = c[b]; }
+            running += c[b];
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, found);
+        const int src = ballot ? 31 - __clz(int(ballot)) : 0;
+        d = __shfl_sync(0xffffffffu, d, src);
+        new_need = __shfl_sync(0xffffffffu, new_need, src);
+        bucket = __shfl_sync(0xffffffffu, bucket, src);
+        __syncwarp();
+        if (ballot == 0) break;                          // fewer than `need` keys left: keep them all
+        prefix |= uint64_t(d) << shift;
+        mask |= 0xffull << shift;
+        need = new_need;
+        if (bucket == need) break;                       // digit bucket taken whole
+    }
+    // keep keys >= the selected prefix; write them back densely; find the smallest kept key
+    uint32_t running = 0;
+    uint64_t kth = ~0ull;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        const bool keep = key[i] != 0ull && (key[i] & mask) >= prefix;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            list[running + __popc(ballot & ((1u << lane) - 1u))] = key[i];
+            kth = key[i] < kth ? key[i] : kth;
+        }
+        running += __popc(ballot);
+    }
+    return warp_min_u64(kth);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int PASSES, bool BF16, int CPL>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                        const FusedParams p) {
+    using Cfg = StageCfg<PASSES>;
+    constexpr int NS = Cfg::kStages;
+    constexpr uint32_t CAP = uint32_t(CPL) * 32u;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+    // bars: full[NS] | empty[NS] | tmem_full[2] | tmem_empty[2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+    uint32_t* hist_all = tmem_ptr_smem + 4;                      // NUM_EPI_WARPS x 256
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(NS + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * uint32_t(2 * NS + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * uint32_t(2 * NS + 2 + b); };
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+        if (PASSES == 3) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+        }
+        for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+    const int total_items = p.n_chunks * p.m_tiles;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+                const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
+                const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
+                const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
+                for (int tile = t0; tile < t1; ++tile) {
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag);
+                        const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes;
+                        mbar_expect_tx(full_bar(stage), uint32_t(Cfg::kStageBytes));
+                        if (PASSES == 3) {
+                            tma_load_3d(sb, &tmA0, full_bar(stage), 0, m_tile * BLOCK_M, kb);
+                            tma_load_3d(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), 0, m_tile * BLOCK_M, kb);
+                            tma_load_3d(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), 0, tile * BLOCK_N, kb);
+                            tma_load_3d(sb + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &tmB1, full_bar(stage), 0, tile * BLOCK_N, kb);
+                        } else {
+                            tma_load_3d(sb, &tmA0, full_bar(stage), 0, m_tile * BLOCK_M, kb);
+                            tma_load_3d(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), 0, tile * BLOCK_N, kb);
+                        }
+                        if (++stage == NS) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B f16 or bf16, both K-major, N = 256, M = 128
+            const uint32_t fmt = BF16 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+                const int chunk = w / p.m_tiles;
+                const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
+                const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
+                for (int tile = t0; tile < t1; ++tile) {
+                    mbar_wait(tempty_bar(buf), acc_phase ^ 1u, p.error_flag);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + uint32_t(buf) * BLOCK_N;
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(full_bar(stage), phase, p.error_flag);
+                        tcgen05_fence_after();
+                        const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes;
+#pragma unroll
+                        for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                            const uint32_t koff = uint32_t(ks) * UMMA_K * 2;          // bytes inside the 64 B row
+                            const uint32_t accum = (kb | ks) != 0 ? 1u : 0u;
+                            if (PASSES == 3) {
+                                const uint64_t a_h = make_smem_desc_sw64(sb + koff);
+                                const uint64_t a_l = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
+                                const uint64_t b_h = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + koff);
+                                const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + B_PLANE_BYTES + koff);
+                                umma_f16(d_tmem, a_h, b_h, idesc, accum);
+                                umma_f16(d_tmem, a_h, b_l, idesc, 1u);
+                                umma_f16(d_tmem, a_l, b_h, idesc, 1u);
+                            } else {
+                                const uint64_t a = make_smem_desc_sw64(sb + koff);
+                                const uint64_t b = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
+                                umma_f16(d_tmem, a, b, idesc, accum);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                        if (++stage == NS) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(buf));                       // accumulator ready for the epilogue
+                    if (++buf == 2) { buf = 0; acc_phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        uint32_t* hist = hist_all + (warp - 2) * 256;
+        int buf = 0; uint32_t acc_phase = 0;
+        const uint32_t k = uint32_t(p.k);
+        for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+            const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
+            const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
+            const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
+            const int row = m_tile * BLOCK_M + q * 32 + int(lane);
+            const bool row_ok = row < p.n_queries;
+            const int row_c = row_ok ? row : 0;
+            uint64_t* list = p.cand + (int64_t(row_c) * p.n_chunks + chunk) * int64_t(CAP);
+            uint32_t cnt = 0;
+            float thr_own = -INFINITY;
+            for (int tile = t0; tile < t1; ++tile) {
+                // refresh the cross-chunk bound (exclusive) before blocking on the accumulator
+                float thr = INFINITY;
+                if (row_ok) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
+                mbar_wait(tfull_bar(buf), acc_phase, p.error_flag);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
+                const int col_tile = tile * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    // make room: a 32-column group can add at most 32 survivors to a list
+                    uint32_t full_mask = __ballot_sync(0xffffffffu, cnt > CAP - 32u);
+                    while (full_mask) {
+                        const int src = __ffs(int(full_mask)) - 1;
+                        full_mask &= full_mask - 1;
+                        const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
+                        const uint64_t lp = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(list), src);
+                        __syncwarp();
+                        const uint64_t kth = warp_compact_list<CPL>(reinterpret_cast<uint64_t*>(lp), n_src, k, hist);
+                        __syncwarp();
+                        if (int(lane) == src) {
+                            cnt = k;
+                            thr_own = key_score(kth);
+                            thr = fmaxf(thr, thr_own);
+                            atomicMax(p.thr_shared + row, float_to_ordered(thr_own) - 1u);
+                        }
+                    }
+                    float v[32];
+                    tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
+                    float m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                    if (m > thr) {
+                        const int col0 = col_tile + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] > thr && col0 + j < p.n_items) {
+                                list[cnt] = make_key(v[j], uint32_t(col0 + j));
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                if (++buf == 2) { buf = 0; acc_phase ^= 1u; }
+            }
+            // close the work item: lists longer than k are cut back so the merge sees <= k per chunk
+            uint32_t over_mask = __ballot_sync(0xffffffffu, row_ok && cnt > k);
+            while (over_mask) {
+                const int src = __ffs(int(over_mask)) - 1;
+                over_mask &= over_mask - 1;
+                const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
+                const uint64_t lp = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(list), src);
+                __syncwarp();
+                const uint64_t kth = warp_compact_list<CPL>(reinterpret_cast<uint64_t*>(lp), n_src, k, hist);
+                __syncwarp();
+                if (int(lane) == src) {
+                    cnt = k;
+                    atomicMax(p.thr_shared + row, float_to_ordered(key_score(kth)) - 1u);
+                }
+            }
+            if (row_ok) p.counts[int64_t(row) * p.n_chunks + chunk] = cnt;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- operand packing ------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ X, int64_t ld, int rows, int64_t cols, uint32_t* out_bits) {
+    float m = 0.f;
+    const int64_t total = int64_t(rows) * cols;
+    for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+        float x = fabsf(X[(t / cols) * ld + (t % cols)]);
+        if (x <= FLT_MAX) m = fmaxf(m, x);      // ignore inf / NaN when choosing the scale
+    }
+    m = warp_max_f(m);
+    if (lane_id() == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// power-of-two scale that maps [0, maxabs] into [0, 2^14): fp16 then holds h and the residual l
+__device__ __forceinline__ float pow2_scale_for(float maxabs) {
+    if (!(maxabs > 0.f)) return 1.f;
+    int e;
+    frexpf(maxabs, &e);                          // maxabs = f * 2^e, f in [0.5, 1)
+    e = 14 - e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    return ldexpf(1.f, e);
+}
+
+__global__ void finish_scale_kernel(const uint32_t* maxabs_bits, float* scale_out, bool bf16) {
+    scale_out[0] = bf16 ? 1.f : pow2_scale_for(__uint_as_float(maxabs_bits[0]));
+}
+
+template <bool BF16>
+__device__ __forceinline__ void split_store(float x, uint16_t* plane_h, uint16_t* plane_l, int64_t off) {
+    if (BF16) {
+        plane_h[off] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    } else {
+        __half h = __float2half_rn(x);
+        __half l = __float2half_rn(x - __half2float(h));
+        plane_h[off] = __half_as_ushort(h);
+        plane_l[off] = __half_as_ushort(l);
+    }
+}
+
+// E (k_dim x N, N contiguous) -> plane[kb][n][32].  CTA = one k-block x 64 items, transposed via smem.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int k_dim, const float* __restrict__ scale_p,
+                  uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l) {
+    __shared__ float tile[32][65];
+    const float scale = scale_p[0];
+    const int kb = blockIdx.y;
+    const int64_t n0 = int64_t(blockIdx.x) * 64;
+    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
+        int kk = e / 64, j = e % 64;
+        int kidx = kb * 32 + kk;
+        int64_t n = n0 + j;
+        tile[kk][j] = (kidx < k_dim && n < n_items) ? E[int64_t(kidx) * lde + n] * scale : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+        int j = e / 32, kk = e % 32;
+        int64_t n = n0 + j;
+        if (n < n_items) split_store<BF16>(tile[kk][j], plane_h, plane_l, (int64_t(kb) * n_items + n) * 32 + kk);
+    }
+}
+
+// Q (B x k_dim, k contiguous) -> plane[kb][b][32], one warp per query row, per-row power-of-two scale.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int k_dim, int num_kb,
+                    const float* __restrict__ e_scale, uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l,
+                    float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_queries) return;
+    const uint32_t lane = lane_id();
+    const float* q = Q + int64_t(row) * ldq;
+    float scale = 1.f;
+    if (!BF16) {
+        float m = 0.f;
+        for (int kidx = lane; kidx < k_dim; kidx += 32) {
+            float x = fabsf(q[kidx]);
+            if (x <= FLT_MAX) m = fmaxf(m, x);
+        }
+        scale = pow2_scale_for(warp_max_f(m));
+    }
+    for (int kb = 0; kb < num_kb; ++kb) {
+        int kidx = kb * 32 + int(lane);
+        float x = kidx < k_dim ? q[kidx] * scale : 0.f;
+        split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
+    }
+    if (lane == 0) {
+        row_inv_scale[row] = 1.f / (scale * e_scale[0]);
+        thr_shared[row] = float_to_ordered(-INFINITY);
+    }
+}
+
+__global__ void fill_zero_scores_kernel(int n_queries, int k, int64_t n_items, int64_t idx_offset, float* out_vals,
+                                        int64_t* out_idx) {
+    const int64_t total = int64_t(n_queries) * k;
+    for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+        int j = int(t % k);
+        bool ok = j < n_items;
+        out_vals[t] = ok ? 0.f : ANNCUR_PAD_VAL;
+        out_idx[t] = ok ? j + idx_offset : -1;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int num_kb, int box_rows, bool bf16) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ANNCUR_E_CUDA; }
+    cuuint64_t dims[3] = {cuuint64_t(BLOCK_K), cuuint64_t(rows), cuuint64_t(num_kb)};
+    cuuint64_t strides[2] = {cuuint64_t(BLOCK_K * 2), cuuint64_t(rows) * BLOCK_K * 2};
+    cuuint32_t box[3] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld kb=%d)", int(r), (long long)rows, num_kb); return ANNCUR_E_CUDA; }
+    return ANNCUR_OK;
+}
+
+static int num_kb_for(int k_dim) { return (k_dim + BLOCK_K - 1) / BLOCK_K; }
+static int planes_for(int kind) { return kind == ANNCUR_KIND_F32X3 ? 2 : 1; }
+static size_t plane_bytes(int64_t rows, int k_dim) { return align_up(size_t(num_kb_for(k_dim)) * size_t(rows) * BLOCK_K * 2, 256); }
+
+static uint32_t cap_for_k(int k) {
+    uint32_t want = uint32_t(2 * k) > 256u ? uint32_t(2 * k) : 256u;
+    uint32_t cap = 256;
+    while (cap < want) cap <<= 1;
+    return cap;
+}
+
+// Number of item chunks: pick the split of the item tiles that balances (chunks x query tiles)
+// work items over the SMs; every chunk pays a threshold warm-up worth roughly two tiles.
+static int choose_chunks(int m_tiles, int n_tiles, int sms) {
+    int best_c = 1;
+    double best_cost = 1e300;
+    const int c_max = n_tiles < 256 ? n_tiles : 256;
+    for (int c = 1; c <= c_max; ++c) {
+        const long long items = 1ll * m_tiles * c;
+        const long long waves = (items + sms - 1) / sms;
+        const int tiles_per = (n_tiles + c - 1) / c;
+        const double cost = double(waves) * (tiles_per + 2.0);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+struct FusedPlan {
+    int num_kb, m_tiles, n_tiles, n_chunks;
+    uint32_t cap;
+    size_t off_qplanes, off_inv_scale, off_thr, off_counts, off_cand, off_err, total;
+};
+
+static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
+    FusedPlan pl{};
+    pl.num_kb = num_kb_for(k_dim);
+    pl.m_tiles = (n_queries + BLOCK_M - 1) / BLOCK_M;
+    pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
+    pl.n_chunks = choose_chunks(pl.m_tiles > 0 ? pl.m_tiles : 1, pl.n_tiles > 0 ? pl.n_tiles : 1, sm_count());
+    pl.cap = cap_for_k(k);
+    size_t off = 0;
+    pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, k_dim);
+    pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
+    pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
+    pl.off_counts = off; off += align_up(sizeof(uint32_t) * size_t(n_queries) * pl.n_chunks, 256);
+    pl.off_cand = off; off += align_up(sizeof(uint64_t) * size_t(n_queries) * pl.n_chunks * pl.cap, 256);
+    pl.off_err = off; off += 256;
+    pl.total = off;
+    return pl;
+}
+
+size_t packed_items_bytes(int64_t n_items, int k_dim, int kind) {
+    if (n_items <= 0 || k_dim <= 0) return 256;
+    return size_t(planes_for(kind)) * plane_bytes(n_items, k_dim) + 256;   // +256: max-abs scratch
+}
+
+int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind, void* packed, float* e_scale_out,
+               cudaStream_t stream) {
+    if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_BF16) { set_error("pack_items: unknown kind %d", kind); return ANNCUR_E_INVALID; }
+    const bool bf16 = kind == ANNCUR_KIND_BF16;
+    if (n_items <= 0 || k_dim <= 0) {
+        finish_scale_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(packed), e_scale_out, true);
+        ANNCUR_LAUNCH_OK("finish_scale_kernel");
+        return ANNCUR_OK;
+    }
+    if (n_items >= (int64_t(1) << 31) - BLOCK_N) { set_error("pack_items: n_items %lld too large for one shard", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
+    const size_t pb = plane_bytes(n_items, k_dim);
+    uint16_t* plane_h = reinterpret_cast<uint16_t*>(packed);
+    uint16_t* plane_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(packed) + pb);
+    uint32_t* maxabs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(packed) + size_t(planes_for(kind)) * pb);
+    ANNCUR_CUDA_OK(cudaMemsetAsync(maxabs, 0, 4, stream));
+    if (!bf16) {
+        absmax_kernel<<<sm_count() * 8, 256, 0, stream>>>(E, lde, k_dim, n_items, maxabs);
+        ANNCUR_LAUNCH_OK("absmax_kernel");
+    }
+    finish_scale_kernel<<<1, 1, 0, stream>>>(maxabs, e_scale_out, bf16);
+    ANNCUR_LAUNCH_OK("finish_scale_kernel");
+    dim3 grid(unsigned((n_items + 63) / 64), unsigned(num_kb_for(k_dim)));
+    if (bf16) pack_items_kernel<true><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
+    else pack_items_kernel<false><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
+    ANNCUR_LAUNCH_OK("pack_items_kernel");
+    return ANNCUR_OK;
+}
+
+size_t score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
+    if (n_queries <= 0 || n_items <= 0 || k_dim <= 0 || k <= 0) return 256;
+    return make_plan(n_queries, n_items, k_dim, k, kind).total;
+}
+
+template <int PASSES, bool BF16, int CPL>
+static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+                        const FusedParams& fp, int grid, cudaStream_t stream) {
+    using Cfg = StageCfg<PASSES>;
+    const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4;
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(fused_score_topk_kernel<PASSES, BF16, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fused_score_topk_kernel<PASSES, BF16, CPL><<<grid, FUSED_THREADS, smem, stream>>>(a0, a1, b0, b1, fp);
+    ANNCUR_LAUNCH_OK("fused_score_topk_kernel");
+    return ANNCUR_OK;
+}
+
+template <int PASSES, bool BF16>
+static int dispatch_cap(uint32_t cap, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                        const CUtensorMap& b1, const FusedParams& fp, int grid, cudaStream_t stream) {
+    switch (cap) {
+        case 256: return launch_fused<PASSES, BF16, 8>(a0, a1, b0, b1, fp, grid, stream);
+        case 512: return launch_fused<PASSES, BF16, 16>(a0, a1, b0, b1, fp, grid, stream);
+        case 1024: return launch_fused<PASSES, BF16, 32>(a0, a1, b0, b1, fp, grid, stream);
+        case 2048: return launch_fused<PASSES, BF16, 64>(a0, a1, b0, b1, fp, grid, stream);
+    }
+    set_error("score_topk: no kernel for candidate capacity %u", cap);
+    return ANNCUR_E_UNSUPPORTED;
+}
+
+int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                     int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
+                     int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_BF16) { set_error("score_topk: unknown kind %d", kind); return ANNCUR_E_INVALID; }
+    if (k < 1 || k > ANNCUR_MAX_K_FUSED) { set_error("score_topk: k = %d outside [1, %d]", k, ANNCUR_MAX_K_FUSED); return ANNCUR_E_INVALID; }
+    if (n_queries <= 0) return ANNCUR_OK;
+    if (n_items <= 0 || k_dim <= 0) {
+        // empty anchor set (k_i = 0 is in the reference's grid): all approximate scores are 0
+        fill_zero_scores_kernel<<<sm_count(), 256, 0, stream>>>(n_queries, k, n_items, idx_offset, out_vals, out_idx);
+        ANNCUR_LAUNCH_OK("fill_zero_scores_kernel");
+        return ANNCUR_OK;
+    }
+    if (n_items >= (int64_t(1) << 31) - BLOCK_N) { set_error("score_topk: n_items %lld too large for one shard", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
+    const FusedPlan pl = make_plan(n_queries, n_items, k_dim, k, kind);
+    if (workspace_bytes < pl.total) { set_error("score_topk workspace too small: %zu < %zu", workspace_bytes, pl.total); return ANNCUR_E_WORKSPACE; }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(packed_items) & 255)) {
+        set_error("score_topk: workspace and packed_items must be 256-byte aligned");
+        return ANNCUR_E_INVALID;
+    }
+    const bool bf16 = kind == ANNCUR_KIND_BF16;
+    char* ws = reinterpret_cast<char*>(workspace);
+    const size_t qpb = plane_bytes(n_queries, k_dim);
+    uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
+    uint16_t* q_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
+    float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
+    uint32_t* thr = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pl.off_counts);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+    int* err = reinterpret_cast<int*>(ws + pl.off_err);
+
+    const int qgrid = (n_queries + 7) / 8;
+    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr);
+    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr);
+    ANNCUR_LAUNCH_OK("pack_queries_kernel");
+
+    const size_t epb = plane_bytes(n_items, k_dim);
+    const char* items = reinterpret_cast<const char*>(packed_items);
+    CUtensorMap a0, a1, b0, b1;
+    int rc;
+    if ((rc = make_plane_map(&a0, q_h, n_queries, pl.num_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, BLOCK_N, bf16)) != ANNCUR_OK) return rc;
+    if (bf16) { a1 = a0; b1 = b0; }
+    else {
+        if ((rc = make_plane_map(&a1, q_l, n_queries, pl.num_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&b1, items + epb, n_items, pl.num_kb, BLOCK_N, false)) != ANNCUR_OK) return rc;
+    }
+    FusedParams fp{};
+    fp.n_queries = n_queries; fp.n_items = int(n_items); fp.num_kb = pl.num_kb; fp.k = k;
+    fp.m_tiles = pl.m_tiles; fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
+    fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err;
+    const long long items_total = 1ll * pl.m_tiles * pl.n_chunks;
+    const int grid = int(items_total < sm_count() ? items_total : sm_count());
+    rc = bf16 ? dispatch_cap<1, true>(pl.cap, a0, a1, b0, b1, fp, grid, stream)
+              : dispatch_cap<3, false>(pl.cap, a0, a1, b0, b1, fp, grid, stream);
+    if (rc != ANNCUR_OK) return rc;
+    return select_topk_keylists(cand, counts, pl.n_chunks, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
+                                out_idx, stream);
+}
+
+}  // namespace anncur

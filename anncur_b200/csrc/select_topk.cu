@@ -1,0 +1,226 @@
+// Per-row top-k selection over 64-bit candidate keys (see common.cuh for the key order).
+//
+// One CTA per row.  Three key sources share the kernel:
+//   DenseRow   : a row of fp32 scores            (torch.topk(row, k) of the eval loops; the
+//                 FFMA fallback of score+top-k)   -- HBM/L2-bound streaming, 8-bit radix select
+//   KeyLists   : per-(row, chunk) survivor lists written by the fused tcgen05 kernel
+//   PairLists  : (val, idx) candidate lists       (merge of all-gathered per-shard top-k)
+// Selection = MSD radix select on the key (early exit as soon as a digit bucket is taken whole),
+// then the <= k winners are sorted best-first in shared memory.  When a row's candidates fit in
+// shared memory they are sorted there directly and the radix passes are skipped.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace anncur {
+
+constexpr int kSelectThreads = 512;
+constexpr int kSmemSortCap = 4096;  // keys sorted directly in smem when a row has at most this many
+constexpr int kMaxLists = 1024;     // survivor lists per row (= item chunks of the fused kernel)
+
+struct DenseRow {
+    static constexpr bool kIsLists = false;
+    const float* S;
+    int64_t lds;
+    int64_t n_cols;
+    __device__ int64_t size(int) const { return n_cols; }
+    __device__ uint64_t key(int row, int64_t j) const {
+        return make_key(__ldg(S + int64_t(row) * lds + j), uint32_t(j));
+    }
+};
+
+struct KeyLists {
+    static constexpr bool kIsLists = true;
+    const uint64_t* keys;     // [row][n_lists][cap]
+    const uint32_t* counts;   // [row][n_lists]
+    int n_lists;
+    int cap;
+    __device__ int64_t size(int) const { return int64_t(n_lists) * cap; }
+    __device__ uint64_t key(int row, int64_t j) const {
+        int list = int(j / cap), pos = int(j % cap);
+        uint32_t c = __ldg(counts + int64_t(row) * n_lists + list);
+        return pos < int(c) ? __ldcg(keys + (int64_t(row) * n_lists + list) * cap + pos) : 0ull;
+    }
+};
+
+struct PairLists {
+    static constexpr bool kIsLists = false;
+    const float* vals;        // [row][n_cand]
+    const int64_t* idx;       // [row][n_cand], < 0 = padding
+    int n_cand;
+    __device__ int64_t size(int) const { return n_cand; }
+    __device__ uint64_t key(int row, int64_t j) const {
+        int64_t i = __ldg(idx + int64_t(row) * n_cand + j);
+        return i < 0 ? 0ull : make_key(__ldg(vals + int64_t(row) * n_cand + j), uint32_t(i));
+    }
+};
+
+struct SelectOut {
+    float* vals;              // [row][k]
+    int64_t* idx;             // [row][k]
+    int64_t idx_offset;
+    const float* row_scale;   // optional: value = score * row_scale[row]
+    int k;
+    int n_sort;               // next_pow2(k) (radix path) -- smem holds max(n_sort, kSmemSortCap) keys
+};
+
+__device__ __forceinline__ void write_sorted(const uint64_t* sel, int row, const SelectOut& o) {
+    float scale = o.row_scale ? o.row_scale[row] : 1.0f;
+    for (int t = threadIdx.x; t < o.k; t += blockDim.x) {
+        uint64_t key = sel[t];
+        bool ok = key != 0ull;
+        o.vals[int64_t(row) * o.k + t] = ok ? key_score(key) * scale : ANNCUR_PAD_VAL;
+        o.idx[int64_t(row) * o.k + t] = ok ? int64_t(key_index(key)) + o.idx_offset : int64_t(-1);
+    }
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, SelectOut o) {
+    extern __shared__ __align__(16) uint64_t sel[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_cnt;
+    __shared__ uint64_t s_prefix, s_mask;
+    __shared__ uint32_t s_need, s_done;
+
+    const int row = blockIdx.x;
+    const int64_t M = src.size(row);
+    const int tid = threadIdx.x;
+
+    // ---- survivor lists: usually a few thousand live keys in a much larger slot space -> gather
+    //      the live ones into shared memory and sort there ------------------------------------
+    if constexpr (Src::kIsLists) {
+        __shared__ uint32_t offs[kMaxLists + 1];
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int l = 0; l < src.n_lists; ++l) {
+                offs[l] = run;
+                run += min(__ldg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
+            }
+            offs[src.n_lists] = run;
+        }
+        __syncthreads();
+        const uint32_t total = offs[src.n_lists];
+        if (total <= uint32_t(kSmemSortCap)) {
+            int n_pow2 = 2;
+            while (n_pow2 < int(total) || n_pow2 < o.k) n_pow2 <<= 1;
+            for (int t = tid + int(total); t < n_pow2; t += blockDim.x) sel[t] = 0ull;
+            const int warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+            for (int l = warp; l < src.n_lists; l += n_warps) {
+                const uint32_t base = offs[l], cnt = offs[l + 1] - offs[l];
+                const uint64_t* p = src.keys + (int64_t(row) * src.n_lists + l) * src.cap;
+                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = __ldcg(p + t);
+            }
+            block_bitonic_sort_desc(sel, n_pow2);
+            write_sorted(sel, row, o);
+            return;
+        }
+    }
+
+    // ---- small rows: everything fits in shared memory -> one sort, no radix passes -----------
+    if (M <= kSmemSortCap) {
+        int n_pow2 = 1;
+        while (n_pow2 < M || n_pow2 < o.k) n_pow2 <<= 1;
+        if (n_pow2 < 2) n_pow2 = 2;
+        for (int t = tid; t < n_pow2; t += blockDim.x) sel[t] = t < M ? src.key(row, t) : 0ull;
+        block_bitonic_sort_desc(sel, n_pow2);
+        write_sorted(sel, row, o);
+        return;
+    }
+
+    // ---- radix select of the k-th largest key ---------------------------------------------------
+    if (tid == 0) { s_prefix = 0; s_mask = 0; s_need = uint32_t(o.k); s_done = 0; s_cnt = 0; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int t = tid; t < 256; t += blockDim.x) hist[t] = 0;
+        __syncthreads();
+        if (s_done) break;
+        const uint64_t prefix = s_prefix, mask = s_mask;
+        for (int64_t j = tid; j < M; j += blockDim.x) {
+            uint64_t key = src.key(row, j);
+            if ((key & mask) == prefix) atomicAdd(&hist[uint32_t(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t need = s_need;
+            uint32_t c[8], lane_sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { c[b] = hist[tid * 8 + b]; lane_sum += c[b]; }
+            uint32_t incl = lane_sum;   // inclusive suffix sum over lanes (towards higher digits)
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_down_sync(0xffffffffu, incl, off);
+                if (tid + off < 32) incl += t;
+            }
+            uint32_t running = incl - lane_sum;
+            bool found = false;
+            uint32_t d = 0, new_need = 0, bucket = 0;
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+                if (!found && running + c[b] >= need) {
+                    found = true; d = uint32_t(tid * 8 + b); new_need = need - running; bucket = c[b];
+                }
+                running += c[b];
+            }
+            uint32_t ballot = __ballot_sync(0xffffffffu, found);
+            int src_lane = ballot ? 31 - __clz(int(ballot)) : 0;
+            d = __shfl_sync(0xffffffffu, d, src_lane);
+            new_need = __shfl_sync(0xffffffffu, new_need, src_lane);
+            bucket = __shfl_sync(0xffffffffu, bucket, src_lane);
+            if (tid == 0) {
+                s_prefix = prefix | (uint64_t(d) << shift);
+                s_mask = mask | (0xffull << shift);
+                s_need = new_need;
+                if (bucket == new_need || ballot == 0) s_done = 1;   // bucket taken whole
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- collect the winners, sort them, write ----------------------------------------------------
+    const uint64_t prefix = s_prefix, mask = s_mask;
+    for (int t = tid; t < o.n_sort; t += blockDim.x) sel[t] = 0ull;
+    __syncthreads();
+    for (int64_t j = tid; j < M; j += blockDim.x) {
+        uint64_t key = src.key(row, j);
+        if (key != 0ull && (key & mask) >= prefix) {
+            uint32_t pos = atomicAdd(&s_cnt, 1u);
+            if (pos < uint32_t(o.n_sort)) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(sel, o.n_sort);
+    write_sorted(sel, row, o);
+}
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <class Src>
+static int launch_select(const Src& src, int n_rows, int k, int64_t idx_offset, const float* row_scale,
+                         float* out_vals, int64_t* out_idx, cudaStream_t stream) {
+    if (n_rows == 0) return ANNCUR_OK;
+    SelectOut o{out_vals, out_idx, idx_offset, row_scale, k, next_pow2(k < 2 ? 2 : k)};
+    size_t smem = sizeof(uint64_t) * size_t(o.n_sort > kSmemSortCap ? o.n_sort : kSmemSortCap);
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(select_topk_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(smem)));
+    select_topk_kernel<Src><<<n_rows, kSelectThreads, smem, stream>>>(src, o);
+    ANNCUR_LAUNCH_OK("select_topk_kernel");
+    return ANNCUR_OK;
+}
+
+int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, int k, int64_t idx_offset,
+                      float* out_vals, int64_t* out_idx, cudaStream_t stream) {
+    return launch_select(DenseRow{S, lds, n_cols}, n_rows, k, idx_offset, nullptr, out_vals, out_idx, stream);
+}
+
+int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
+                         int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
+                         cudaStream_t stream) {
+    return launch_select(KeyLists{keys, counts, n_lists, cap}, n_rows, k, idx_offset, row_scale, out_vals,
+                         out_idx, stream);
+}
+
+int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
+                      int64_t* out_idx, cudaStream_t stream) {
+    return launch_select(PairLists{vals, idx, n_cand}, n_rows, k, 0, nullptr, out_vals, out_idx, stream);
+}
+
+}  // namespace anncur

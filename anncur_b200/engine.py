@@ -1,0 +1,266 @@
+"""Torch-tensor front end of the C ABI: allocates outputs / workspaces as CUDA tensors, passes raw
+device pointers and the current CUDA stream, and returns CUDA tensors.  Everything here requires a
+CUDA device -- there is no CPU path (the CPU restatement lives in oracle/ and is test-only)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import KIND_BF16, KIND_F32X3, MAX_K, MAX_K_FUSED  # noqa: F401
+
+KINDS = {"f32x3": KIND_F32X3, "bf16": KIND_BF16}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("anncur_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32(t, device=None):
+    """fp32 CUDA tensor with unit stride in the last dimension (row stride may be anything)."""
+    require_cuda()
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    dev = device if device is not None else (t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    t = t.to(device=dev, dtype=torch.float32, non_blocking=True)
+    if t.dim() >= 1 and t.shape[-1] > 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    if t.dim() == 2 and t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if (t.dim() == 2 and t.shape[0] > 1) else max(t.shape[-1], 1)
+
+
+class _Workspace:
+    """Grow-only per-device scratch buffers keyed by purpose (caller-owned memory for the ABI)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device):
+        k = (key, device.index)
+        buf = self._bufs.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            self._bufs.pop(k, None)
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+WORKSPACE = _Workspace()
+
+
+def launch_count():
+    return int(_lib.load().anncur_kernel_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().anncur_reset_kernel_launch_count()
+
+
+# ---- K1 -------------------------------------------------------------------------------------------
+def pinv(A, rcond=1e-15, return_cond=False):
+    """pinv of an (m x n) fp32 matrix -> (n x m) fp32 on the GPU (eval/matrix_approx_zeshel.py:47,49)."""
+    lib = _lib.load()
+    A = _f32(A)
+    assert A.dim() == 2
+    m, n = A.shape
+    out = torch.empty((n, m), dtype=torch.float32, device=A.device)
+    cond = torch.zeros(2, dtype=torch.float64, device=A.device)
+    if m > 0 and n > 0:
+        nbytes = lib.anncur_pinv_workspace_bytes(m, n)
+        ws = WORKSPACE.get("pinv", nbytes, A.device)
+        with torch.cuda.device(A.device):
+            _lib.check(lib.anncur_pinv_f32(_ptr(A), m, n, _ld(A), float(rcond), _ptr(out), max(m, 1), _ptr(cond),
+                                           _ptr(ws), ws.numel(), _stream()))
+    return (out, cond) if return_cond else out
+
+
+# ---- K2 -------------------------------------------------------------------------------------------
+def gemm(A, B):
+    """A (m x k) @ B (k x n) in fp32 FFMA (eval/matrix_approx_zeshel.py:61,65,74,79,85,97,118)."""
+    lib = _lib.load()
+    A = _f32(A)
+    B = _f32(B, device=A.device)
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[0], (A.shape, B.shape)
+    m, k = A.shape
+    n = B.shape[1]
+    out = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    if m > 0 and n > 0:
+        with torch.cuda.device(A.device):
+            _lib.check(lib.anncur_gemm_f32(_ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(out), max(n, 1), m, n, k, _stream()))
+    return out
+
+
+# ---- packed item index ----------------------------------------------------------------------------
+class PackedItems:
+    """E = latent_cols (k_dim x N) in the TMA/tcgen05 streaming layout of one precision kind."""
+
+    def __init__(self, E, kind="f32x3"):
+        lib = _lib.load()
+        E = _f32(E)
+        assert E.dim() == 2
+        self.kind_name, self.kind = kind, KINDS[kind]
+        self.k_dim, self.n_items = int(E.shape[0]), int(E.shape[1])
+        self.device = E.device
+        nbytes = lib.anncur_packed_items_bytes(self.n_items, self.k_dim, self.kind)
+        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=E.device)
+        self.scale = torch.ones(1, dtype=torch.float32, device=E.device)
+        with torch.cuda.device(E.device):
+            _lib.check(lib.anncur_pack_items(_ptr(E), _ld(E), self.n_items, self.k_dim, self.kind, _ptr(self.buf),
+                                             _ptr(self.scale), _stream()))
+
+    @property
+    def nbytes(self):
+        return self.buf.numel()
+
+
+# ---- K3 + K4 --------------------------------------------------------------------------------------
+def score_topk(Q, packed, k, idx_offset=0, out=None):
+    """Fused tensor-core approximate score + top-k (eval/matrix_approx_zeshel.py:109-126)."""
+    lib = _lib.load()
+    Q = _f32(Q, device=packed.device)
+    assert Q.dim() == 2 and Q.shape[1] == packed.k_dim, (Q.shape, packed.k_dim)
+    B = int(Q.shape[0])
+    if out is None:
+        vals = torch.empty((B, k), dtype=torch.float32, device=Q.device)
+        idx = torch.empty((B, k), dtype=torch.int64, device=Q.device)
+    else:
+        vals, idx = out
+    if B > 0:
+        nbytes = lib.anncur_score_topk_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
+        ws = WORKSPACE.get("score_topk", nbytes, Q.device)
+        with torch.cuda.device(Q.device):
+            _lib.check(lib.anncur_score_topk(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), packed.n_items,
+                                             packed.k_dim, packed.kind, int(k), int(idx_offset), _ptr(vals), _ptr(idx),
+                                             _ptr(ws), ws.numel(), _stream()))
+    return vals, idx
+
+
+def score_topk_f32(Q, E, k, idx_offset=0):
+    """Plain-fp32 FFMA score + top-k on unpacked E (any k <= MAX_K)."""
+    lib = _lib.load()
+    Q = _f32(Q)
+    E = _f32(E, device=Q.device)
+    assert Q.dim() == 2 and E.dim() == 2 and Q.shape[1] == E.shape[0]
+    B, K = Q.shape
+    N = E.shape[1]
+    vals = torch.empty((B, k), dtype=torch.float32, device=Q.device)
+    idx = torch.empty((B, k), dtype=torch.int64, device=Q.device)
+    if B > 0:
+        nbytes = lib.anncur_score_topk_f32_workspace_bytes(B, N, K, k)
+        ws = WORKSPACE.get("score_topk_f32", nbytes, Q.device)
+        with torch.cuda.device(Q.device):
+            _lib.check(lib.anncur_score_topk_f32(_ptr(Q), _ld(Q), B, _ptr(E), _ld(E), N, K, int(k), int(idx_offset),
+                                                 _ptr(vals), _ptr(idx), _ptr(ws), ws.numel(), _stream()))
+    return vals, idx
+
+
+def topk_rows(S, k, idx_offset=0):
+    """torch.topk(S, k, dim=1) on the GPU, ties -> lower index."""
+    lib = _lib.load()
+    S = _f32(S)
+    assert S.dim() == 2
+    n, N = S.shape
+    vals = torch.empty((n, k), dtype=torch.float32, device=S.device)
+    idx = torch.empty((n, k), dtype=torch.int64, device=S.device)
+    if n > 0:
+        with torch.cuda.device(S.device):
+            _lib.check(lib.anncur_topk_rows_f32(_ptr(S), _ld(S), n, N, int(k), int(idx_offset), _ptr(vals), _ptr(idx),
+                                                _stream()))
+    return vals, idx
+
+
+def merge_topk(cand_vals, cand_idx, k):
+    """Best k of n_cand (val, idx) candidates per row; idx < 0 marks padding."""
+    lib = _lib.load()
+    cand_vals = _f32(cand_vals).contiguous()
+    cand_idx = cand_idx.to(device=cand_vals.device, dtype=torch.int64).contiguous()
+    assert cand_vals.shape == cand_idx.shape and cand_vals.dim() == 2
+    n, m = cand_vals.shape
+    vals = torch.empty((n, k), dtype=torch.float32, device=cand_vals.device)
+    idx = torch.empty((n, k), dtype=torch.int64, device=cand_vals.device)
+    if n > 0:
+        with torch.cuda.device(cand_vals.device):
+            _lib.check(lib.anncur_merge_topk(_ptr(cand_vals), _ptr(cand_idx), n, m, int(k), _ptr(vals), _ptr(idx), _stream()))
+    return vals, idx
+
+
+# ---- K5 + K6 --------------------------------------------------------------------------------------
+def rerank_overlap(exact, retr_idx, exact_idx, k_list):
+    """Exact-score rerank of retrieved items + |exact[:k] & reranked[:k]| for each k in k_list.
+    Returns (rr_idx [n x k_max], rr_vals [n x k_max], common [n x len(k_list)] int32)."""
+    lib = _lib.load()
+    exact = _f32(exact)
+    dev = exact.device
+    retr_idx = retr_idx.to(device=dev, dtype=torch.int64).contiguous()
+    exact_idx = exact_idx.to(device=dev, dtype=torch.int64).contiguous()
+    n, N = exact.shape
+    k_retr, k_max = int(retr_idx.shape[1]), int(exact_idx.shape[1])
+    k_list = [int(x) for x in k_list]
+    rr_idx = torch.empty((n, k_max), dtype=torch.int64, device=dev)
+    rr_vals = torch.empty((n, k_max), dtype=torch.float32, device=dev)
+    common = torch.empty((n, len(k_list)), dtype=torch.int32, device=dev)
+    if n > 0:
+        arr = (C.c_int * len(k_list))(*k_list)
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_rerank_overlap(_ptr(exact), _ld(exact), n, N, _ptr(retr_idx), k_retr, _ptr(exact_idx),
+                                                 k_max, arr, len(k_list), _ptr(rr_idx), _ptr(rr_vals), _ptr(common),
+                                                 _stream()))
+    return rr_idx, rr_vals, common
+
+
+# ---- K7 -------------------------------------------------------------------------------------------
+def recon_error_rows(Q, E, A):
+    """Per-row sum_j (Q.E - A)^2 and sum_j A^2 in fp64 without materialising Q.E."""
+    lib = _lib.load()
+    A = _f32(A)
+    Q = _f32(Q, device=A.device)
+    E = _f32(E, device=A.device)
+    n, N = A.shape
+    K = Q.shape[1]
+    assert Q.shape[0] == n and E.shape == (K, N)
+    err2 = torch.empty(n, dtype=torch.float64, device=A.device)
+    norm2 = torch.empty(n, dtype=torch.float64, device=A.device)
+    if n > 0:
+        with torch.cuda.device(A.device):
+            _lib.check(lib.anncur_recon_error_f32(_ptr(Q), _ld(Q), _ptr(E), _ld(E), _ptr(A), _ld(A), n, N, K,
+                                                  _ptr(err2), _ptr(norm2), _stream()))
+    return err2, norm2
+
+
+# ---- K8 -------------------------------------------------------------------------------------------
+def adaptive_round(R_anc, anchors, c, n_next, rcond=1e-15):
+    """One adaptive ANNCUR round (see include/anncur_b200.h).  Returns (next_idx, next_val)."""
+    lib = _lib.load()
+    R_anc = _f32(R_anc)
+    dev = R_anc.device
+    anchors = anchors.to(device=dev, dtype=torch.int64).contiguous()
+    c = _f32(c, device=dev).contiguous()
+    k_q, N = R_anc.shape
+    B, m = anchors.shape
+    next_idx = torch.empty((B, n_next), dtype=torch.int64, device=dev)
+    next_val = torch.empty((B, n_next), dtype=torch.float32, device=dev)
+    if B > 0:
+        nbytes = lib.anncur_adaptive_round_workspace_bytes(B, k_q, m, N, n_next)
+        ws = WORKSPACE.get("adaptive", nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_adaptive_round(_ptr(R_anc), _ld(R_anc), k_q, N, _ptr(anchors), _ptr(c), B, m,
+                                                 float(rcond), int(n_next), _ptr(next_idx), _ptr(next_val), _ptr(ws),
+                                                 ws.numel(), _stream()))
+    return next_idx, next_val

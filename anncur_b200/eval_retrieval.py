@@ -1,0 +1,183 @@
+"""Drop-ins for the per-query retrieve / rerank / overlap evaluation of the reference:
+
+* ``compute_overlap``                        eval/eval_utils.py:115-150
+* ``run_approx_eval_w_seed``                 eval/run_retrieval_eval_wrt_exact_crossenc.py:47-158
+* ``eval_approx_score_mat_for_all_topk``     ..._w_fixed_train_test_splits.py:51-135
+* ``eval_approx_score_mat``                  ..._w_fixed_train_test_splits.py:138-206
+* ``_get_indices_scores``                    ..._w_fixed_train_test_splits.py:34-47
+
+Same signatures, same result keys (``exact_vs_reranked_approx_retvr~<metric>_<stat>``, values rounded
+to 4 decimals exactly as the reference's format-then-parse does).  The Python per-row loop with three
+``topk`` calls and an N-long temporary per query becomes three batched kernels: exact row top-k,
+approximate row top-k (or the fused score+top-k when an index is given), and rerank+overlap.
+"""
+import numpy as np
+import torch
+
+from . import engine
+from .matrix_approx import CURApprox
+
+METRICS = ("common", "diff", "total", "common_frac", "diff_frac")
+PREFIX = "exact_vs_reranked_approx_retvr"
+
+
+def _get_indices_scores(topk_preds):
+    indices, scores = zip(*topk_preds)
+    if torch.is_tensor(indices[0]):
+        indices, scores = torch.cat(indices), torch.cat(scores)
+        return {"indices": indices.cpu().numpy(), "scores": scores.cpu().numpy()}
+    return {"indices": np.concatenate(indices), "scores": np.concatenate(scores)}
+
+
+def _stats_strings(common, k):
+    """Reference formatting (eval/eval_utils.py:131-136) from per-row intersection counts."""
+    common = np.asarray(common, dtype=np.float64)
+    if common.size == 0:
+        return {m: ("mean 0.0", "std 0.0", "p50 0.0") for m in METRICS}
+    per_metric = {"common": common, "diff": k - common, "total": np.full_like(common, k),
+                  "common_frac": common / k, "diff_frac": (k - common) / k}
+    return {m: ("mean {:.4f}".format(np.mean(v)), "std {:.4f}".format(np.std(v)),
+                "p50 {:.4f}".format(np.percentile(v, 50))) for m, v in per_metric.items()}
+
+
+def _flatten(strings):
+    out = {}
+    for m, (mean, std, p50) in strings.items():
+        out[f"{PREFIX}~{m}_mean"] = float(mean[5:])
+        out[f"{PREFIX}~{m}_std"] = float(std[4:])
+        out[f"{PREFIX}~{m}_p50"] = float(p50[4:])
+    return out
+
+
+def compute_overlap(indices_list1, indices_list2):
+    """|set(a) & set(b)| per row pair and the reference's mean/std/p50 strings."""
+    n = len(indices_list1)
+    if n == 0 or len(indices_list2) == 0:
+        return {m: ("mean 0.0", "std 0.0", "p50 0.0") for m in METRICS}
+    engine.require_cuda()
+    a = torch.as_tensor(np.asarray(indices_list1)).cuda()
+    b = torch.as_tensor(np.asarray(indices_list2)).cuda()
+    assert a.shape == b.shape, f"Len of both indices is not same => {a.shape[-1]} != {b.shape[-1]}"
+    k = a.shape[1]
+    # membership of each a[i, j] in row b[i]: sort b, binary search (unique indices per row assumed, as top-k lists are)
+    bs, _ = torch.sort(b, dim=1)
+    pos = torch.searchsorted(bs, a.contiguous()).clamp_(max=k - 1)
+    common = (torch.gather(bs, 1, pos) == a).sum(dim=1)
+    return _stats_strings(common.cpu().numpy(), k)
+
+
+def retrieve_rerank_overlap(all_scores, approx_scores, k_list, top_k_retvr, *, approx_topk=None):
+    """Batched body of the reference's per-query loop.  Returns dict with exact / approx / reranked
+    (indices, scores) CUDA tensors and ``common`` [n x len(k_list)] intersection counts.
+    ``approx_topk``: optional precomputed (vals, idx) of the approximate top-k_retvr (fused path)."""
+    exact = engine._f32(all_scores)
+    k_max = max(k_list)
+    ex_v, ex_i = engine.topk_rows(exact, k_max)
+    if approx_topk is None:
+        ap_v, ap_i = engine.topk_rows(engine._f32(approx_scores, device=exact.device), top_k_retvr)
+    else:
+        ap_v, ap_i = approx_topk
+    rr_i, rr_v, common = engine.rerank_overlap(exact, ap_i, ex_i, k_list)
+    return {"exact": (ex_i, ex_v), "approx": (ap_i, ap_v), "reranked": (rr_i, rr_v), "common": common}
+
+
+def eval_approx_score_mat_for_all_topk(all_ment_to_ent_scores, approx_ment_to_ent_scores, arg_top_k_vals, top_k_retvr,
+                                       *, approx_topk=None):
+    top_k_vals = [int(k) for k in arg_top_k_vals if k <= top_k_retvr]
+    if len(top_k_vals) == 0:
+        return {}
+    res = retrieve_rerank_overlap(all_ment_to_ent_scores, approx_ment_to_ent_scores, top_k_vals, int(top_k_retvr),
+                                  approx_topk=approx_topk)
+    common = res["common"].cpu().numpy()
+    return {k: _flatten(_stats_strings(common[:, j], k)) for j, k in enumerate(top_k_vals)}
+
+
+def eval_approx_score_mat(all_ment_to_ent_scores, approx_ment_to_ent_scores, top_k, top_k_retvr, *, approx_topk=None):
+    res = retrieve_rerank_overlap(all_ment_to_ent_scores, approx_ment_to_ent_scores, [int(top_k)], int(top_k_retvr),
+                                  approx_topk=approx_topk)
+    return _flatten(_stats_strings(res["common"].cpu().numpy()[:, 0], int(top_k)))
+
+
+def run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors, n_ent_anchors, top_k, top_k_retvr,
+                           seed, precomp_approx_ment_to_ent_scores=None, *, precision="f32x3"):
+    engine.require_cuda()
+    A = engine._f32(all_ment_to_ent_scores)
+    n_ments, n_ents = A.shape
+    rng = np.random.default_rng(seed=seed)                                       # reference :65-70
+    anchor_ment_idxs = sorted(rng.choice(n_ments, size=n_ment_anchors, replace=False))
+    anchor_ent_idxs = sorted(rng.choice(n_ents, size=n_ent_anchors, replace=False))
+    rows = A[torch.as_tensor(np.asarray(anchor_ment_idxs, dtype=np.int64), device=A.device), :]
+    cols = A[:, torch.as_tensor(np.asarray(anchor_ent_idxs, dtype=np.int64), device=A.device)]
+    non_anchor_ment_idxs = sorted(set(range(n_ments)) - set(anchor_ment_idxs))
+
+    approx_topk = None
+    err2 = norm2 = None
+    if approx_method in ["bienc", "fixed_anc_ent"] or approx_method.startswith("fixed_anc_ent_cur_"):
+        approx = engine._f32(precomp_approx_ment_to_ent_scores, device=A.device)
+    elif approx_method in ("cur", "cur_oracle"):
+        cur = CURApprox(row_idxs=anchor_ment_idxs, col_idxs=anchor_ent_idxs, rows=rows, cols=cols,
+                        approx_preference="rows", A=(A if approx_method == "cur_oracle" else None), precision=precision)
+        approx = None
+        # retrieval straight from the index: scores for all rows never leave the tensor core epilogue
+        if top_k_retvr <= engine.MAX_K_FUSED and precision != "f32":
+            v, i = engine.score_topk(cur._latent_rows_dev, cur.packed_items(), int(top_k_retvr))
+        else:
+            v, i = engine.score_topk_f32(cur._latent_rows_dev, cur._latent_cols_dev, int(top_k_retvr))
+        approx_topk = (v, i)
+        err2, norm2 = engine.recon_error_rows(cur._latent_rows_dev, cur._latent_cols_dev, A)
+    else:
+        raise NotImplementedError(f"approx_method = {approx_method} not supported")
+
+    res = retrieve_rerank_overlap(A, approx, [int(top_k)], int(top_k_retvr), approx_topk=approx_topk)
+    common = res["common"].cpu().numpy()[:, 0]
+    if err2 is None:
+        diff = approx - A
+        err2 = (diff.double() ** 2).sum(dim=1)
+        norm2 = (A.double() ** 2).sum(dim=1)
+    err2, norm2 = err2.cpu().numpy(), norm2.cpu().numpy()
+
+    def score(idxs):
+        idxs = np.asarray(idxs, dtype=np.int64)
+        out = _flatten(_stats_strings(common[idxs], int(top_k)))
+        e = float(np.sqrt(err2[idxs].sum()))
+        out["approx_error"] = e                                                   # reference :146
+        nrm = float(np.sqrt(norm2[idxs].sum()))
+        out["approx_error_relative"] = e / nrm if nrm > 0 else float("nan")      # reference :147
+        return out
+
+    return {"anchor": score(anchor_ment_idxs), "non_anchor": score(non_anchor_ment_idxs),
+            "all": score(list(range(n_ments)))}
+
+
+def fixed_split_cur_eval(train_scores, test_scores, n_ent_anchors_vals, top_k_vals, top_k_retvr_vals, seed,
+                         *, precision="f32x3"):
+    """The ``cur`` method of run_eval_method (..._w_fixed_train_test_splits.py:286-303 + :403-429) end to end on
+    the GPU: ONE numpy Generator replayed across the k_i grid, every training row an anchor query, and for each
+    (k_r, k_i) the all-top-k evaluation.  Returns {f"top_k={k}": {f"k_retvr={k_r}": {f"anc_n_e={k_i}": metrics}}}
+    restricted to the combinations the reference evaluates (k <= k_r, k_r <= N)."""
+    engine.require_cuda()
+    train = engine._f32(train_scores)
+    test = engine._f32(test_scores, device=train.device)
+    n_train, n_ents = train.shape
+    rng = np.random.default_rng(seed=seed)
+    out = {}
+    max_kr = max([kr for kr in top_k_retvr_vals if kr <= n_ents] + [0])
+    for k_i in n_ent_anchors_vals:
+        anc = sorted(rng.choice(n_ents, size=k_i, replace=False))
+        anc_t = torch.as_tensor(np.asarray(anc, dtype=np.int64), device=train.device)
+        cur = CURApprox(row_idxs=np.arange(n_train), col_idxs=anc, rows=train, cols=train[:, anc_t],
+                        approx_preference="rows", precision=precision)
+        if max_kr == 0:
+            continue
+        # one retrieval at the largest k_r: every smaller k_r list is a prefix of it
+        Q = test[:, anc_t]
+        if k_i == 0:
+            continue
+        v, i = cur.topk_in_row(Q, max_kr)
+        for k_r in top_k_retvr_vals:
+            if k_r > n_ents or k_r == 0:
+                continue
+            res = eval_approx_score_mat_for_all_topk(test, None, top_k_vals, k_r, approx_topk=(v[:, :k_r].contiguous(), i[:, :k_r].contiguous()))
+            for k, metrics in res.items():
+                out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_e={k_i}"] = metrics
+    return out

@@ -1,0 +1,174 @@
+"""Drop-in for the reference's ``eval/matrix_approx_zeshel.py::CURApprox`` (:19-126) on the B200 engine.
+
+Same constructor, attributes and methods; tensors may be CPU (as the reference passes them) or CUDA.
+Results come back on the device the inputs lived on, so the reference's eval scripts run unchanged.
+All arithmetic runs in libanncur_b200.so; there is no CPU code path here.
+
+Differences a caller can observe, all deliberate:
+* the reference's ``assert torch.eq(C[rows], R[:, cols])`` (:44) raises for any real input unless
+  Python runs with -O; here the intended check (``torch.equal``) is performed under ``check=True``
+  (off by default to match what the reference actually executes);
+* ``topk_in_row`` never materialises the (B x N) score matrix (fused tcgen05 GEMM + streaming top-k);
+  ties are broken towards the lower item index (torch.topk leaves tie order unspecified);
+* pinv is computed by an fp64 Jacobi SVD (numpy uses fp32 LAPACK), so U / latent_cols agree with the
+  reference to ~cond * eps_fp32, not bit-for-bit.
+"""
+import numpy as np
+import torch
+
+from . import engine
+
+
+def _as_index_tensor(idx, device):
+    if torch.is_tensor(idx):
+        return idx.to(device=device, dtype=torch.int64)
+    return torch.as_tensor(np.asarray(idx, dtype=np.int64), device=device)
+
+
+class CURApprox(object):
+    """M (n x m) ~= C . U . R with C (n x k_c) anchor-item columns, R (k_r x m) anchor-query rows."""
+
+    def __init__(self, rows, cols, row_idxs, col_idxs, approx_preference, A=None, *, precision="f32x3",
+                 check=False, rcond=1e-15, device=None):
+        engine.require_cuda()
+        rows = torch.as_tensor(rows)
+        cols = torch.as_tensor(cols)
+        self._home = rows.device                       # results are returned where the inputs live
+        self._dev = torch.device(device) if device is not None else (
+            rows.device if rows.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        self.n = cols.shape[0]
+        self.m = rows.shape[1]
+        self.row_idxs = row_idxs
+        self.col_idxs = col_idxs
+        self.C = cols
+        self.R = rows
+        self.approx_preference = approx_preference
+        self.precision = precision
+        self.rcond = rcond
+
+        assert self._is_sorted(self.row_idxs), "row_idxs should be sorted"
+        assert self._is_sorted(self.col_idxs), "col_idxs should be sorted"
+        assert len(row_idxs) == self.R.shape[0]
+        assert len(col_idxs) == self.C.shape[1]
+        if approx_preference not in ("rows", "cols"):
+            raise NotImplementedError(f"approx_preference = {approx_preference} not supported")
+
+        self._R_dev = rows.to(self._dev, torch.float32)
+        self._C_dev = cols.to(self._dev, torch.float32)
+        ridx = _as_index_tensor(row_idxs, self._dev)
+        intersect = self._C_dev.index_select(0, ridx) if len(row_idxs) else self._C_dev[:0]   # k_r x k_c
+        if check:
+            cidx = _as_index_tensor(col_idxs, self._dev)
+            if not torch.equal(intersect, self._R_dev.index_select(1, cidx)):
+                raise AssertionError("Invalid rows and cols as their intersection does not match")
+
+        if A is not None:   # cur_oracle: U = pinv(C) . A . pinv(R)   (reference :46-47)
+            A_dev = torch.as_tensor(A).to(self._dev, torch.float32)
+            U = engine.gemm(engine.gemm(engine.pinv(self._C_dev, rcond), A_dev), engine.pinv(self._R_dev, rcond))
+            self._cond = None
+        else:               # U = pinv(C[row_idxs, :])                (reference :49)
+            U, cond = engine.pinv(intersect, rcond, return_cond=True)
+            self._cond = cond
+        self._U_dev = U                                                      # k_c x k_r
+        if approx_preference == "cols":                                      # reference :60-62
+            self._latent_rows_dev = engine.gemm(self._C_dev, U)              # n x k_r
+            self._latent_cols_dev = self._R_dev                              # k_r x m
+        else:                                                                # reference :63-65
+            self._latent_rows_dev = self._C_dev                              # n x k_c
+            self._latent_cols_dev = engine.gemm(U, self._R_dev)              # k_c x m   == E
+        self._packed = {}
+        self._home_cache = {}
+
+    # -- attributes the reference exposes (lazily copied to the caller's device) ------------------
+    def _to_home(self, name, t):
+        if t.device == self._home:
+            return t
+        if name not in self._home_cache:
+            self._home_cache[name] = t.to(self._home)
+        return self._home_cache[name]
+
+    @property
+    def U(self):
+        return self._to_home("U", self._U_dev)
+
+    @property
+    def latent_rows(self):
+        return self._to_home("latent_rows", self._latent_rows_dev)
+
+    @property
+    def latent_cols(self):
+        return self._to_home("latent_cols", self._latent_cols_dev)
+
+    @property
+    def intersect_cond(self):
+        """s_max / s_min_kept of the inverted intersection (None for the cur_oracle construction)."""
+        if self._cond is None:
+            return None
+        s_max, s_min = self._cond.tolist()
+        return float("inf") if s_min == 0 else s_max / s_min
+
+    @staticmethod
+    def _is_sorted(idx_list):
+        return all(i < j for i, j in zip(idx_list[:-1], idx_list[1:]))
+
+    def _out(self, t):
+        return t if t.device == self._home else t.to(self._home)
+
+    # -- dense getters (reference :71-86) ----------------------------------------------------------
+    def get_rows(self, row_idxs):
+        r = _as_index_tensor(row_idxs, self._dev)
+        return self._out(engine.gemm(self._latent_rows_dev.index_select(0, r), self._latent_cols_dev))
+
+    def get_cols(self, col_idxs):
+        c = _as_index_tensor(col_idxs, self._dev)
+        return self._out(engine.gemm(self._latent_rows_dev, self._latent_cols_dev.index_select(1, c)))
+
+    def get(self, row_idxs, col_idxs):
+        r = _as_index_tensor(row_idxs, self._dev)
+        c = _as_index_tensor(col_idxs, self._dev)
+        lc = self._latent_cols_dev
+        if not (c.numel() == lc.shape[1] and bool((c == torch.arange(lc.shape[1], device=c.device)).all())):
+            lc = lc.index_select(1, c)
+        return self._out(engine.gemm(self._latent_rows_dev.index_select(0, r), lc))
+
+    # -- column side (reference :88-106) ------------------------------------------------------------
+    def get_complete_col(self, sparse_cols):
+        if self.approx_preference != "cols":
+            raise NotImplementedError("This is not designed to give good approx of cols as U matrix is multiplied w/ R matrix. Build index w/ approx_preference = cols instead.")
+        return self._out(engine.gemm(self._latent_rows_dev, torch.as_tensor(sparse_cols).to(self._dev, torch.float32)))
+
+    def topk_in_col(self, sparse_cols, k):
+        if self.approx_preference != "cols":
+            raise NotImplementedError("This is not designed to give good approx of cols as U matrix is multiplied w/ R matrix. Build index w/ approx_preference = cols instead.")
+        dense = engine.gemm(self._latent_rows_dev, torch.as_tensor(sparse_cols).to(self._dev, torch.float32))
+        if k > dense.shape[1]:
+            raise RuntimeError("selected index k out of range")
+        v, i = engine.topk_rows(dense, k)
+        return torch.return_types.topk((self._out(v), self._out(i)))
+
+    # -- row side = the hot path (reference :109-126) -----------------------------------------------
+    def get_complete_row(self, sparse_rows):
+        if self.approx_preference != "rows":
+            raise NotImplementedError("This is not designed to give good approx of rows as C and U matrix are multiplied together. Build index w/ approx_preference = rows instead.")
+        return self._out(engine.gemm(torch.as_tensor(sparse_rows).to(self._dev, torch.float32), self._latent_cols_dev))
+
+    def packed_items(self, precision=None):
+        """The item-embedding matrix in the tensor-core streaming layout (built once per precision)."""
+        precision = precision or self.precision
+        if precision not in self._packed:
+            self._packed[precision] = engine.PackedItems(self._latent_cols_dev, precision)
+        return self._packed[precision]
+
+    def topk_in_row(self, sparse_rows, k, precision=None):
+        if self.approx_preference != "rows":
+            raise NotImplementedError("This is not designed to give good approx of rows as C and U matrix are multiplied together. Build index w/ approx_preference = rows instead.")
+        precision = precision or self.precision
+        Q = torch.as_tensor(sparse_rows).to(self._dev, torch.float32)
+        N = self._latent_cols_dev.shape[1]
+        if k > N:
+            raise RuntimeError("selected index k out of range")       # what torch.topk raises
+        if precision == "f32" or k > engine.MAX_K_FUSED:
+            v, i = engine.score_topk_f32(Q, self._latent_cols_dev, k)
+        else:
+            v, i = engine.score_topk(Q, self.packed_items(precision), k)
+        return torch.return_types.topk((self._out(v), self._out(i)))

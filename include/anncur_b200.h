@@ -1,0 +1,165 @@
+/*
+ * anncur_b200.h -- C ABI of libanncur_b200.so: the B200 (sm_100a) engine behind the ANNCUR
+ * test-time search path of iesl/anncur.
+ *
+ * The reference has no FFI of its own: its boundary is the Python call surface of
+ *   eval/matrix_approx_zeshel.py   (class CURApprox, :19-126)
+ *   models/nearest_nbr.py          (build_flat_or_ivff_index(...).search, :24-55)
+ *   eval/run_retrieval_eval_wrt_exact_crossenc*.py (per-query retrieve/rerank/overlap loops)
+ * Each entry point below names the reference lines whose arithmetic it replaces.  The host-side
+ * mirror of those Python surfaces lives in anncur_b200/*.py and binds this ABI with ctypes
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; all matrices are row-major,
+ *    dense unless a leading dimension (ld*, in elements) is given;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *    never synchronises the device;
+ *  - the library never allocates device memory: scratch comes from the caller, sized by the
+ *    matching *_workspace_bytes() query (workspaces must be 256-byte aligned);
+ *  - return value 0 = success, negative = ANNCUR_E_* ; anncur_last_error() returns a thread-local
+ *    message for the last failure on this host thread;
+ *  - top-k results are best-first; ties are broken towards the LOWER item index; indices are
+ *    int64 like torch.topk / faiss; unused slots (k larger than the candidate set) hold
+ *    idx = -1, val = -FLT_MAX (faiss' inner-product padding).
+ */
+#ifndef ANNCUR_B200_H_
+#define ANNCUR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ANNCUR_API __attribute__((visibility("default")))
+#else
+#define ANNCUR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANNCUR_ABI_VERSION 1
+
+#define ANNCUR_OK            0
+#define ANNCUR_E_INVALID    -1  /* bad argument (shape, k, null pointer, alignment)            */
+#define ANNCUR_E_WORKSPACE  -2  /* workspace too small                                          */
+#define ANNCUR_E_CUDA       -3  /* a CUDA runtime / driver call failed (message has the code)   */
+#define ANNCUR_E_UNSUPPORTED -4 /* shape outside what this kernel family handles                */
+
+/* precision of the fused score + top-k tensor-core path */
+#define ANNCUR_KIND_F32X3 0  /* fp32-grade: operands split into two fp16 terms, 3 tcgen05 passes */
+#define ANNCUR_KIND_BF16  1  /* single bf16 pass (reported separately as recall@k)             */
+
+#define ANNCUR_MAX_K        2048  /* largest k of any top-k entry point                         */
+#define ANNCUR_MAX_K_FUSED  1024  /* largest k of the fused tensor-core path                    */
+
+ANNCUR_API int         anncur_abi_version(void);
+ANNCUR_API const char* anncur_last_error(void);
+
+/* ---- K1: pseudo-inverse -------------------------------------------------------------------
+ * Replaces np.linalg.pinv at eval/matrix_approx_zeshel.py:47,49 (U = pinv(C[row_idxs,:])).
+ * A is m x n fp32 (lda), out is n x m fp32 (ldo).  One-sided Jacobi SVD in fp64; singular values
+ * <= rcond * s_max are dropped (numpy's rule; the reference uses numpy's default rcond = 1e-15).
+ * cond_out (optional, device double[2]) receives {s_max, s_min_kept}. */
+ANNCUR_API size_t anncur_pinv_workspace_bytes(int m, int n);
+ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo,
+                    double* cond_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2 / dense products -------------------------------------------------------------------
+ * C[m x n] = A[m x k] . B[k x n], fp32 FFMA accumulate.  Replaces `U @ R`
+ * (eval/matrix_approx_zeshel.py:65), `C @ U` (:61) and the dense getters get_rows/get_cols/get/
+ * get_complete_row/get_complete_col (:71-119) when the caller wants the full matrix. */
+ANNCUR_API int anncur_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                    int m, int n, int k, void* stream);
+
+/* ---- item-embedding index for the tensor-core path ------------------------------------------
+ * Packs E = latent_cols (k_i x N fp32, row-major, N contiguous as the reference stores it,
+ * eval/matrix_approx_zeshel.py:65) into the k-block-major fp16-pair / bf16 planes the fused
+ * kernel streams with TMA.  `packed` must hold anncur_packed_items_bytes().  e_scale_out
+ * (device float[1]) receives the power-of-two scale applied before the fp16 split. */
+ANNCUR_API size_t anncur_packed_items_bytes(int64_t n_items, int k_dim, int kind);
+ANNCUR_API int anncur_pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind,
+                      void* packed, float* e_scale_out, void* stream);
+
+/* ---- K3+K4: fused approximate score + per-row top-k -----------------------------------------
+ * Replaces CURApprox.topk_in_row = torch.topk(sparse_rows @ latent_cols, k, dim=1)
+ * (eval/matrix_approx_zeshel.py:109-126) and IndexFlatIP.search (models/nearest_nbr.py:36-38):
+ * the B x N score matrix is never written.  Q is B x k_dim fp32 (ldq).  out_idx = local item
+ * index + idx_offset (the shard's first global item).  Requires 1 <= k <=
+ * ANNCUR_MAX_K_FUSED. */
+ANNCUR_API size_t anncur_score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind);
+ANNCUR_API int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed_items,
+                      const float* e_scale, int64_t n_items, int k_dim, int kind, int k,
+                      int64_t idx_offset, float* out_vals, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same contract on plain fp32 E (k_dim x N, lde) with FFMA arithmetic: scores are materialised
+ * in row blocks inside the workspace and reduced by the row top-k below.  Any k <= ANNCUR_MAX_K. */
+ANNCUR_API size_t anncur_score_topk_f32_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k);
+ANNCUR_API int anncur_score_topk_f32(const float* Q, int ldq, int n_queries, const float* E, int64_t lde,
+                          int64_t n_items, int k_dim, int k, int64_t idx_offset,
+                          float* out_vals, int64_t* out_idx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- row top-k over dense scores -------------------------------------------------------------
+ * torch.topk(row, k) for every row of S (n_rows x n_cols fp32, lds): the exact-score top-k of
+ * the eval loops (eval/run_retrieval_eval_wrt_exact_crossenc.py:103,
+ * ..._w_fixed_train_test_splits.py:86). */
+ANNCUR_API int anncur_topk_rows_f32(const float* S, int64_t lds, int n_rows, int64_t n_cols, int k,
+                         int64_t idx_offset, float* out_vals, int64_t* out_idx, void* stream);
+
+/* ---- K9: merge of per-shard candidate lists ---------------------------------------------------
+ * cand_vals/cand_idx: n_rows x n_cand (row-major; e.g. the all-gathered [P x k] lists laid out
+ * per row).  Entries with idx < 0 are padding.  Output: best k per row. */
+ANNCUR_API int anncur_merge_topk(const float* cand_vals, const int64_t* cand_idx, int n_rows, int n_cand,
+                      int k, float* out_vals, int64_t* out_idx, void* stream);
+
+/* ---- K5+K6: rerank the retrieved items by exact score, then overlap with the exact top-k -----
+ * Replaces the per-query loop body at eval/run_retrieval_eval_wrt_exact_crossenc.py:108-113 /
+ * ..._w_fixed_train_test_splits.py:91-96 (temp = -1e14; temp[idx] = exact[idx]; temp.topk) and
+ * _compute_overlap_helper (eval/eval_utils.py:139-150).
+ *   exact      n_rows x n_cols fp32 (lds)            exact CE scores
+ *   retr_idx   n_rows x k_retr int64                 approx top-k_retr (item indices)
+ *   exact_idx  n_rows x k_max  int64                 exact top-k_max (best first)
+ *   k_list     n_k ints (host), each <= k_max <= k_retr
+ *   out_rr_idx/out_rr_vals  n_rows x k_max           reranked lists
+ *   out_common n_rows x n_k int32                    |exact[:k] & reranked[:k]| per row and k   */
+ANNCUR_API int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols,
+                          const int64_t* retr_idx, int k_retr, const int64_t* exact_idx, int k_max,
+                          const int* k_list_host, int n_k, int64_t* out_rr_idx, float* out_rr_vals,
+                          int32_t* out_common, void* stream);
+
+/* ---- K7: reconstruction error without materialising the approximation -------------------------
+ * Replaces torch.norm((approx - A)[rows,:]) and torch.norm(A[rows,:])
+ * (eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147): per row r of Q (n x k_dim) and
+ * A (n x N): out_err2[r] = sum_j (Q[r,:].E[:,j] - A[r,j])^2, out_norm2[r] = sum_j A[r,j]^2, fp64.
+ * The caller sums rows over its subsets (anchor / non-anchor / all) and takes square roots. */
+ANNCUR_API int anncur_recon_error_f32(const float* Q, int ldq, const float* E, int64_t lde, const float* A,
+                           int64_t lda, int n_rows, int64_t n_items, int k_dim,
+                           double* out_err2, double* out_norm2, void* stream);
+
+/* ---- K8: adaptive multi-round ANNCUR (not in the reference) --------------
+ * One round for a batch of queries that all hold m anchors:
+ *   M_b = R_anc[:, anchors[b,:]] (k_q x m);  e_b = c_b . pinv(M_b);  s_b = e_b . R_anc with the
+ *   anchors masked;  next[b,:] = top-n_next(s_b).
+ * solved through the regularisation-free normal equations in fp64 (Cholesky with diagonal
+ * pivot guard; rank-deficient systems fall back to the min-norm rule of pinv by dropping
+ * pivots <= rcond * max pivot).
+ *   R_anc    k_q x N fp32 (ldr)        anchors  B x m int64        c  B x m fp32 (exact scores)
+ *   next_idx B x n_next int64          next_val B x n_next fp32    (approx scores of the picks) */
+ANNCUR_API size_t anncur_adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next);
+ANNCUR_API int anncur_adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items,
+                          const int64_t* anchors, const float* c, int n_queries, int m,
+                          double rcond, int n_next, int64_t* next_idx, float* next_val,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection used by bench.py ("gpu_launches") ------------------------------------------
+ * Number of kernels this library has launched on the calling host thread since the last reset. */
+ANNCUR_API uint64_t anncur_kernel_launch_count(void);
+ANNCUR_API void     anncur_reset_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANNCUR_B200_H_ */

@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports exactly what include/anncur_b200.h declares."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from anncur_b200.csrc import build
+    build.build()
+    from anncur_b200 import _lib
+    return _lib.load()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "anncur_b200.h")).read()
+    return sorted(set(re.findall(r"ANNCUR_API[^;(]*?\b(anncur_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from anncur_b200 import _lib
+    declared = _declared()
+    assert len(declared) >= 19
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (anncur_[a-z0-9_]+)", out)))
+    assert exported == declared
+    assert sorted(_lib.PROTOTYPES) == declared          # the ctypes binding covers the whole header
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_abi_version_and_size_queries(lib):
+    assert lib.anncur_abi_version() == 1
+    # host-only queries (no device work)
+    assert lib.anncur_pinv_workspace_bytes(2000, 500) >= 8 * (2000 * 500 + 500 * 500 + 500)
+    assert lib.anncur_packed_items_bytes(100000, 500, 0) >= 2 * 16 * 100000 * 64
+    assert lib.anncur_packed_items_bytes(100000, 500, 1) >= 16 * 100000 * 64
+    assert lib.anncur_packed_items_bytes(0, 500, 0) == 256
+
+
+def test_argument_errors_are_reported_without_a_gpu(lib):
+    from anncur_b200 import _lib
+    rc = lib.anncur_merge_topk(None, None, 4, 8, 0, None, None, None)
+    assert rc == _lib.E_INVALID and b"k = 0" in lib.anncur_last_error()
+    rc = lib.anncur_topk_rows_f32(None, 0, 3, 10, 5000, 0, None, None, None)
+    assert rc == _lib.E_INVALID
+    assert lib.anncur_gemm_f32(None, 0, None, 0, None, 0, 0, 5, 3, None) == 0      # empty problem is a no-op
+
+
+def test_built_for_sm100a_with_tcgen05_and_tma():
+    from anncur_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):          # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnemonic in sass, mnemonic
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "anncur_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f

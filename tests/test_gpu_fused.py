@@ -1,0 +1,136 @@
+"""GPU parity of the fused tcgen05 score + top-k kernel (anncur_score_topk) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cur_oracle as O
+from tests.parity import assert_scores_close, assert_sorted_desc, assert_topk_sets_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from anncur_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32) * np.float32(scale))
+
+
+def _check(eng, Q, E, k, kind="f32x3", rel=1e-4, offset=0):
+    packed = eng.PackedItems(E.cuda(), kind)
+    v, i = eng.score_topk(Q.cuda(), packed, k, idx_offset=offset)
+    torch.cuda.synchronize()
+    v, i = v.cpu().numpy(), i.cpu().numpy() - offset
+    dense = (Q.double() @ E.double()).numpy()
+    ref = O.score_topk(Q, E, min(k, E.shape[1]))
+    kk = ref.indices.shape[1]
+    assert_topk_sets_match(i[:, :kk], ref.indices.numpy(), full_scores=dense, rel=rel)
+    assert_scores_close(v[:, :kk], np.take_along_axis(dense, i[:, :kk], 1), rel=rel, what="scores of returned items")
+    assert_sorted_desc(v[:, :kk])
+    if k > kk:
+        assert (i[:, kk:] == -1 - offset).all()
+    return v, i
+
+
+@pytest.mark.parametrize("B,K,N,k", [
+    (128, 32, 256, 10),         # exactly one tile, one k-block
+    (1, 50, 10000, 100),        # single query (HBM-bound regime), ragged K
+    (7, 500, 3000, 100),        # ragged everything
+    (130, 64, 777, 64),         # two query tiles, last one nearly empty; N tail inside a tile
+    (300, 200, 20000, 1),       # k = 1
+    (64, 500, 50000, 100),
+    (256, 96, 4096, 128),       # k at a capacity boundary (cap 256)
+    (33, 40, 9000, 129),        # cap 512
+    (20, 128, 30000, 500),      # cap 1024
+    (12, 64, 20000, 1000),      # cap 2048 (k_r = 1000 is the reference's largest retrieval size)
+])
+def test_fused_f32x3_matches_oracle(eng, B, K, N, k):
+    _check(eng, _rand((B, K), B + K), _rand((K, N), N + k), k)
+
+
+def test_fused_k_larger_than_items_pads(eng):
+    _check(eng, _rand((5, 16), 1), _rand((16, 40), 2), 64)
+
+
+def test_fused_index_offset_is_int64(eng):
+    _check(eng, _rand((3, 16), 1), _rand((16, 500), 2), 5, offset=2**40)
+
+
+def test_fused_scale_extremes(eng):
+    # CE-logit scale (+-15), tiny and huge magnitudes, and a mixed-magnitude batch (per-row query scale)
+    for qs, es in [(15.0, 15.0), (1e-6, 1e-3), (3e4, 2e3)]:
+        _check(eng, _rand((40, 100), 3, qs), _rand((100, 6000), 4, es), 50)
+    Q = _rand((64, 100), 5)
+    Q *= torch.logspace(-6, 6, 64).unsqueeze(1)
+    _check(eng, Q, _rand((100, 6000), 6), 50)
+
+
+def test_fused_adversarial_ascending_scores(eng):
+    # scores increase with the item index: every element beats the running threshold (worst case for the
+    # survivor lists, exercises repeated compaction); and all-equal scores: pure index tie-break
+    K, N = 32, 20000
+    E = torch.zeros(K, N)
+    E[0] = torch.arange(N, dtype=torch.float32) / N
+    Q = torch.zeros(70, K)
+    Q[:, 0] = torch.linspace(0.5, 2.0, 70)
+    v, i = _check(eng, Q, E, 100)
+    assert (i == np.arange(N - 1, N - 101, -1)[None, :]).all()
+    packed = eng.PackedItems(torch.ones(K, N).cuda(), "f32x3")
+    v, i = eng.score_topk(torch.ones(3, K).cuda(), packed, 10)
+    assert (i.cpu().numpy() == np.arange(10)[None, :]).all() and np.allclose(v.cpu().numpy(), K)
+
+
+def test_fused_zero_anchor_items(eng):
+    # k_i = 0 is in the reference's grid: all approximate scores are 0
+    packed = eng.PackedItems(torch.zeros(0, 50).cuda(), "f32x3")
+    v, i = eng.score_topk(torch.zeros(4, 0).cuda(), packed, 5)
+    assert (v == 0).all() and i[0].tolist() == [0, 1, 2, 3, 4]
+
+
+def test_fused_bf16_recall(eng):
+    Q, E = _rand((200, 500), 1), _rand((500, 30000), 2)
+    packed = eng.PackedItems(E.cuda(), "bf16")
+    v, i = eng.score_topk(Q.cuda(), packed, 100)
+    ref = O.score_topk(Q, E, 100)
+    i = i.cpu().numpy()
+    recall = np.mean([len(set(i[r]) & set(ref.indices[r].tolist())) / 100 for r in range(200)])
+    assert recall > 0.9, recall                                    # reported, not a parity claim
+    dense = (Q @ E).numpy()
+    assert_scores_close(v.cpu().numpy(), np.take_along_axis(dense, i, 1), rel=2e-2)
+
+
+def test_fused_c1_config_against_oracle(eng):
+    """BASELINE config 1: 1k queries x 10k items, k_q = k_i = 50, top-100 (the reference's CPU-runnable case)."""
+    A = torch.from_numpy(O.synthetic_scores(1000, 10000, rank=64, noise=0.05, seed=0))
+    rows_i, cols_i = O.sample_anchors(1000, 10000, 50, 50, 0)
+    f = O.cur_build(A[rows_i, :], A[:, cols_i], rows_i, cols_i, "rows", check=False)
+    Q = A[:, cols_i].contiguous()
+    _check(eng, Q, f.latent_cols, 100)
+
+
+def test_fused_c2_config_sharded_merge_property(eng):
+    """BASELINE config 2 size (N = 100k, k_i = 500, B = 4096): oracle on a row sample, and the
+    size-independent property that an item-sharded search merged by anncur_merge_topk equals the
+    single-shard answer."""
+    K, N, B, k = 500, 100000, 4096, 100
+    Q, E = _rand((B, K), 21), _rand((K, N), 22)
+    Ec = E.cuda()
+    packed = eng.PackedItems(Ec, "f32x3")
+    v, i = eng.score_topk(Q.cuda(), packed, k)
+    rows = np.random.default_rng(0).choice(B, 96, replace=False)
+    dense = (Q[rows].double() @ E.double()).numpy()
+    ref = torch.topk(torch.from_numpy(dense), k, dim=1)
+    assert_topk_sets_match(i[rows].cpu().numpy(), ref.indices.numpy(), full_scores=dense)
+    assert_scores_close(v[rows].cpu().numpy(), ref.values.numpy())
+    P = 4
+    cv, ci = [], []
+    for p in range(P):
+        lo, hi = p * N // P, (p + 1) * N // P
+        pv, pi = eng.score_topk(Q.cuda(), eng.PackedItems(Ec[:, lo:hi], "f32x3"), k, idx_offset=lo)
+        cv.append(pv), ci.append(pi)
+    mv, mi = eng.merge_topk(torch.cat(cv, 1), torch.cat(ci, 1), k)
+    assert torch.equal(mi, i) and torch.allclose(mv, v, rtol=1e-5, atol=1e-5)

@@ -1,0 +1,169 @@
+"""GPU parity: every kernel family through the C ABI (anncur_b200.engine) against the CPU oracle /
+plain torch fp32 on the same seeded inputs.  Integer/index results are compared with the near-tie
+rule of tests/parity.py; floating point with the 1e-4 relative tolerance of BASELINE.json."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cur_oracle as O
+from tests.parity import assert_scores_close, assert_sorted_desc, assert_topk_sets_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from anncur_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+def _rand(shape, seed):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- top-k
+@pytest.mark.parametrize("n,N,k", [(1, 1, 1), (3, 10, 10), (5, 1000, 7), (17, 4096, 100), (4, 5000, 1000),
+                                   (2, 70000, 64), (3, 200000, 2048)])
+def test_topk_rows_matches_torch(eng, n, N, k):
+    S = _rand((n, N), n * 1000 + k)
+    v, i = eng.topk_rows(S.cuda(), k)
+    ref = torch.topk(S, k, dim=1)
+    assert torch.equal(v.cpu(), ref.values)              # bit-exact values: pure selection
+    assert_topk_sets_match(i.cpu().numpy(), ref.indices.numpy(), full_scores=S.numpy())
+    assert_sorted_desc(v.cpu().numpy())
+    assert torch.equal(torch.gather(S, 1, i.cpu()), v.cpu())
+
+
+def test_topk_rows_ties_lowest_index_first_and_padding(eng):
+    S = torch.zeros(2, 6000)
+    S[0, [5, 900, 4500]] = 1.0
+    v, i = eng.topk_rows(S.cuda(), 6)
+    assert i[0].tolist() == [5, 900, 4500, 0, 1, 2] and i[1].tolist() == [0, 1, 2, 3, 4, 5]
+    v, i = eng.topk_rows(torch.tensor([[3.0, 1.0, 2.0]]).cuda(), 5)          # k > N: faiss-style padding
+    assert i[0].tolist() == [0, 2, 1, -1, -1]
+    assert v[0, 3].item() == -np.finfo(np.float32).max
+    v, i = eng.topk_rows(S[:, ::7].cuda(), 3)                                 # strided rows (lds != n_cols)
+    assert v.shape == (2, 3)
+    v2, i2 = eng.topk_rows(S.cuda(), 4, idx_offset=10**10)                    # int64 offsets survive
+    assert i2[1].tolist() == [10**10 + j for j in range(4)]
+
+
+def test_merge_topk_matches_oracle(eng):
+    rng = np.random.default_rng(3)
+    P, B, k = 8, 37, 100
+    vals = rng.standard_normal((P, B, k)).astype(np.float32)
+    idx = np.stack([rng.permutation(10**6)[: B * k].reshape(B, k) + p * 10**6 for p in range(P)]).astype(np.int64)
+    idx[3, :, 90:] = -1                                                        # a short shard
+    want_v, want_i = O.merge_topk(vals, idx, k)
+    cv = torch.from_numpy(vals).permute(1, 0, 2).reshape(B, P * k)
+    ci = torch.from_numpy(idx).permute(1, 0, 2).reshape(B, P * k)
+    v, i = eng.merge_topk(cv.cuda(), ci.cuda(), k)
+    assert np.array_equal(i.cpu().numpy(), want_i) and np.array_equal(v.cpu().numpy(), want_v)
+
+
+# ---------------------------------------------------------------------------------------------- gemm
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (50, 50, 10000), (130, 17, 257), (500, 2000, 3000), (64, 0, 33)])
+def test_gemm_matches_torch(eng, m, k, n):
+    A, B = _rand((m, k), 1), _rand((k, n), 2)
+    C = eng.gemm(A.cuda(), B.cuda()).cpu()
+    ref = A @ B
+    assert C.shape == ref.shape
+    if k:
+        bound = (A.abs() @ B.abs()).numpy()               # |a|.|b| bounds fp32 summation-order differences
+        assert (np.abs(C.numpy() - ref.numpy()) <= 1e-5 * bound + 1e-30).all()
+    else:
+        assert torch.count_nonzero(C) == 0
+
+
+def test_gemm_strided_operands(eng):
+    A, B = _rand((70, 90), 5), _rand((60, 300), 6)
+    C = eng.gemm(A.cuda()[:, :60], B.cuda()[:, 10:250]).cpu()
+    assert_scores_close(C.numpy(), (A[:, :60] @ B[:, 10:250]).numpy(), rel=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------- pinv
+@pytest.mark.parametrize("m,n", [(50, 50), (200, 50), (40, 160), (1, 7), (2000, 500), (33, 1)])
+def test_pinv_matches_numpy(eng, m, n):
+    A = O.synthetic_scores(m, n, rank=min(m, n, 64), noise=0.05, seed=m + n)
+    P, cond = eng.pinv(torch.from_numpy(A).cuda(), return_cond=True)
+    P = P.cpu().numpy().astype(np.float64)
+    ref = np.linalg.pinv(A.astype(np.float64), rcond=1e-15)
+    s = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    c = s[0] / s[-1]
+    assert np.linalg.norm(P - ref) / np.linalg.norm(ref) <= max(1e-5, 10 * c * np.finfo(np.float32).eps)
+    smax, smin = cond.tolist()
+    assert abs(smax - s[0]) <= 1e-6 * s[0] and abs(smin - s[-1]) <= 1e-4 * s[-1] + 1e-9 * s[0]
+    # Moore-Penrose identities in fp64 on our result
+    A64 = A.astype(np.float64)
+    assert np.linalg.norm(A64 @ P @ A64 - A64) <= 1e-4 * c * np.linalg.norm(A64) * 1e-2 + 1e-5 * np.linalg.norm(A64)
+
+
+def test_pinv_drops_null_directions(eng):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((60, 5))
+    A = (X @ rng.standard_normal((5, 30))).astype(np.float32)      # rank 5
+    P = eng.pinv(torch.from_numpy(A).cuda(), rcond=1e-5).cpu().numpy().astype(np.float64)
+    ref = np.linalg.pinv(A.astype(np.float64), rcond=1e-5)
+    assert np.linalg.norm(P - ref) / np.linalg.norm(ref) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- FFMA score + top-k
+@pytest.mark.parametrize("B,K,N,k", [(1, 50, 10000, 100), (200, 500, 20000, 100), (37, 7, 300, 300), (9, 64, 5000, 1500)])
+def test_score_topk_f32_matches_oracle(eng, B, K, N, k):
+    Q, E = _rand((B, K), 11), _rand((K, N), 12)
+    v, i = eng.score_topk_f32(Q.cuda(), E.cuda(), k)
+    dense = (Q @ E).numpy()
+    ref = O.score_topk(Q, E, k)
+    assert_topk_sets_match(i.cpu().numpy(), ref.indices.numpy(), full_scores=dense)
+    assert_scores_close(v.cpu().numpy(), ref.values.numpy())
+    assert_sorted_desc(v.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------- rerank / overlap
+@pytest.mark.parametrize("n,N,k_list,k_r", [(40, 900, [1, 10, 50], 200), (7, 3000, [100], 1000), (5, 64, [64], 64)])
+def test_rerank_overlap_matches_oracle(eng, n, N, k_list, k_r):
+    exact = O.synthetic_scores(n, N, rank=8, seed=3)
+    approx = exact + 0.3 * np.random.default_rng(4).standard_normal((n, N)).astype(np.float32)
+    k_max = max(k_list)
+    lists = O.retrieve_and_rerank(exact, approx, k_max, k_r)
+    ex_i, ap_i = torch.from_numpy(lists["exact"][0]).cuda(), torch.from_numpy(lists["approx"][0]).cuda()
+    rr_i, rr_v, common = eng.rerank_overlap(torch.from_numpy(exact).cuda(), ap_i, ex_i, k_list)
+    want_i, want_v = lists["reranked"]
+    assert np.array_equal(rr_v.cpu().numpy(), want_v)                       # exact scores, bit for bit
+    assert_topk_sets_match(rr_i.cpu().numpy(), want_i, full_scores=exact)
+    for j, k in enumerate(k_list):
+        want = [O.overlap_one(lists["exact"][0][q, :k], want_i[q, :k])["common"] for q in range(n)]
+        assert common[:, j].cpu().tolist() == want
+
+
+# ---------------------------------------------------------------------------------------------- recon error
+def test_recon_error_matches_torch(eng):
+    n, K, N = 300, 40, 5000
+    Q, E, A = _rand((n, K), 1), _rand((K, N), 2), _rand((n, N), 3)
+    e2, n2 = eng.recon_error_rows(Q.cuda(), E.cuda(), A.cuda())
+    d = (Q.double() @ E.double() - A.double())
+    assert torch.allclose(e2.cpu(), (d ** 2).sum(1), rtol=1e-5)
+    assert torch.allclose(n2.cpu(), (A.double() ** 2).sum(1), rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- adaptive (parity unpinned)
+def test_adaptive_round_matches_oracle_restatement(eng):
+    rng = np.random.default_rng(0)
+    k_q, N, B, m, n_next = 40, 700, 9, 16, 8
+    A = O.synthetic_scores(k_q + B, N, rank=12, noise=0.02, seed=2)
+    R, X = A[:k_q], A[k_q:]
+    anchors = np.stack([np.sort(rng.choice(N, m, replace=False)) for _ in range(B)])
+    c = np.take_along_axis(X, anchors, 1)
+    nxt, val = eng.adaptive_round(torch.from_numpy(R).cuda(), torch.from_numpy(anchors).cuda(), torch.from_numpy(c).cuda(), n_next)
+    for q in range(B):
+        e = c[q].astype(np.float64) @ np.linalg.pinv(R[:, anchors[q]].astype(np.float64))
+        s = e @ R.astype(np.float64)
+        s[anchors[q]] = -np.inf
+        want = np.argsort(-s, kind="stable")[:n_next]
+        kth = s[want[-1]]
+        tau = 1e-4 * np.abs(s[np.isfinite(s)]).max()
+        got = nxt[q].cpu().numpy()
+        assert all(s[j] >= kth - tau for j in got) and len(set(got.tolist())) == n_next
+        assert not set(got.tolist()) & set(anchors[q].tolist())
+        assert np.allclose(val[q].cpu().numpy(), s[got], atol=10 * tau)
