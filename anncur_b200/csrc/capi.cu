@@ -172,6 +172,9 @@ int anncur_recon_error_f32(const float* Q, int ldq, const float* E, int64_t lde,
     return recon_error(Q, ldq, E, lde, A, lda, n_rows, n_items, k_dim, out_err2, out_norm2, cudaStream_t(stream));
 }
 
+int anncur_profile_enable(int on) { return profile_enable(on); }
+int anncur_profile_read(double* fused_ms_sum, int* fused_launches) { return profile_read(fused_ms_sum, fused_launches); }
+
 size_t anncur_adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next) {
     return adaptive_round_workspace_bytes(n_queries, k_q, m, n_items, n_next);
 }

@@ -40,6 +40,9 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
                      int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
                      int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int profile_enable(int on);
+int profile_read(double* ms_sum, int* launches);
+
 // adaptive.cu
 size_t adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next);
 int adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const int64_t* anchors,

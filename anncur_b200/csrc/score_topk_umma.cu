@@ -30,6 +30,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -642,14 +644,58 @@ size_t score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int
     return make_plan(n_queries, n_items, k_dim, k, kind).total;
 }
 
+// ---- optional event timing of the fused kernel (anncur_profile_*) ---------------------------------
+struct ProfileState {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+static thread_local ProfileState g_prof;
+
+int profile_enable(int on) {
+    g_prof.on = on != 0;
+    if (!g_prof.on) {
+        for (auto& e : g_prof.events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        g_prof.events.clear();
+    }
+    return ANNCUR_OK;
+}
+
+int profile_read(double* ms_sum, int* launches) {
+    double sum = 0.0;
+    int n = 0;
+    for (auto& e : g_prof.events) {
+        ANNCUR_CUDA_OK(cudaEventSynchronize(e.second));
+        float ms = 0.f;
+        ANNCUR_CUDA_OK(cudaEventElapsedTime(&ms, e.first, e.second));
+        sum += ms;
+        ++n;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    g_prof.events.clear();
+    if (ms_sum) *ms_sum = sum;
+    if (launches) *launches = n;
+    return ANNCUR_OK;
+}
+
 template <int PASSES, bool BF16, int CPL>
 static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                         const FusedParams& fp, int grid, cudaStream_t stream) {
     using Cfg = StageCfg<PASSES>;
     const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4;
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(fused_score_topk_kernel<PASSES, BF16, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_prof.on) {
+        ANNCUR_CUDA_OK(cudaEventCreate(&ev0));
+        ANNCUR_CUDA_OK(cudaEventCreate(&ev1));
+        ANNCUR_CUDA_OK(cudaEventRecord(ev0, stream));
+    }
     fused_score_topk_kernel<PASSES, BF16, CPL><<<grid, FUSED_THREADS, smem, stream>>>(a0, a1, b0, b1, fp);
     ANNCUR_LAUNCH_OK("fused_score_topk_kernel");
+    if (g_prof.on) {
+        ANNCUR_CUDA_OK(cudaEventRecord(ev1, stream));
+        g_prof.events.emplace_back(ev0, ev1);
+    }
     return ANNCUR_OK;
 }
 

@@ -73,6 +73,17 @@ def reset_launch_count():
     _lib.load().anncur_reset_kernel_launch_count()
 
 
+def profile_enable(on=True):
+    _lib.check(_lib.load().anncur_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """(summed fused-kernel milliseconds, launches) since the last read; waits for the recorded events."""
+    ms, n = C.c_double(0.0), C.c_int(0)
+    _lib.check(_lib.load().anncur_profile_read(C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
 # ---- K1 -------------------------------------------------------------------------------------------
 def pinv(A, rcond=1e-15, return_cond=False):
     """pinv of an (m x n) fp32 matrix -> (n x m) fp32 on the GPU (eval/matrix_approx_zeshel.py:47,49)."""

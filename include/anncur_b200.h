@@ -154,6 +154,14 @@ ANNCUR_API int anncur_adaptive_round(const float* R_anc, int64_t ldr, int k_q, i
                           double rcond, int n_next, int64_t* next_idx, float* next_val,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- per-kernel device timing (bench.py's roofline) ---------------------------------------------
+ * While enabled, every anncur_score_topk call records a CUDA-event pair around its fused tcgen05
+ * kernel on the call's stream.  anncur_profile_read waits for the recorded events (it is the one
+ * call that blocks), returns the summed kernel milliseconds and the number of launches, and clears
+ * the record. */
+ANNCUR_API int anncur_profile_enable(int on);
+ANNCUR_API int anncur_profile_read(double* fused_ms_sum, int* fused_launches);
+
 /* ---- introspection used by bench.py ("gpu_launches") ------------------------------------------
  * Number of kernels this library has launched on the calling host thread since the last reset. */
 ANNCUR_API uint64_t anncur_kernel_launch_count(void);
