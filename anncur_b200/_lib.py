@@ -24,6 +24,8 @@ PROTOTYPES = {
     "anncur_pack_items": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "anncur_score_topk_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "anncur_score_topk": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_search_host_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
+    "anncur_search_host": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_score_topk_f32_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "anncur_score_topk_f32": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_topk_rows_f32": (_i, [_vp, _i64, _i, _i64, _i, _i64, _vp, _vp, _vp]),

@@ -98,6 +98,45 @@ int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed
                             out_idx, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+
+// ---- host-buffer search: H2D of the query batch, fused score + top-k, D2H of the result ----------
+static size_t host_stage_q_bytes(int n_queries, int k_dim) { return align_up(sizeof(float) * size_t(n_queries) * size_t(k_dim > 0 ? k_dim : 1), 256); }
+static size_t host_stage_v_bytes(int n_queries, int k) { return align_up(sizeof(float) * size_t(n_queries) * size_t(k), 256); }
+static size_t host_stage_i_bytes(int n_queries, int k) { return align_up(sizeof(int64_t) * size_t(n_queries) * size_t(k), 256); }
+
+size_t anncur_search_host_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
+    if (n_queries <= 0 || k <= 0) return 256;
+    return host_stage_q_bytes(n_queries, k_dim) + host_stage_v_bytes(n_queries, k) + host_stage_i_bytes(n_queries, k) +
+           score_topk_workspace_bytes(n_queries, n_items, k_dim, k, kind);
+}
+
+int anncur_search_host(const float* Q_host, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                       int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals_host,
+                       int64_t* out_idx_host, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim >= 0 && k >= 1, "search_host: bad shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_vals_host && out_idx_host && workspace, "search_host: null pointer");
+    ANNCUR_REQUIRE(k_dim == 0 || (Q_host && ldq >= k_dim), "search_host: null Q or ldq < k_dim");
+    ANNCUR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "search_host: workspace must be 256-byte aligned");
+    const size_t need = anncur_search_host_workspace_bytes(n_queries, n_items, k_dim, k, kind);
+    if (workspace_bytes < need) { set_error("search_host workspace too small: %zu < %zu", workspace_bytes, need); return ANNCUR_E_WORKSPACE; }
+    cudaStream_t s = cudaStream_t(stream);
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* q_dev = reinterpret_cast<float*>(ws);                      ws += host_stage_q_bytes(n_queries, k_dim);
+    float* v_dev = reinterpret_cast<float*>(ws);                      ws += host_stage_v_bytes(n_queries, k);
+    int64_t* i_dev = reinterpret_cast<int64_t*>(ws);                  ws += host_stage_i_bytes(n_queries, k);
+    const size_t inner = workspace_bytes - size_t(ws - reinterpret_cast<char*>(workspace));
+    if (k_dim > 0)
+        ANNCUR_CUDA_OK(cudaMemcpy2DAsync(q_dev, sizeof(float) * size_t(k_dim), Q_host, sizeof(float) * size_t(ldq),
+                                         sizeof(float) * size_t(k_dim), size_t(n_queries), cudaMemcpyHostToDevice, s));
+    int rc = anncur_score_topk(q_dev, k_dim, n_queries, packed_items, e_scale, n_items, k_dim, kind, k, idx_offset, v_dev,
+                               i_dev, ws, inner, stream);
+    if (rc != ANNCUR_OK) return rc;
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(out_vals_host, v_dev, sizeof(float) * size_t(n_queries) * size_t(k), cudaMemcpyDeviceToHost, s));
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(out_idx_host, i_dev, sizeof(int64_t) * size_t(n_queries) * size_t(k), cudaMemcpyDeviceToHost, s));
+    return ANNCUR_OK;
+}
+
 size_t anncur_score_topk_f32_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k) {
     (void)k_dim; (void)k;
     if (n_queries <= 0 || n_items <= 0) return 256;

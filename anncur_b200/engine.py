@@ -163,6 +163,27 @@ def score_topk(Q, packed, k, idx_offset=0, out=None):
     return vals, idx
 
 
+def search_host(Q_host, packed, k, out_vals_host, out_idx_host, idx_offset=0, ws_key="search_host"):
+    """Host-buffer form (anncur_search_host): Q_host / out_* are CPU tensors (pinned => fully asynchronous).
+    Enqueues H2D -> fused score + top-k -> D2H on the current stream of the index's device and returns at
+    once; the outputs are valid after that stream (or the device) is synchronised."""
+    lib = _lib.load()
+    assert not Q_host.is_cuda and Q_host.dtype == torch.float32 and Q_host.dim() == 2 and Q_host.stride(1) == 1
+    assert Q_host.shape[1] == packed.k_dim, (Q_host.shape, packed.k_dim)
+    B = int(Q_host.shape[0])
+    assert out_vals_host.shape == (B, k) and out_vals_host.dtype == torch.float32 and out_vals_host.is_contiguous()
+    assert out_idx_host.shape == (B, k) and out_idx_host.dtype == torch.int64 and out_idx_host.is_contiguous()
+    assert not out_vals_host.is_cuda and not out_idx_host.is_cuda
+    if B > 0:
+        nbytes = lib.anncur_search_host_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
+        ws = WORKSPACE.get(ws_key, nbytes, packed.device)
+        with torch.cuda.device(packed.device):
+            _lib.check(lib.anncur_search_host(_ptr(Q_host), _ld(Q_host), B, _ptr(packed.buf), _ptr(packed.scale),
+                                              packed.n_items, packed.k_dim, packed.kind, int(k), int(idx_offset),
+                                              _ptr(out_vals_host), _ptr(out_idx_host), _ptr(ws), ws.numel(), _stream()))
+    return out_vals_host, out_idx_host
+
+
 def score_topk_f32(Q, E, k, idx_offset=0):
     """Plain-fp32 FFMA score + top-k on unpacked E (any k <= MAX_K)."""
     lib = _lib.load()

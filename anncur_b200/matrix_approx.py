@@ -159,15 +159,32 @@ class CURApprox(object):
             self._packed[precision] = engine.PackedItems(self._latent_cols_dev, precision)
         return self._packed[precision]
 
-    def topk_in_row(self, sparse_rows, k, precision=None):
+    def topk_in_row(self, sparse_rows, k, precision=None, out=None):
+        """torch.topk(sparse_rows @ latent_cols, k, dim=1) (reference :121-126) without the B x N matrix.
+        CPU inputs (what the reference's scripts pass) go through the host-buffer entry point: one H2D
+        of the query batch, the fused kernel, one D2H of (values, indices).  ``out`` = optional
+        (values fp32 [B x k], indices int64 [B x k]) CPU tensors to fill (pin them to make the copies
+        asynchronous); the call still synchronises before returning, like the reference."""
         if self.approx_preference != "rows":
             raise NotImplementedError("This is not designed to give good approx of rows as C and U matrix are multiplied together. Build index w/ approx_preference = rows instead.")
         precision = precision or self.precision
-        Q = torch.as_tensor(sparse_rows).to(self._dev, torch.float32)
+        Q = torch.as_tensor(sparse_rows)
         N = self._latent_cols_dev.shape[1]
         if k > N:
             raise RuntimeError("selected index k out of range")       # what torch.topk raises
-        if precision == "f32" or k > engine.MAX_K_FUSED:
+        fused = not (precision == "f32" or k > engine.MAX_K_FUSED)
+        if fused and not Q.is_cuda and Q.dim() == 2 and Q.shape[0] > 0 and self._latent_cols_dev.shape[0] > 0:
+            Qh = Q.to(torch.float32)
+            if Qh.stride(1) != 1:
+                Qh = Qh.contiguous()
+            if out is None:
+                out = (torch.empty((Qh.shape[0], k), dtype=torch.float32), torch.empty((Qh.shape[0], k), dtype=torch.int64))
+            with torch.cuda.device(self._dev):
+                v, i = engine.search_host(Qh, self.packed_items(precision), k, out[0], out[1])
+                torch.cuda.current_stream().synchronize()
+            return torch.return_types.topk((v, i))
+        Q = Q.to(self._dev, torch.float32)
+        if not fused:
             v, i = engine.score_topk_f32(Q, self._latent_cols_dev, k)
         else:
             v, i = engine.score_topk(Q, self.packed_items(precision), k)

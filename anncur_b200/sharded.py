@@ -37,7 +37,8 @@ def unpack_candidates(buf, k):
 class ShardedIndex:
     """This rank's slice of the item-embedding matrix plus the collective search."""
 
-    def __init__(self, E_local, lo, n_items_total, *, precision="f32x3", group=None, local_search=None, merge=None):
+    def __init__(self, E_local, lo, n_items_total, *, precision="f32x3", group=None, local_search=None, merge=None,
+                 packed=None):
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -48,7 +49,7 @@ class ShardedIndex:
         if local_search is None:
             from . import engine
             engine.require_cuda()
-            self._packed = engine.PackedItems(E_local, precision)
+            self._packed = packed if packed is not None else engine.PackedItems(E_local, precision)
             local_search = lambda Q, k: engine.score_topk(Q, self._packed, k, idx_offset=self.lo)   # noqa: E731
             merge = merge or engine.merge_topk
         self._local_search = local_search

@@ -94,6 +94,18 @@ ANNCUR_API int anncur_score_topk(const float* Q, int ldq, int n_queries, const v
                       int64_t idx_offset, float* out_vals, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-buffer form of the same call -- what a CPU-resident caller such as the reference's eval
+ * scripts (CPU torch tensors, eval/run_retrieval_eval_wrt_exact_crossenc_w_fixed_train_test_splits.py
+ * :298-301) binds: Q_host / out_*_host are HOST pointers (pinned for the copies to be asynchronous);
+ * the call enqueues H2D(Q) -> fused score + top-k -> D2H(vals, idx) on `stream` and returns; the
+ * results are valid after the stream is synchronised.  The workspace (device memory) also holds
+ * the staging copies. */
+ANNCUR_API size_t anncur_search_host_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind);
+ANNCUR_API int anncur_search_host(const float* Q_host, int ldq, int n_queries, const void* packed_items,
+                       const float* e_scale, int64_t n_items, int k_dim, int kind, int k,
+                       int64_t idx_offset, float* out_vals_host, int64_t* out_idx_host,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same contract on plain fp32 E (k_dim x N, lde) with FFMA arithmetic: scores are materialised
  * in row blocks inside the workspace and reduced by the row top-k below.  Any k <= ANNCUR_MAX_K. */
 ANNCUR_API size_t anncur_score_topk_f32_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k);
