@@ -19,16 +19,31 @@
 //   warp 0      TMA producer  (4-stage ring: Q tile 128 x 32 and E tile 256 x 32 per plane)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator 128 x 256 fp32,
 //               double-buffered in the 512 TMEM columns
-//   warps 2-5   epilogue: thread = one query row; tcgen05.ld 32 columns at a time, compare with
-//               the row's running threshold (k-th best so far), push the rare survivors as 64-bit
-//               keys to the row's candidate list (L2-resident), and when a list fills up the warp
-//               radix-selects it back to k entries and tightens the threshold.  Thresholds are
-//               shared between the item chunks of a row through global memory.
+//   warps 2-5   epilogue: thread = one query row; tcgen05.ld 32 columns at a time (the next load is
+//               in flight while the current one is processed), compare with the row's threshold,
+//               push the rare survivors as 64-bit keys to the row's candidate list (L2-resident);
+//               if a list fills up the warp radix-selects it back to k entries and tightens the
+//               threshold (streaming fallback -- stays correct for adversarial inputs).
 // Work item = (chunk of item tiles, 128-query tile), ordered chunk-major so that co-resident CTAs
 // stream the same slice of E and it is read from HBM once.
+//
+// Thresholds.  Pushing is only cheap when the threshold is tight from the first tile on, so a call
+// runs the kernel up to three times:
+//   SAMPLE  every G-th item (a strided TMA view of the same packed planes, no copy) is scored and
+//           the epilogue only records the maximum of each 32-column group; the j-th largest group
+//           maximum of a row (sample_threshold_kernel) is <= the j-th best sampled score, so at
+//           least j sampled items reach it.  j is chosen so that P[Binomial(k-1, 1/G) >= j] <= 1e-8:
+//           then at least k items of the full row reach the threshold except with that probability,
+//           and about j*G items do (a few hundred).
+//   MAIN    all items, thresholds preloaded; survivors >= threshold are pushed.
+//   REDO    rows that ended with fewer than k candidates (the rare miss, found by the select
+//           kernel) are re-run with the threshold reset to -inf and streaming compaction; query
+//           tiles without such a row are skipped, so normally this launch exits at once.
+// Small item sets (too few sampled groups) skip SAMPLE/REDO and run MAIN in streaming mode.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <math.h>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -55,9 +70,12 @@ template <int PASSES> struct StageCfg {
     static constexpr int kStages = PASSES == 3 ? 4 : 8;
 };
 
+enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
+
 struct FusedParams {
+    int mode;                // MODE_MAIN: push survivors;  MODE_SAMPLE: record 32-column group maxima
     int n_queries;
-    int n_items;
+    int n_items;             // valid columns of this pass (all items, or the sampled ones)
     int num_kb;
     int k;
     int m_tiles;
@@ -66,6 +84,10 @@ struct FusedParams {
     uint64_t* cand;          // [n_queries][n_chunks][cap]
     uint32_t* counts;        // [n_queries][n_chunks]
     uint32_t* thr_shared;    // [n_queries] ordered-uint lower bound (exclusive) on useful scores
+    const uint32_t* mtile_flags;   // optional [m_tiles]: work items of query tiles whose flag is 0 are skipped
+    float* smax;             // MODE_SAMPLE: [n_queries][n_smax] group maxima
+    int n_smax;
+    int close_compact;       // MODE_MAIN: cut lists back to k at the end of a work item (streaming mode: tightens the shared bound)
     int* error_flag;
 };
 
@@ -127,8 +149,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
     d |= uint64_t(4) << 61;                       // layout type SWIZZLE_64B
     return d;
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane: issue only (asynchronous) ...
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -138,9 +160,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// ... and the wait for every outstanding load.  The registers are in/out operands so that no use of
+// them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 
 // ---- warp-cooperative compaction of one row's candidate list back to its best k -----------------
@@ -256,6 +286,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
     const int total_items = p.n_chunks * p.m_tiles;
+    // a work item is skipped by all three roles when its query tile is not flagged (REDO launch only)
+    auto item_live = [&](int m_tile) { return p.mtile_flags == nullptr || __ldg(p.mtile_flags + m_tile) != 0u; };
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -263,6 +295,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             int stage = 0; uint32_t phase = 0;
             for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
                 const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
+                if (!item_live(m_tile)) continue;
                 const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
@@ -294,6 +327,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             int buf = 0; uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
                 const int chunk = w / p.m_tiles;
+                if (!item_live(w % p.m_tiles)) continue;
                 const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
@@ -336,66 +370,112 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         uint32_t* hist = hist_all + (warp - 2) * 256;
         int buf = 0; uint32_t acc_phase = 0;
         const uint32_t k = uint32_t(p.k);
+        const bool sample = p.mode == MODE_SAMPLE;
         for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
             const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
+            if (!item_live(m_tile)) continue;
             const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
             const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
             const int row = m_tile * BLOCK_M + q * 32 + int(lane);
             const bool row_ok = row < p.n_queries;
             const int row_c = row_ok ? row : 0;
             uint64_t* list = p.cand + (int64_t(row_c) * p.n_chunks + chunk) * int64_t(CAP);
+            float* smax_row = p.smax + int64_t(row_c) * p.n_smax;
             uint32_t cnt = 0;
             float thr_own = -INFINITY;
-            for (int tile = t0; tile < t1; ++tile) {
-                // refresh the cross-chunk bound (exclusive) before blocking on the accumulator
-                float thr = INFINITY;
-                if (row_ok) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
-                mbar_wait(tfull_bar(buf), acc_phase, p.error_flag);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
-                const int col_tile = tile * BLOCK_N;
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    // make room: a 32-column group can add at most 32 survivors to a list
-                    uint32_t full_mask = __ballot_sync(0xffffffffu, cnt > CAP - 32u);
-                    while (full_mask) {
-                        const int src = __ffs(int(full_mask)) - 1;
-                        full_mask &= full_mask - 1;
-                        const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
-                        const uint64_t lp = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(list), src);
-                        __syncwarp();
-                        const uint64_t kth = warp_compact_list<CPL>(reinterpret_cast<uint64_t*>(lp), n_src, k, hist);
-                        __syncwarp();
-                        if (int(lane) == src) {
-                            cnt = k;
-                            thr_own = key_score(kth);
-                            thr = fmaxf(thr, thr_own);
-                            atomicMax(p.thr_shared + row, float_to_ordered(thr_own) - 1u);
-                        }
+            float thr = INFINITY;
+
+            // one 32-column group of this thread's row, already in registers
+            auto process = [&](const uint32_t (&r)[32], int tile, int c) {
+                const int col0 = tile * BLOCK_N + c * 32;
+                float g[4];
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    float m01 = fmaxf(__uint_as_float(r[gi * 8 + 0]), __uint_as_float(r[gi * 8 + 1]));
+                    float m23 = fmaxf(__uint_as_float(r[gi * 8 + 2]), __uint_as_float(r[gi * 8 + 3]));
+                    float m45 = fmaxf(__uint_as_float(r[gi * 8 + 4]), __uint_as_float(r[gi * 8 + 5]));
+                    float m67 = fmaxf(__uint_as_float(r[gi * 8 + 6]), __uint_as_float(r[gi * 8 + 7]));
+                    g[gi] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+                }
+                if (sample) {
+                    float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+                    if (col0 + 32 > p.n_items) {                      // ragged last group: ignore the zero-filled tail
+                        m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n_items) m = fmaxf(m, __uint_as_float(r[j]));
                     }
-                    float v[32];
-                    tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
-                    float m = v[0];
+                    if (row_ok) smax_row[tile * (BLOCK_N / 32) + c] = m;
+                    return;
+                }
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                    if (m > thr) {
-                        const int col0 = col_tile + c * 32;
+                for (int gi = 0; gi < 4; ++gi) {
+                    if (g[gi] > thr) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] > thr && col0 + j < p.n_items) {
-                                list[cnt] = make_key(v[j], uint32_t(col0 + j));
+                        for (int j = 0; j < 8; ++j) {
+                            const float v = __uint_as_float(r[gi * 8 + j]);
+                            if (v > thr && col0 + gi * 8 + j < p.n_items) {
+                                list[cnt] = make_key(v, uint32_t(col0 + gi * 8 + j));
                                 ++cnt;
                             }
                         }
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(buf));
+            };
+            // make room: a 32-column group can add at most 32 survivors to a list
+            auto make_room = [&]() {
+                uint32_t full_mask = __ballot_sync(0xffffffffu, cnt > CAP - 32u);
+                while (full_mask) {
+                    const int src = __ffs(int(full_mask)) - 1;
+                    full_mask &= full_mask - 1;
+                    const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
+                    const uint64_t lp = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(list), src);
+                    __syncwarp();
+                    const uint64_t kth = warp_compact_list<CPL>(reinterpret_cast<uint64_t*>(lp), n_src, k, hist);
+                    __syncwarp();
+                    if (int(lane) == src) {
+                        cnt = k;
+                        thr_own = key_score(kth);
+                        thr = fmaxf(thr, thr_own);
+                        atomicMax(p.thr_shared + row, float_to_ordered(thr_own) - 1u);
+                    }
+                }
+            };
+
+            for (int tile = t0; tile < t1; ++tile) {
+                // refresh the cross-chunk bound (exclusive) before blocking on the accumulator
+                if (!sample) {
+                    thr = INFINITY;
+                    if (row_ok) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
+                }
+                mbar_wait(tfull_bar(buf), acc_phase, p.error_flag);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
+                uint32_t ra[32], rb[32];
+                tmem_ld_issue(taddr, ra);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                    tmem_ld_wait(ra);
+                    tmem_ld_issue(taddr + uint32_t((c + 1) * 32), rb);
+                    if (!sample) make_room();
+                    process(ra, tile, c);
+                    tmem_ld_wait(rb);
+                    if (c + 2 < BLOCK_N / 32) {
+                        tmem_ld_issue(taddr + uint32_t((c + 2) * 32), ra);
+                    } else {
+                        // the whole accumulator is in registers: hand the TMEM buffer back before the last group
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(buf));
+                    }
+                    if (!sample) make_room();
+                    process(rb, tile, c + 1);
+                }
                 if (++buf == 2) { buf = 0; acc_phase ^= 1u; }
             }
-            // close the work item: lists longer than k are cut back so the merge sees <= k per chunk
-            uint32_t over_mask = __ballot_sync(0xffffffffu, row_ok && cnt > k);
+            if (sample) continue;
+            // close the work item (streaming mode): lists longer than k are cut back, which publishes a tighter bound
+            uint32_t over_mask = __ballot_sync(0xffffffffu, p.close_compact != 0 && row_ok && cnt > k);
             while (over_mask) {
                 const int src = __ffs(int(over_mask)) - 1;
                 over_mask &= over_mask - 1;
@@ -487,7 +567,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int k_dim, int num_kb,
                     const float* __restrict__ e_scale, uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l,
-                    float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared) {
+                    float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared,
+                    uint32_t* __restrict__ mtile_flags) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_queries) return;
     const uint32_t lane = lane_id();
@@ -509,6 +590,7 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     if (lane == 0) {
         row_inv_scale[row] = 1.f / (scale * e_scale[0]);
         thr_shared[row] = float_to_ordered(-INFINITY);
+        if ((row % BLOCK_M) == 0) mtile_flags[row / BLOCK_M] = 0u;
     }
 }
 
@@ -520,6 +602,61 @@ __global__ void fill_zero_scores_kernel(int n_queries, int k, int64_t n_items, i
         bool ok = j < n_items;
         out_vals[t] = ok ? 0.f : ANNCUR_PAD_VAL;
         out_idx[t] = ok ? j + idx_offset : -1;
+    }
+}
+
+// ---- SAMPLE -> per-row threshold -------------------------------------------------------------------
+// One warp per query row: j-th largest of the row's n_smax group maxima (MSD radix select on the
+// order-preserving 32-bit image of the floats), published as the exclusive bound of the MAIN pass.
+__global__ void __launch_bounds__(256)
+sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_queries, int j, uint32_t* __restrict__ thr_shared) {
+    __shared__ uint32_t hist_all[8][256];
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_queries) return;
+    const uint32_t lane = lane_id();
+    uint32_t* hist = hist_all[threadIdx.x >> 5];
+    const float* v = smax + int64_t(row) * n_smax;
+    uint32_t prefix = 0, mask = 0, need = uint32_t(j);
+    bool have = n_smax >= j;
+    for (int shift = 24; have && shift >= 0; shift -= 8) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int t = int(lane); t < n_smax; t += 32) {
+            const uint32_t key = float_to_ordered(__ldcg(v + t));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t c[8], lane_sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+        uint32_t incl = lane_sum;                       // inclusive suffix sum towards the higher digits
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_down_sync(0xffffffffu, incl, off);
+            if (lane + off < 32) incl += t;
+        }
+        uint32_t running = incl - lane_sum;
+        bool found = false;
+        uint32_t d = 0, new_need = 0;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+            if (!found && running + c[b] >= need) { found = true; d = lane * 8 + b; new_need = need - running; }
+            running += c[b];
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, found);
+        if (ballot == 0) { have = false; break; }
+        const int src = 31 - __clz(int(ballot));
+        d = __shfl_sync(0xffffffffu, d, src);
+        need = __shfl_sync(0xffffffffu, new_need, src);
+        prefix |= d << shift;
+        mask |= 0xffu << shift;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        // prefix = ordered image of the j-th largest maximum; scores >= it are kept (exclusive bound = it - 1)
+        const uint32_t lowest = float_to_ordered(-INFINITY);
+        thr_shared[row] = (have && prefix > lowest) ? prefix - 1u : lowest;
     }
 }
 
@@ -541,11 +678,14 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int num_kb, int box_rows, bool bf16) {
+// rows = rows of the plane; row_stride > 1 makes a view of every row_stride-th row (the SAMPLE pass)
+static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int num_kb, int box_rows, bool bf16,
+                          int row_stride = 1) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ANNCUR_E_CUDA; }
-    cuuint64_t dims[3] = {cuuint64_t(BLOCK_K), cuuint64_t(rows), cuuint64_t(num_kb)};
-    cuuint64_t strides[2] = {cuuint64_t(BLOCK_K * 2), cuuint64_t(rows) * BLOCK_K * 2};
+    const int64_t view_rows = (rows + row_stride - 1) / row_stride;
+    cuuint64_t dims[3] = {cuuint64_t(BLOCK_K), cuuint64_t(view_rows), cuuint64_t(num_kb)};
+    cuuint64_t strides[2] = {cuuint64_t(BLOCK_K * 2) * cuuint64_t(row_stride), cuuint64_t(rows) * BLOCK_K * 2};
     cuuint32_t box[3] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
@@ -559,48 +699,99 @@ static int num_kb_for(int k_dim) { return (k_dim + BLOCK_K - 1) / BLOCK_K; }
 static int planes_for(int kind) { return kind == ANNCUR_KIND_F32X3 ? 2 : 1; }
 static size_t plane_bytes(int64_t rows, int k_dim) { return align_up(size_t(num_kb_for(k_dim)) * size_t(rows) * BLOCK_K * 2, 256); }
 
-static uint32_t cap_for_k(int k) {
-    uint32_t want = uint32_t(2 * k) > 256u ? uint32_t(2 * k) : 256u;
+static uint32_t pow2_at_least(uint32_t want) {
     uint32_t cap = 256;
     while (cap < want) cap <<= 1;
     return cap;
 }
 
 // Number of item chunks: pick the split of the item tiles that balances (chunks x query tiles)
-// work items over the SMs; every chunk pays a threshold warm-up worth roughly two tiles.
-static int choose_chunks(int m_tiles, int n_tiles, int sms) {
-    int best_c = 1;
-    double best_cost = 1e300;
+// work items over the SMs; `warmup_tiles` is what a chunk pays before its threshold is useful
+// (about two tiles when streaming from -inf, next to nothing with sampled thresholds).
+static int choose_chunks(int m_tiles, int n_tiles, int sms, double warmup_tiles, int c_min = 1) {
     const int c_max = n_tiles < 256 ? n_tiles : 256;
-    for (int c = 1; c <= c_max; ++c) {
+    if (c_min > c_max) c_min = c_max;
+    int best_c = c_min;
+    double best_cost = 1e300;
+    for (int c = c_min; c <= c_max; ++c) {
         const long long items = 1ll * m_tiles * c;
         const long long waves = (items + sms - 1) / sms;
         const int tiles_per = (n_tiles + c - 1) / c;
-        const double cost = double(waves) * (tiles_per + 2.0);
+        const double cost = double(waves) * (tiles_per + warmup_tiles);
         if (cost < best_cost * 0.999) { best_cost = cost; best_c = c; }
     }
     return best_c;
 }
 
+// smallest j with P[Binomial(n, p) >= j] <= eps
+static int binomial_tail_rank(int n, double p, double eps) {
+    if (n <= 0) return 1;
+    // pmf by recurrence from the mode outwards is overkill here: n <= 1023, plain forward recurrence in log space
+    std::vector<double> pmf(size_t(n) + 1);
+    double logq = log1p(-p), logp = log(p);
+    double lc = 0.0;                                           // log C(n, i)
+    for (int i = 0; i <= n; ++i) {
+        if (i > 0) lc += log(double(n - i + 1)) - log(double(i));
+        pmf[size_t(i)] = exp(lc + i * logp + (n - i) * logq);
+    }
+    double tail = 0.0;
+    int j = n + 1;
+    for (int i = n; i >= 1; --i) {
+        tail += pmf[size_t(i)];
+        if (tail > eps) break;
+        j = i;
+    }
+    return j < 1 ? 1 : j;
+}
+
 struct FusedPlan {
     int num_kb, m_tiles, n_tiles, n_chunks;
     uint32_t cap;
-    size_t off_qplanes, off_inv_scale, off_thr, off_counts, off_cand, off_err, total;
+    // SAMPLE pass (sample_stride == 0: not used, MAIN streams from -inf)
+    int sample_stride, sample_rank, s_items, s_tiles, s_chunks, n_smax;
+    size_t off_qplanes, off_inv_scale, off_thr, off_flags, off_counts, off_cand, off_smax, off_err, total;
 };
 
 static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
     FusedPlan pl{};
+    const int sms = sm_count();
     pl.num_kb = num_kb_for(k_dim);
     pl.m_tiles = (n_queries + BLOCK_M - 1) / BLOCK_M;
     pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
-    pl.n_chunks = choose_chunks(pl.m_tiles > 0 ? pl.m_tiles : 1, pl.n_tiles > 0 ? pl.n_tiles : 1, sm_count());
-    pl.cap = cap_for_k(k);
+    // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row
+    for (int G : {16, 8, 4}) {
+        const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-8);
+        const int64_t s_items = (n_items + G - 1) / G;
+        const int64_t n_smax = (s_items + 31) / 32;
+        if (n_smax >= 4ll * j && s_items >= 4 * BLOCK_N) {
+            pl.sample_stride = G; pl.sample_rank = j; pl.s_items = int(s_items);
+            pl.s_tiles = int((s_items + BLOCK_N - 1) / BLOCK_N);
+            pl.n_smax = pl.s_tiles * (BLOCK_N / 32);
+            pl.s_chunks = choose_chunks(pl.m_tiles, pl.s_tiles, sms, 0.25);
+            break;
+        }
+    }
+    const bool sampled = pl.sample_stride != 0;
+    // with sampled thresholds a row keeps ~1.25 j G survivors: enough chunks that one list holds twice its share
+    const int c_min = sampled ? int((2.5 * pl.sample_rank * pl.sample_stride) / 1984.0) + 1 : 1;
+    pl.n_chunks = choose_chunks(pl.m_tiles > 0 ? pl.m_tiles : 1, pl.n_tiles > 0 ? pl.n_tiles : 1, sms, sampled ? 0.5 : 2.0, c_min);
+    // list capacity: room for 2k (streaming compaction keeps k) and for twice the expected survivors of a chunk
+    uint32_t want = uint32_t(2 * k);
+    if (sampled) {
+        const double expect = 1.25 * pl.sample_rank * pl.sample_stride / double(pl.n_chunks);
+        const uint32_t w2 = uint32_t(2.0 * expect) + 64u;
+        if (w2 > want) want = w2;
+    }
+    pl.cap = pow2_at_least(want);
+    if (pl.cap > 2048u) pl.cap = 2048u;
     size_t off = 0;
     pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, k_dim);
     pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
+    pl.off_flags = off; off += align_up(sizeof(uint32_t) * size_t(pl.m_tiles > 0 ? pl.m_tiles : 1), 256);
     pl.off_counts = off; off += align_up(sizeof(uint32_t) * size_t(n_queries) * pl.n_chunks, 256);
     pl.off_cand = off; off += align_up(sizeof(uint64_t) * size_t(n_queries) * pl.n_chunks * pl.cap, 256);
+    pl.off_smax = off; off += align_up(sizeof(float) * size_t(n_queries) * size_t(pl.n_smax > 0 ? pl.n_smax : 1), 256);
     pl.off_err = off; off += 256;
     pl.total = off;
     return pl;
@@ -680,19 +871,20 @@ int profile_read(double* ms_sum, int* launches) {
 
 template <int PASSES, bool BF16, int CPL>
 static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-                        const FusedParams& fp, int grid, cudaStream_t stream) {
+                        const FusedParams& fp, int grid, bool timed, cudaStream_t stream) {
     using Cfg = StageCfg<PASSES>;
     const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4;
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(fused_score_topk_kernel<PASSES, BF16, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (g_prof.on) {
+    timed = timed && g_prof.on;
+    if (timed) {
         ANNCUR_CUDA_OK(cudaEventCreate(&ev0));
         ANNCUR_CUDA_OK(cudaEventCreate(&ev1));
         ANNCUR_CUDA_OK(cudaEventRecord(ev0, stream));
     }
     fused_score_topk_kernel<PASSES, BF16, CPL><<<grid, FUSED_THREADS, smem, stream>>>(a0, a1, b0, b1, fp);
     ANNCUR_LAUNCH_OK("fused_score_topk_kernel");
-    if (g_prof.on) {
+    if (timed) {
         ANNCUR_CUDA_OK(cudaEventRecord(ev1, stream));
         g_prof.events.emplace_back(ev0, ev1);
     }
@@ -701,12 +893,12 @@ static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
 
 template <int PASSES, bool BF16>
 static int dispatch_cap(uint32_t cap, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                        const CUtensorMap& b1, const FusedParams& fp, int grid, cudaStream_t stream) {
+                        const CUtensorMap& b1, const FusedParams& fp, int grid, bool timed, cudaStream_t stream) {
     switch (cap) {
-        case 256: return launch_fused<PASSES, BF16, 8>(a0, a1, b0, b1, fp, grid, stream);
-        case 512: return launch_fused<PASSES, BF16, 16>(a0, a1, b0, b1, fp, grid, stream);
-        case 1024: return launch_fused<PASSES, BF16, 32>(a0, a1, b0, b1, fp, grid, stream);
-        case 2048: return launch_fused<PASSES, BF16, 64>(a0, a1, b0, b1, fp, grid, stream);
+        case 256: return launch_fused<PASSES, BF16, 8>(a0, a1, b0, b1, fp, grid, timed, stream);
+        case 512: return launch_fused<PASSES, BF16, 16>(a0, a1, b0, b1, fp, grid, timed, stream);
+        case 1024: return launch_fused<PASSES, BF16, 32>(a0, a1, b0, b1, fp, grid, timed, stream);
+        case 2048: return launch_fused<PASSES, BF16, 64>(a0, a1, b0, b1, fp, grid, timed, stream);
     }
     set_error("score_topk: no kernel for candidate capacity %u", cap);
     return ANNCUR_E_UNSUPPORTED;
@@ -732,19 +924,22 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         return ANNCUR_E_INVALID;
     }
     const bool bf16 = kind == ANNCUR_KIND_BF16;
+    const bool sampled = pl.sample_stride != 0;
     char* ws = reinterpret_cast<char*>(workspace);
     const size_t qpb = plane_bytes(n_queries, k_dim);
     uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
     uint16_t* q_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
     float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
     uint32_t* thr = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pl.off_counts);
     uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+    float* smax = reinterpret_cast<float*>(ws + pl.off_smax);
     int* err = reinterpret_cast<int*>(ws + pl.off_err);
 
     const int qgrid = (n_queries + 7) / 8;
-    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr);
-    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr);
+    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags);
+    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags);
     ANNCUR_LAUNCH_OK("pack_queries_kernel");
 
     const size_t epb = plane_bytes(n_items, k_dim);
@@ -758,17 +953,40 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         if ((rc = make_plane_map(&a1, q_l, n_queries, pl.num_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
         if ((rc = make_plane_map(&b1, items + epb, n_items, pl.num_kb, BLOCK_N, false)) != ANNCUR_OK) return rc;
     }
+    auto launch = [&](const CUtensorMap& mb0, const CUtensorMap& mb1, const FusedParams& fp, bool timed) {
+        const long long items_total = 1ll * fp.m_tiles * fp.n_chunks;
+        const int grid = int(items_total < sm_count() ? items_total : sm_count());
+        return bf16 ? dispatch_cap<1, true>(pl.cap, a0, a1, mb0, mb1, fp, grid, timed, stream)
+                    : dispatch_cap<3, false>(pl.cap, a0, a1, mb0, mb1, fp, grid, timed, stream);
+    };
     FusedParams fp{};
-    fp.n_queries = n_queries; fp.n_items = int(n_items); fp.num_kb = pl.num_kb; fp.k = k;
-    fp.m_tiles = pl.m_tiles; fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
-    fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err;
-    const long long items_total = 1ll * pl.m_tiles * pl.n_chunks;
-    const int grid = int(items_total < sm_count() ? items_total : sm_count());
-    rc = bf16 ? dispatch_cap<1, true>(pl.cap, a0, a1, b0, b1, fp, grid, stream)
-              : dispatch_cap<3, false>(pl.cap, a0, a1, b0, b1, fp, grid, stream);
-    if (rc != ANNCUR_OK) return rc;
+    fp.n_queries = n_queries; fp.num_kb = pl.num_kb; fp.k = k; fp.m_tiles = pl.m_tiles;
+    fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err; fp.smax = smax; fp.n_smax = pl.n_smax;
+
+    if (sampled) {
+        // SAMPLE: every G-th item through a strided view of the same planes -> 32-column group maxima -> thresholds
+        CUtensorMap s0, s1;
+        if ((rc = make_plane_map(&s0, items, n_items, pl.num_kb, BLOCK_N, bf16, pl.sample_stride)) != ANNCUR_OK) return rc;
+        if (bf16) s1 = s0;
+        else if ((rc = make_plane_map(&s1, items + epb, n_items, pl.num_kb, BLOCK_N, false, pl.sample_stride)) != ANNCUR_OK) return rc;
+        FusedParams sp = fp;
+        sp.mode = MODE_SAMPLE; sp.n_items = pl.s_items; sp.n_tiles = pl.s_tiles; sp.n_chunks = pl.s_chunks;
+        if ((rc = launch(s0, s1, sp, false)) != ANNCUR_OK) return rc;
+        sample_threshold_kernel<<<qgrid, 256, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, thr);
+        ANNCUR_LAUNCH_OK("sample_threshold_kernel");
+    }
+    // MAIN
+    fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
+    fp.close_compact = sampled ? 0 : 1;
+    if ((rc = launch(b0, b1, fp, true)) != ANNCUR_OK) return rc;
+    rc = select_topk_keylists(cand, counts, pl.n_chunks, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
+                              out_idx, sampled ? 1 : 0, thr, flags, n_items, stream);
+    if (rc != ANNCUR_OK || !sampled) return rc;
+    // REDO: rows that came up short restart from -inf in streaming mode; unflagged query tiles are skipped
+    fp.mtile_flags = flags; fp.close_compact = 1;
+    if ((rc = launch(b0, b1, fp, false)) != ANNCUR_OK) return rc;
     return select_topk_keylists(cand, counts, pl.n_chunks, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                                out_idx, stream);
+                                out_idx, 2, thr, flags, n_items, stream);
 }
 
 }  // namespace anncur

@@ -34,6 +34,13 @@ struct KeyLists {
     const uint32_t* counts;   // [row][n_lists]
     int n_lists;
     int cap;
+    // flag_mode 1: rows whose lists hold fewer than min(k, n_items) candidates are flagged for the REDO pass
+    // (thr_shared[row] = -inf, query-tile flag set), every other row gets thr_shared[row] = +inf;
+    // flag_mode 2: only rows flagged by mode 1 are processed (thr_shared[row] != +inf).
+    int flag_mode;
+    uint32_t* thr_shared;
+    uint32_t* mtile_flags;
+    int64_t n_items;
     __device__ int64_t size(int) const { return int64_t(n_lists) * cap; }
     __device__ uint64_t key(int row, int64_t j) const {
         int list = int(j / cap), pos = int(j % cap);
@@ -89,6 +96,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
     //      the live ones into shared memory and sort there ------------------------------------
     if constexpr (Src::kIsLists) {
         __shared__ uint32_t offs[kMaxLists + 1];
+        if (src.flag_mode == 2 && __ldcg(src.thr_shared + row) == float_to_ordered(INFINITY)) return;
         if (tid == 0) {
             uint32_t run = 0;
             for (int l = 0; l < src.n_lists; ++l) {
@@ -96,6 +104,12 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
                 run += min(__ldg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
             }
             offs[src.n_lists] = run;
+            if (src.flag_mode == 1) {
+                const int64_t need = src.n_items < int64_t(o.k) ? src.n_items : int64_t(o.k);
+                const bool short_row = int64_t(run) < need;
+                src.thr_shared[row] = float_to_ordered(short_row ? -INFINITY : INFINITY);
+                if (short_row) atomicOr(src.mtile_flags + row / 128, 1u);
+            }
         }
         __syncthreads();
         const uint32_t total = offs[src.n_lists];
@@ -213,9 +227,11 @@ int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, i
 
 int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
                          int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
+                         int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int64_t n_items,
                          cudaStream_t stream) {
-    return launch_select(KeyLists{keys, counts, n_lists, cap}, n_rows, k, idx_offset, row_scale, out_vals,
-                         out_idx, stream);
+    if (n_lists > kMaxLists) { set_error("select_topk_keylists: %d lists per row > %d", n_lists, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
+    return launch_select(KeyLists{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, n_items}, n_rows, k,
+                         idx_offset, row_scale, out_vals, out_idx, stream);
 }
 
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,

@@ -84,6 +84,37 @@ def test_fused_adversarial_ascending_scores(eng):
     assert (i.cpu().numpy() == np.arange(10)[None, :]).all() and np.allclose(v.cpu().numpy(), K)
 
 
+def test_fused_sampled_threshold_miss_is_redone(eng):
+    # N large enough for the SAMPLE pass (every 16th item).  Items 0, 16, 32, ... score far above the rest, so
+    # the sampled threshold admits only ~j < k items: every row comes up short in MAIN and must be recovered by
+    # the REDO pass.  Also a second batch where only a few rows are hit (mixed flagged / unflagged query tiles).
+    K, N, B, k = 32, 60000, 300, 100
+    E = _rand((K, N), 7)
+    Q = _rand((B, K), 8)
+    E2 = E.clone()
+    E2[0, ::16] += 50.0
+    Q2 = Q.clone()
+    Q2[:, 0] = 1.0
+    _check(eng, Q2, E2, k)
+    Q3 = Q.clone()
+    Q3[:, 0] = 0.0
+    Q3[5, 0] = 1.0
+    Q3[131, 0] = 1.0
+    Q3[299, 0] = 1.0
+    _check(eng, Q3, E2, k)
+
+
+def test_fused_sampled_heavy_ties_and_small_k(eng):
+    # sampled path with k = 1 / 10 and with massive ties at the top (threshold admits thousands: list overflow ->
+    # in-kernel compaction), on a size where SAMPLE is active
+    K, N, B = 64, 80000, 150
+    Q, E = _rand((B, K), 11), _rand((K, N), 12)
+    _check(eng, Q, E, 1)
+    _check(eng, Q, E, 10)
+    E[:, 1000:9000] = E[:, 999:1000]                  # 8001 identical items
+    v, i = _check(eng, Q, E, 100)
+
+
 def test_fused_zero_anchor_items(eng):
     # k_i = 0 is in the reference's grid: all approximate scores are 0
     packed = eng.PackedItems(torch.zeros(0, 50).cuda(), "f32x3")
