@@ -19,7 +19,9 @@
 //   warp 0      TMA producer  (4-stage ring: Q tile 128 x 32 and E tile 256 x 32 per plane)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator 128 x 256 fp32,
 //               double-buffered in the 512 TMEM columns
-//   warps 2-5   epilogue: thread = one query row; tcgen05.ld 32 columns at a time (the next load is
+//   warps 2-9   epilogue: thread = one query row x one half of the tile's columns (two warps per TMEM
+//               lane quarter, so every scheduler has two epilogue warps to interleave); tcgen05.ld 32
+//               columns at a time (the next load is
 //               in flight while the current one is processed), compare with the row's threshold,
 //               push the rare survivors as 64-bit keys to the row's candidate list (L2-resident);
 //               if a list fills up the warp radix-selects it back to k entries and tightens the
@@ -32,7 +34,7 @@
 //   SAMPLE  every G-th item (a strided TMA view of the same packed planes, no copy) is scored and
 //           the epilogue only records the maximum of each 32-column group; the j-th largest group
 //           maximum of a row (sample_threshold_kernel) is <= the j-th best sampled score, so at
-//           least j sampled items reach it.  j is chosen so that P[Binomial(k-1, 1/G) >= j] <= 1e-8:
+//           least j sampled items reach it.  j is chosen so that P[Binomial(k-1, 1/G) >= j] <= 1e-6:
 //           then at least k items of the full row reach the threshold except with that probability,
 //           and about j*G items do (a few hundred).
 //   MAIN    all items, thresholds preloaded; survivors >= threshold are pushed.
@@ -60,7 +62,8 @@ constexpr int BLOCK_K = 32;            // 16-bit elements per k-block = 64 bytes
 constexpr int UMMA_K = 16;
 constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 8 KB
 constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, each takes half of a tile's columns
+constexpr int EPI_HALVES = NUM_EPI_WARPS / 4;
 constexpr int FUSED_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
@@ -81,8 +84,8 @@ struct FusedParams {
     int m_tiles;
     int n_tiles;
     int n_chunks;
-    uint64_t* cand;          // [n_queries][n_chunks][cap]
-    uint32_t* counts;        // [n_queries][n_chunks]
+    uint64_t* cand;          // [n_queries][n_chunks * EPI_HALVES][cap]
+    uint32_t* counts;        // [n_queries][n_chunks * EPI_HALVES]
     uint32_t* thr_shared;    // [n_queries] ordered-uint lower bound (exclusive) on useful scores
     const uint32_t* mtile_flags;   // optional [m_tiles]: work items of query tiles whose flag is 0 are skipped
     float* smax;             // MODE_SAMPLE: [n_queries][n_smax] group maxima
@@ -367,6 +370,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     } else {
         // ===================================== epilogue =========================================
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                         // which half of a tile's 32-column groups
+        constexpr int GROUPS_PER_HALF = BLOCK_N / 32 / EPI_HALVES;
+        const int n_lists = p.n_chunks * EPI_HALVES;
         uint32_t* hist = hist_all + (warp - 2) * 256;
         int buf = 0; uint32_t acc_phase = 0;
         const uint32_t k = uint32_t(p.k);
@@ -379,7 +385,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             const int row = m_tile * BLOCK_M + q * 32 + int(lane);
             const bool row_ok = row < p.n_queries;
             const int row_c = row_ok ? row : 0;
-            uint64_t* list = p.cand + (int64_t(row_c) * p.n_chunks + chunk) * int64_t(CAP);
+            uint64_t* list = p.cand + (int64_t(row_c) * n_lists + chunk * EPI_HALVES + half) * int64_t(CAP);
             float* smax_row = p.smax + int64_t(row_c) * p.n_smax;
             uint32_t cnt = 0;
             float thr_own = -INFINITY;
@@ -452,15 +458,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
                 uint32_t ra[32], rb[32];
-                tmem_ld_issue(taddr, ra);
+                const int c_begin = half * GROUPS_PER_HALF, c_end = c_begin + GROUPS_PER_HALF;
+                tmem_ld_issue(taddr + uint32_t(c_begin * 32), ra);
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                for (int c = c_begin; c < c_end; c += 2) {
                     tmem_ld_wait(ra);
                     tmem_ld_issue(taddr + uint32_t((c + 1) * 32), rb);
                     if (!sample) make_room();
                     process(ra, tile, c);
                     tmem_ld_wait(rb);
-                    if (c + 2 < BLOCK_N / 32) {
+                    if (c + 2 < c_end) {
                         tmem_ld_issue(taddr + uint32_t((c + 2) * 32), ra);
                     } else {
                         // the whole accumulator is in registers: hand the TMEM buffer back before the last group
@@ -489,7 +496,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     atomicMax(p.thr_shared + row, float_to_ordered(key_score(kth)) - 1u);
                 }
             }
-            if (row_ok) p.counts[int64_t(row) * p.n_chunks + chunk] = cnt;
+            if (row_ok) p.counts[int64_t(row) * n_lists + chunk * EPI_HALVES + half] = cnt;
         }
     }
 
@@ -525,6 +532,28 @@ __device__ __forceinline__ float pow2_scale_for(float maxabs) {
 
 __global__ void finish_scale_kernel(const uint32_t* maxabs_bits, float* scale_out, bool bf16) {
     scale_out[0] = bf16 ? 1.f : pow2_scale_for(__uint_as_float(maxabs_bits[0]));
+}
+
+// rowmax[i] = scale * max_n |E[i, n]| for every anchor dimension i (0 for the zero-padded ones): bounds the error
+// of the single-pass SAMPLE scores, see pack_queries_kernel.  One CTA per row of E.
+__global__ void __launch_bounds__(256)
+row_absmax_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int k_dim, const float* __restrict__ scale_p,
+                  float* __restrict__ rowmax) {
+    __shared__ float red[8];
+    const int i = blockIdx.x;
+    float m = 0.f;
+    if (i < k_dim)
+        for (int64_t n = threadIdx.x; n < n_items; n += blockDim.x) {
+            float x = fabsf(E[int64_t(i) * lde + n]);
+            if (x <= FLT_MAX) m = fmaxf(m, x);
+        }
+    m = warp_max_f(m);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        rowmax[i] = m * scale_p[0];
+    }
 }
 
 template <bool BF16>
@@ -568,7 +597,7 @@ __global__ void __launch_bounds__(256)
 pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int k_dim, int num_kb,
                     const float* __restrict__ e_scale, uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l,
                     float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared,
-                    uint32_t* __restrict__ mtile_flags) {
+                    uint32_t* __restrict__ mtile_flags, const float* __restrict__ e_rowmax, float* __restrict__ row_delta) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_queries) return;
     const uint32_t lane = lane_id();
@@ -582,15 +611,29 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         }
         scale = pow2_scale_for(warp_max_f(m));
     }
+    float bound = 0.f;
     for (int kb = 0; kb < num_kb; ++kb) {
         int kidx = kb * 32 + int(lane);
         float x = kidx < k_dim ? q[kidx] * scale : 0.f;
         split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
+        if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+    }
+    if (!BF16) {
+        // SAMPLE scores use the high fp16 halves only.  Each product q_i e_i is then off by q_i e_i (eps_q + eps_e)
+        // with rounding errors |eps| <= 2^-12 (std 2^-12 / sqrt 3), so a sampled score is off by a sum of K such
+        // terms: std <= 0.82 * 2^-12 * sqrt(sum_i q_i^2 max_n e_in^2) (scaled units of the accumulator).  The
+        // threshold is lowered by 2^-9 * sqrt(...) ~ 10 sigma; should that ever not be enough for a row, it ends
+        // MAIN with fewer than k candidates and the REDO pass recomputes it, so the margin is a speed knob only.
+        bound = warp_sum(bound);
+        if (lane == 0) row_delta[row] = sqrtf(bound) * (1.0f / 512.0f);
+    } else if (lane == 0) {
+        row_delta[row] = 0.f;
     }
     if (lane == 0) {
         row_inv_scale[row] = 1.f / (scale * e_scale[0]);
         thr_shared[row] = float_to_ordered(-INFINITY);
         if ((row % BLOCK_M) == 0) mtile_flags[row / BLOCK_M] = 0u;
+        if (row == 0) mtile_flags[(n_queries + BLOCK_M - 1) / BLOCK_M] = 0u;      // number of flagged rows
     }
 }
 
@@ -609,7 +652,8 @@ __global__ void fill_zero_scores_kernel(int n_queries, int k, int64_t n_items, i
 // One warp per query row: j-th largest of the row's n_smax group maxima (MSD radix select on the
 // order-preserving 32-bit image of the floats), published as the exclusive bound of the MAIN pass.
 __global__ void __launch_bounds__(256)
-sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_queries, int j, uint32_t* __restrict__ thr_shared) {
+sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_queries, int j, const float* __restrict__ row_delta,
+                        uint32_t* __restrict__ thr_shared) {
     __shared__ uint32_t hist_all[8][256];
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_queries) return;
@@ -656,7 +700,13 @@ sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_querie
     if (lane == 0) {
         // prefix = ordered image of the j-th largest maximum; scores >= it are kept (exclusive bound = it - 1)
         const uint32_t lowest = float_to_ordered(-INFINITY);
-        thr_shared[row] = (have && prefix > lowest) ? prefix - 1u : lowest;
+        uint32_t bound = lowest;
+        if (have && prefix > lowest) {
+            const float t = ordered_to_float(prefix) - row_delta[row];      // see pack_queries_kernel
+            bound = float_to_ordered(t);
+            bound = bound > lowest ? bound - 1u : lowest;
+        }
+        thr_shared[row] = bound;
     }
 }
 
@@ -749,7 +799,7 @@ struct FusedPlan {
     uint32_t cap;
     // SAMPLE pass (sample_stride == 0: not used, MAIN streams from -inf)
     int sample_stride, sample_rank, s_items, s_tiles, s_chunks, n_smax;
-    size_t off_qplanes, off_inv_scale, off_thr, off_flags, off_counts, off_cand, off_smax, off_err, total;
+    size_t off_qplanes, off_inv_scale, off_delta, off_thr, off_flags, off_counts, off_cand, off_smax, off_err, total;
 };
 
 static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
@@ -760,7 +810,7 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
     // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row
     for (int G : {16, 8, 4}) {
-        const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-8);
+        const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-6);
         const int64_t s_items = (n_items + G - 1) / G;
         const int64_t n_smax = (s_items + 31) / 32;
         if (n_smax >= 4ll * j && s_items >= 4 * BLOCK_N) {
@@ -773,12 +823,12 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     }
     const bool sampled = pl.sample_stride != 0;
     // with sampled thresholds a row keeps ~1.25 j G survivors: enough chunks that one list holds twice its share
-    const int c_min = sampled ? int((2.5 * pl.sample_rank * pl.sample_stride) / 1984.0) + 1 : 1;
+    const int c_min = sampled ? int((2.5 * pl.sample_rank * pl.sample_stride) / (1984.0 * EPI_HALVES)) + 1 : 1;
     pl.n_chunks = choose_chunks(pl.m_tiles > 0 ? pl.m_tiles : 1, pl.n_tiles > 0 ? pl.n_tiles : 1, sms, sampled ? 0.5 : 2.0, c_min);
     // list capacity: room for 2k (streaming compaction keeps k) and for twice the expected survivors of a chunk
     uint32_t want = uint32_t(2 * k);
     if (sampled) {
-        const double expect = 1.25 * pl.sample_rank * pl.sample_stride / double(pl.n_chunks);
+        const double expect = 1.25 * pl.sample_rank * pl.sample_stride / double(pl.n_chunks * EPI_HALVES);
         const uint32_t w2 = uint32_t(2.0 * expect) + 64u;
         if (w2 > want) want = w2;
     }
@@ -787,10 +837,11 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     size_t off = 0;
     pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, k_dim);
     pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
+    pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
-    pl.off_flags = off; off += align_up(sizeof(uint32_t) * size_t(pl.m_tiles > 0 ? pl.m_tiles : 1), 256);
-    pl.off_counts = off; off += align_up(sizeof(uint32_t) * size_t(n_queries) * pl.n_chunks, 256);
-    pl.off_cand = off; off += align_up(sizeof(uint64_t) * size_t(n_queries) * pl.n_chunks * pl.cap, 256);
+    pl.off_flags = off; off += align_up(sizeof(uint32_t) * (size_t(pl.m_tiles > 0 ? pl.m_tiles : 1) + 1 + size_t(n_queries)), 256);
+    pl.off_counts = off; off += align_up(sizeof(uint32_t) * size_t(n_queries) * pl.n_chunks * EPI_HALVES, 256);
+    pl.off_cand = off; off += align_up(sizeof(uint64_t) * size_t(n_queries) * pl.n_chunks * EPI_HALVES * pl.cap, 256);
     pl.off_smax = off; off += align_up(sizeof(float) * size_t(n_queries) * size_t(pl.n_smax > 0 ? pl.n_smax : 1), 256);
     pl.off_err = off; off += 256;
     pl.total = off;
@@ -799,7 +850,8 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
 
 size_t packed_items_bytes(int64_t n_items, int k_dim, int kind) {
     if (n_items <= 0 || k_dim <= 0) return 256;
-    return size_t(planes_for(kind)) * plane_bytes(n_items, k_dim) + 256;   // +256: max-abs scratch
+    // planes | 256 B max-abs scratch | per-anchor-dimension max |E| (num_kb * 32 floats)
+    return size_t(planes_for(kind)) * plane_bytes(n_items, k_dim) + 256 + align_up(sizeof(float) * size_t(num_kb_for(k_dim)) * BLOCK_K, 256);
 }
 
 int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind, void* packed, float* e_scale_out,
@@ -823,6 +875,9 @@ int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind
     }
     finish_scale_kernel<<<1, 1, 0, stream>>>(maxabs, e_scale_out, bf16);
     ANNCUR_LAUNCH_OK("finish_scale_kernel");
+    float* rowmax = reinterpret_cast<float*>(reinterpret_cast<char*>(maxabs) + 256);
+    row_absmax_kernel<<<num_kb_for(k_dim) * BLOCK_K, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, rowmax);
+    ANNCUR_LAUNCH_OK("row_absmax_kernel");
     dim3 grid(unsigned((n_items + 63) / 64), unsigned(num_kb_for(k_dim)));
     if (bf16) pack_items_kernel<true><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
     else pack_items_kernel<false><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
@@ -930,6 +985,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
     uint16_t* q_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
     float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
+    float* delta = reinterpret_cast<float*>(ws + pl.off_delta);
     uint32_t* thr = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
     uint32_t* flags = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pl.off_counts);
@@ -938,12 +994,13 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     int* err = reinterpret_cast<int*>(ws + pl.off_err);
 
     const int qgrid = (n_queries + 7) / 8;
-    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags);
-    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags);
-    ANNCUR_LAUNCH_OK("pack_queries_kernel");
-
     const size_t epb = plane_bytes(n_items, k_dim);
     const char* items = reinterpret_cast<const char*>(packed_items);
+    const float* e_rowmax = reinterpret_cast<const float*>(items + size_t(planes_for(kind)) * epb + 256);
+    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    ANNCUR_LAUNCH_OK("pack_queries_kernel");
+
     CUtensorMap a0, a1, b0, b1;
     int rc;
     if ((rc = make_plane_map(&a0, q_h, n_queries, pl.num_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
@@ -964,29 +1021,32 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err; fp.smax = smax; fp.n_smax = pl.n_smax;
 
     if (sampled) {
-        // SAMPLE: every G-th item through a strided view of the same planes -> 32-column group maxima -> thresholds
-        CUtensorMap s0, s1;
+        // SAMPLE: every G-th item through a strided view of the same planes, ONE tensor pass on the high halves
+        // (the threshold is lowered by the row's error bound) -> 32-column group maxima -> thresholds
+        CUtensorMap s0;
         if ((rc = make_plane_map(&s0, items, n_items, pl.num_kb, BLOCK_N, bf16, pl.sample_stride)) != ANNCUR_OK) return rc;
-        if (bf16) s1 = s0;
-        else if ((rc = make_plane_map(&s1, items + epb, n_items, pl.num_kb, BLOCK_N, false, pl.sample_stride)) != ANNCUR_OK) return rc;
         FusedParams sp = fp;
         sp.mode = MODE_SAMPLE; sp.n_items = pl.s_items; sp.n_tiles = pl.s_tiles; sp.n_chunks = pl.s_chunks;
-        if ((rc = launch(s0, s1, sp, false)) != ANNCUR_OK) return rc;
-        sample_threshold_kernel<<<qgrid, 256, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, thr);
+        const long long s_total = 1ll * sp.m_tiles * sp.n_chunks;
+        const int s_grid = int(s_total < sm_count() ? s_total : sm_count());
+        rc = bf16 ? launch_fused<1, true, 8>(a0, a0, s0, s0, sp, s_grid, false, stream)
+                  : launch_fused<1, false, 8>(a0, a0, s0, s0, sp, s_grid, false, stream);
+        if (rc != ANNCUR_OK) return rc;
+        sample_threshold_kernel<<<qgrid, 256, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr);
         ANNCUR_LAUNCH_OK("sample_threshold_kernel");
     }
     // MAIN
     fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
     fp.close_compact = sampled ? 0 : 1;
     if ((rc = launch(b0, b1, fp, true)) != ANNCUR_OK) return rc;
-    rc = select_topk_keylists(cand, counts, pl.n_chunks, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                              out_idx, sampled ? 1 : 0, thr, flags, n_items, stream);
+    rc = select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
+                              out_idx, sampled ? 1 : 0, thr, flags, pl.m_tiles, n_items, stream);
     if (rc != ANNCUR_OK || !sampled) return rc;
     // REDO: rows that came up short restart from -inf in streaming mode; unflagged query tiles are skipped
     fp.mtile_flags = flags; fp.close_compact = 1;
     if ((rc = launch(b0, b1, fp, false)) != ANNCUR_OK) return rc;
-    return select_topk_keylists(cand, counts, pl.n_chunks, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                                out_idx, 2, thr, flags, n_items, stream);
+    return select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
+                                out_idx, 2, thr, flags, pl.m_tiles, n_items, stream);
 }
 
 }  // namespace anncur

@@ -39,8 +39,11 @@ struct KeyLists {
     // flag_mode 2: only rows flagged by mode 1 are processed (thr_shared[row] != +inf).
     int flag_mode;
     uint32_t* thr_shared;
-    uint32_t* mtile_flags;
+    uint32_t* mtile_flags;    // [m_tiles] query-tile flags, then [1] number of flagged rows, then [n_rows] flagged rows
+    int m_tiles;
     int64_t n_items;
+    __device__ uint32_t* n_flagged() const { return mtile_flags + m_tiles; }
+    __device__ uint32_t* flagged_rows() const { return mtile_flags + m_tiles + 1; }
     __device__ int64_t size(int) const { return int64_t(n_lists) * cap; }
     __device__ uint64_t key(int row, int64_t j) const {
         int list = int(j / cap), pos = int(j % cap);
@@ -80,66 +83,16 @@ __device__ __forceinline__ void write_sorted(const uint64_t* sel, int row, const
     }
 }
 
-template <class Src>
-__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, SelectOut o) {
-    extern __shared__ __align__(16) uint64_t sel[];
+// MSD radix select of the k-th largest of M keys (get(j), j < M; 0 = padding), then the <= k winners are
+// collected into dest[0 .. n_sort) and sorted best-first.  All threads of the CTA call this.
+template <class Get>
+__device__ __forceinline__ void radix_select_collect_sort(Get get, const int64_t M, const SelectOut& o, uint64_t* dest) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_cnt;
     __shared__ uint64_t s_prefix, s_mask;
     __shared__ uint32_t s_need, s_done;
-
-    const int row = blockIdx.x;
-    const int64_t M = src.size(row);
     const int tid = threadIdx.x;
-
-    // ---- survivor lists: usually a few thousand live keys in a much larger slot space -> gather
-    //      the live ones into shared memory and sort there ------------------------------------
-    if constexpr (Src::kIsLists) {
-        __shared__ uint32_t offs[kMaxLists + 1];
-        if (src.flag_mode == 2 && __ldcg(src.thr_shared + row) == float_to_ordered(INFINITY)) return;
-        if (tid == 0) {
-            uint32_t run = 0;
-            for (int l = 0; l < src.n_lists; ++l) {
-                offs[l] = run;
-                run += min(__ldg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
-            }
-            offs[src.n_lists] = run;
-            if (src.flag_mode == 1) {
-                const int64_t need = src.n_items < int64_t(o.k) ? src.n_items : int64_t(o.k);
-                const bool short_row = int64_t(run) < need;
-                src.thr_shared[row] = float_to_ordered(short_row ? -INFINITY : INFINITY);
-                if (short_row) atomicOr(src.mtile_flags + row / 128, 1u);
-            }
-        }
-        __syncthreads();
-        const uint32_t total = offs[src.n_lists];
-        if (total <= uint32_t(kSmemSortCap)) {
-            int n_pow2 = 2;
-            while (n_pow2 < int(total) || n_pow2 < o.k) n_pow2 <<= 1;
-            for (int t = tid + int(total); t < n_pow2; t += blockDim.x) sel[t] = 0ull;
-            const int warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
-            for (int l = warp; l < src.n_lists; l += n_warps) {
-                const uint32_t base = offs[l], cnt = offs[l + 1] - offs[l];
-                const uint64_t* p = src.keys + (int64_t(row) * src.n_lists + l) * src.cap;
-                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = __ldcg(p + t);
-            }
-            block_bitonic_sort_desc(sel, n_pow2);
-            write_sorted(sel, row, o);
-            return;
-        }
-    }
-
-    // ---- small rows: everything fits in shared memory -> one sort, no radix passes -----------
-    if (M <= kSmemSortCap) {
-        int n_pow2 = 1;
-        while (n_pow2 < M || n_pow2 < o.k) n_pow2 <<= 1;
-        if (n_pow2 < 2) n_pow2 = 2;
-        for (int t = tid; t < n_pow2; t += blockDim.x) sel[t] = t < M ? src.key(row, t) : 0ull;
-        block_bitonic_sort_desc(sel, n_pow2);
-        write_sorted(sel, row, o);
-        return;
-    }
-
+    __syncthreads();
     // ---- radix select of the k-th largest key ---------------------------------------------------
     if (tid == 0) { s_prefix = 0; s_mask = 0; s_need = uint32_t(o.k); s_done = 0; s_cnt = 0; }
     for (int shift = 56; shift >= 0; shift -= 8) {
@@ -148,7 +101,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
         if (s_done) break;
         const uint64_t prefix = s_prefix, mask = s_mask;
         for (int64_t j = tid; j < M; j += blockDim.x) {
-            uint64_t key = src.key(row, j);
+            uint64_t key = get(j);
             if ((key & mask) == prefix) atomicAdd(&hist[uint32_t(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -191,31 +144,135 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
 
     // ---- collect the winners, sort them, write ----------------------------------------------------
     const uint64_t prefix = s_prefix, mask = s_mask;
-    for (int t = tid; t < o.n_sort; t += blockDim.x) sel[t] = 0ull;
+    for (int t = tid; t < o.n_sort; t += blockDim.x) dest[t] = 0ull;
     __syncthreads();
     for (int64_t j = tid; j < M; j += blockDim.x) {
-        uint64_t key = src.key(row, j);
+        uint64_t key = get(j);
         if (key != 0ull && (key & mask) >= prefix) {
             uint32_t pos = atomicAdd(&s_cnt, 1u);
-            if (pos < uint32_t(o.n_sort)) sel[pos] = key;
+            if (pos < uint32_t(o.n_sort)) dest[pos] = key;
         }
     }
     __syncthreads();
-    block_bitonic_sort_desc(sel, o.n_sort);
+    block_bitonic_sort_desc(dest, o.n_sort);
+}
+
+
+template <class Src>
+__device__ __forceinline__ void select_one_row(const Src& src, const SelectOut& o, const int row, uint64_t* sel) {
+    const int64_t M = src.size(row);
+    const int tid = threadIdx.x;
+
+    // ---- survivor lists: usually a few thousand live keys in a much larger slot space -> gather
+    //      the live ones into shared memory and sort there ------------------------------------
+    if constexpr (Src::kIsLists) {
+        __shared__ uint32_t offs[kMaxLists + 1];
+        __shared__ uint32_t warp_tot[32];
+        {   // exclusive prefix sum of the list lengths: blocked over the threads, then warp + block scan
+            const int per = (src.n_lists + int(blockDim.x) - 1) / int(blockDim.x);
+            const int l0 = tid * per, l1 = min(l0 + per, src.n_lists);
+            uint32_t local = 0;
+            for (int l = l0; l < l1; ++l) {
+                const uint32_t c = min(__ldcg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
+                offs[l] = local;                       // exclusive within this thread's block, fixed up below
+                local += c;
+            }
+            uint32_t incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((tid & 31) >= off) incl += t;
+            }
+            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t base = incl - local;
+            for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
+            for (int l = l0; l < l1; ++l) offs[l] += base;
+            if (tid == int(blockDim.x) - 1) {
+                const uint32_t run = base + local;
+                offs[src.n_lists] = run;
+                if (src.flag_mode == 1) {
+                    const int64_t need = src.n_items < int64_t(o.k) ? src.n_items : int64_t(o.k);
+                    const bool short_row = int64_t(run) < need;
+                    src.thr_shared[row] = float_to_ordered(short_row ? -INFINITY : INFINITY);
+                    if (short_row) {
+                        atomicOr(src.mtile_flags + row / 128, 1u);
+                        src.flagged_rows()[atomicAdd(src.n_flagged(), 1u)] = uint32_t(row);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t total = offs[src.n_lists];
+        if (total <= uint32_t(kSmemSortCap)) {
+            int n_pow2 = 2;
+            while (n_pow2 < int(total) || n_pow2 < o.k) n_pow2 <<= 1;
+            // many more candidates than k: select in shared memory first, sort only the winners
+            const bool select_first = n_pow2 > 2 * o.n_sort && total <= uint32_t(kSmemSortCap / 2) && o.n_sort <= kSmemSortCap / 2;
+            if (!select_first)
+                for (int t = tid + int(total); t < n_pow2; t += blockDim.x) sel[t] = 0ull;
+            const int warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+            for (int l = warp; l < src.n_lists; l += n_warps) {
+                const uint32_t base = offs[l], cnt = offs[l + 1] - offs[l];
+                const uint64_t* p = src.keys + (int64_t(row) * src.n_lists + l) * src.cap;
+                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = __ldcg(p + t);
+            }
+            if (select_first) {
+                uint64_t* dest = sel + kSmemSortCap / 2;
+                radix_select_collect_sort([&](int64_t j) { return sel[j]; }, int64_t(total), o, dest);
+                write_sorted(dest, row, o);
+            } else {
+                block_bitonic_sort_desc(sel, n_pow2);
+                write_sorted(sel, row, o);
+            }
+            return;
+        }
+    }
+
+    // ---- small rows: everything fits in shared memory -> one sort, no radix passes -----------
+    if (M <= kSmemSortCap) {
+        int n_pow2 = 1;
+        while (n_pow2 < M || n_pow2 < o.k) n_pow2 <<= 1;
+        if (n_pow2 < 2) n_pow2 = 2;
+        for (int t = tid; t < n_pow2; t += blockDim.x) sel[t] = t < M ? src.key(row, t) : 0ull;
+        block_bitonic_sort_desc(sel, n_pow2);
+        write_sorted(sel, row, o);
+        return;
+    }
+
+    // ---- large rows: radix select from the source, then sort the winners --------------------------
+    radix_select_collect_sort([&](int64_t j) { return src.key(row, j); }, M, o, sel);
     write_sorted(sel, row, o);
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, SelectOut o) {
+    extern __shared__ __align__(16) uint64_t sel[];
+    if constexpr (Src::kIsLists) {
+        if (src.flag_mode == 2) {                      // persistent over the (normally empty) list of flagged rows
+            const uint32_t n = __ldcg(src.n_flagged());
+            for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+                select_one_row(src, o, int(__ldcg(src.flagged_rows() + i)), sel);
+                __syncthreads();
+            }
+            return;
+        }
+    }
+    select_one_row(src, o, int(blockIdx.x), sel);
 }
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <class Src>
 static int launch_select(const Src& src, int n_rows, int k, int64_t idx_offset, const float* row_scale,
-                         float* out_vals, int64_t* out_idx, cudaStream_t stream) {
+                         float* out_vals, int64_t* out_idx, cudaStream_t stream, int threads = kSelectThreads,
+                         int grid = 0) {
     if (n_rows == 0) return ANNCUR_OK;
     SelectOut o{out_vals, out_idx, idx_offset, row_scale, k, next_pow2(k < 2 ? 2 : k)};
     size_t smem = sizeof(uint64_t) * size_t(o.n_sort > kSmemSortCap ? o.n_sort : kSmemSortCap);
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(select_topk_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(smem)));
-    select_topk_kernel<Src><<<n_rows, kSelectThreads, smem, stream>>>(src, o);
+    select_topk_kernel<Src><<<grid > 0 ? grid : n_rows, threads, smem, stream>>>(src, o);
     ANNCUR_LAUNCH_OK("select_topk_kernel");
     return ANNCUR_OK;
 }
@@ -227,11 +284,13 @@ int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, i
 
 int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
                          int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
-                         int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int64_t n_items,
+                         int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int m_tiles, int64_t n_items,
                          cudaStream_t stream) {
     if (n_lists > kMaxLists) { set_error("select_topk_keylists: %d lists per row > %d", n_lists, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
-    return launch_select(KeyLists{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, n_items}, n_rows, k,
-                         idx_offset, row_scale, out_vals, out_idx, stream);
+    // a row's live candidates are few (hundreds): 128 threads per row; the REDO select is persistent over flagged rows
+    const int grid = flag_mode == 2 ? (n_rows < 2 * sm_count() ? n_rows : 2 * sm_count()) : 0;
+    return launch_select(KeyLists{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, m_tiles, n_items}, n_rows, k,
+                         idx_offset, row_scale, out_vals, out_idx, stream, 128, grid);
 }
 
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,

@@ -350,23 +350,30 @@ def main():
     qps = units / (ms_total * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI entry ----------------------------------------------
+    # Three streams, each with its own workspace and pinned result buffers, so that the H2D copy of one batch and the
+    # D2H copy of another overlap the kernels of a third (the calls are asynchronous; every step still moves its
+    # own query batch in and its own result out inside the timed region).
+    N_SLOTS = 3
     Qh = [b.cpu().pin_memory() for b in batches]
-    vh = [torch.empty((B, k), dtype=torch.float32).pin_memory() for _ in range(2)]
-    ih = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(2)]
+    vh = [torch.empty((B, k), dtype=torch.float32).pin_memory() for _ in range(N_SLOTS)]
+    ih = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(N_SLOTS)]
+    streams = [torch.cuda.Stream(device=device) for _ in range(N_SLOTS)]
+    q_stage = [torch.empty_like(batches[0]) for _ in range(N_SLOTS)]
 
     def step_e2e(j):
-        if index is not None:
-            # item-sharded: H2D of the (replicated) batch, collective search, D2H of the merged result on every rank
-            q = batches[j % N_BATCHES]
-            q.copy_(Qh[j % N_BATCHES], non_blocking=True)
-            v, i = index.search(q, k)
-            vh[j % 2].copy_(v, non_blocking=True)
-            ih[j % 2].copy_(i, non_blocking=True)
-        else:
-            engine.search_host(Qh[j % N_BATCHES], packed, k, vh[j % 2], ih[j % 2], idx_offset=lo)
+        s = j % N_SLOTS
+        with torch.cuda.stream(streams[s]):
+            if index is not None:
+                # item-sharded: H2D of the (replicated) batch, collective search, D2H of the merged result on every rank
+                q_stage[s].copy_(Qh[j % N_BATCHES], non_blocking=True)
+                v, i = index.search(q_stage[s], k)
+                vh[s].copy_(v, non_blocking=True)
+                ih[s].copy_(i, non_blocking=True)
+            else:
+                engine.search_host(Qh[j % N_BATCHES], packed, k, vh[s], ih[s], idx_offset=lo, ws_key=f"search_host{s}")
 
     e2e_steps = args.steps
-    for j in range(3):
+    for j in range(2 * N_SLOTS):
         step_e2e(j)
     sync_all()
     t0 = time.perf_counter()
@@ -383,7 +390,7 @@ def main():
     chk_v, chk_i = engine.score_topk(batches[(e2e_steps - 1) % N_BATCHES], packed, k, idx_offset=lo) if index is None \
         else index.search(batches[(e2e_steps - 1) % N_BATCHES], k)
     torch.cuda.synchronize()
-    assert torch.equal(chk_i.cpu(), ih[(e2e_steps - 1) % 2]) and torch.equal(chk_v.cpu(), vh[(e2e_steps - 1) % 2]), \
+    assert torch.equal(chk_i.cpu(), ih[(e2e_steps - 1) % N_SLOTS]) and torch.equal(chk_v.cpu(), vh[(e2e_steps - 1) % N_SLOTS]), \
         "host-buffer result differs from the device-resident result"
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
