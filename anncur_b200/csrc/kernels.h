@@ -12,7 +12,7 @@ int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, i
 int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
                          int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
                          int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int m_tiles, int64_t n_items,
-                         cudaStream_t stream);
+                         uint32_t* big_rows, cudaStream_t stream);
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
                       int64_t* out_idx, cudaStream_t stream);
 

@@ -799,7 +799,7 @@ struct FusedPlan {
     uint32_t cap;
     // SAMPLE pass (sample_stride == 0: not used, MAIN streams from -inf)
     int sample_stride, sample_rank, s_items, s_tiles, s_chunks, n_smax;
-    size_t off_qplanes, off_inv_scale, off_delta, off_thr, off_flags, off_counts, off_cand, off_smax, off_err, total;
+    size_t off_qplanes, off_inv_scale, off_delta, off_thr, off_flags, off_big, off_counts, off_cand, off_smax, off_err, total;
 };
 
 static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
@@ -840,6 +840,7 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
     pl.off_flags = off; off += align_up(sizeof(uint32_t) * (size_t(pl.m_tiles > 0 ? pl.m_tiles : 1) + 1 + size_t(n_queries)), 256);
+    pl.off_big = off; off += align_up(sizeof(uint32_t) * (1 + size_t(n_queries)), 256);
     pl.off_counts = off; off += align_up(sizeof(uint32_t) * size_t(n_queries) * pl.n_chunks * EPI_HALVES, 256);
     pl.off_cand = off; off += align_up(sizeof(uint64_t) * size_t(n_queries) * pl.n_chunks * EPI_HALVES * pl.cap, 256);
     pl.off_smax = off; off += align_up(sizeof(float) * size_t(n_queries) * size_t(pl.n_smax > 0 ? pl.n_smax : 1), 256);
@@ -988,6 +989,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     float* delta = reinterpret_cast<float*>(ws + pl.off_delta);
     uint32_t* thr = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
     uint32_t* flags = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
+    uint32_t* big_rows = reinterpret_cast<uint32_t*>(ws + pl.off_big);
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pl.off_counts);
     uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
     float* smax = reinterpret_cast<float*>(ws + pl.off_smax);
@@ -1040,13 +1042,13 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     fp.close_compact = sampled ? 0 : 1;
     if ((rc = launch(b0, b1, fp, true)) != ANNCUR_OK) return rc;
     rc = select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                              out_idx, sampled ? 1 : 0, thr, flags, pl.m_tiles, n_items, stream);
+                              out_idx, sampled ? 1 : 0, thr, flags, pl.m_tiles, n_items, big_rows, stream);
     if (rc != ANNCUR_OK || !sampled) return rc;
     // REDO: rows that came up short restart from -inf in streaming mode; unflagged query tiles are skipped
     fp.mtile_flags = flags; fp.close_compact = 1;
     if ((rc = launch(b0, b1, fp, false)) != ANNCUR_OK) return rc;
     return select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                                out_idx, 2, thr, flags, pl.m_tiles, n_items, stream);
+                                out_idx, 2, thr, flags, pl.m_tiles, n_items, big_rows, stream);
 }
 
 }  // namespace anncur

@@ -42,6 +42,7 @@ struct KeyLists {
     uint32_t* mtile_flags;    // [m_tiles] query-tile flags, then [1] number of flagged rows, then [n_rows] flagged rows
     int m_tiles;
     int64_t n_items;
+    const uint32_t* row_list; // optional: [0] = count, then the rows to process (CTA kernel, after the warp kernel)
     __device__ uint32_t* n_flagged() const { return mtile_flags + m_tiles; }
     __device__ uint32_t* flagged_rows() const { return mtile_flags + m_tiles + 1; }
     __device__ int64_t size(int) const { return int64_t(n_lists) * cap; }
@@ -257,8 +258,177 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
             }
             return;
         }
+        if (src.row_list != nullptr) {                 // persistent over the rows the warp kernel passed on
+            const uint32_t n = __ldcg(src.row_list);
+            for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+                select_one_row(src, o, int(__ldcg(src.row_list + 1 + i)), sel);
+                __syncthreads();
+            }
+            return;
+        }
     }
     select_one_row(src, o, int(blockIdx.x), sel);
+}
+
+// ---- survivor lists, one WARP per row --------------------------------------------------------------
+// The fused kernel leaves a few hundred live keys per row spread over its lists.  A warp gathers them into
+// its slice of shared memory (coalesced per list), radix-selects the k-th largest, compacts the winners in
+// place, bitonic-sorts them and writes the row -- no block-wide barriers, so the many rows in flight on an SM
+// hide each other's memory latency.  Rows with more than kWarpSelCap live keys (streaming-mode overflow,
+// adversarial inputs) are appended to a list and handled by the CTA-per-row kernel afterwards.
+constexpr int kWarpSelCap = 1024;
+constexpr int kWarpSelWarps = 8;
+
+__global__ void __launch_bounds__(kWarpSelWarps * 32)
+select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __restrict__ big_rows /* [0] = count, then rows */) {
+    extern __shared__ __align__(16) uint64_t wsel_smem[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t* keys = wsel_smem + size_t(warp) * kWarpSelCap;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(wsel_smem + size_t(kWarpSelWarps) * kWarpSelCap) + warp * 256;
+    uint32_t* offs = reinterpret_cast<uint32_t*>(wsel_smem + size_t(kWarpSelWarps) * kWarpSelCap) + kWarpSelWarps * 256 +
+                     warp * (src.n_lists + 1);
+    const uint32_t n_sort = uint32_t(o.n_sort);
+
+    for (int row = blockIdx.x * kWarpSelWarps + warp; row < n_rows; row += gridDim.x * kWarpSelWarps) {
+        // list lengths -> exclusive offsets in shared memory (one parallel read of the counts, then a warp scan)
+        for (int l = int(lane); l < src.n_lists; l += 32)
+            offs[l + 1] = min(__ldcg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
+        __syncwarp();
+        uint32_t carry = 0;
+        for (int base = 0; base < src.n_lists; base += 32) {
+            const int l = base + int(lane);
+            const uint32_t v = l < src.n_lists ? offs[l + 1] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= uint32_t(off)) incl += t;
+            }
+            if (l < src.n_lists) offs[l + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) offs[0] = 0;
+        const uint32_t total = carry;
+        __syncwarp();
+        if (src.flag_mode == 1 && lane == 0) {
+            const int64_t need = src.n_items < int64_t(o.k) ? src.n_items : int64_t(o.k);
+            const bool short_row = int64_t(total) < need;
+            src.thr_shared[row] = float_to_ordered(short_row ? -INFINITY : INFINITY);
+            if (short_row) {
+                atomicOr(src.mtile_flags + row / 128, 1u);
+                src.flagged_rows()[atomicAdd(src.n_flagged(), 1u)] = uint32_t(row);
+            }
+        }
+        if (total > uint32_t(kWarpSelCap)) {
+            if (lane == 0) big_rows[1 + atomicAdd(big_rows, 1u)] = uint32_t(row);
+            __syncwarp();
+            continue;
+        }
+        // gather: flat element e -> (list, position) by binary search in the offsets; four loads in flight per lane
+        const uint64_t* row_keys = src.keys + int64_t(row) * src.n_lists * src.cap;
+        for (uint32_t e0 = 0; e0 < total; e0 += 128) {
+            uint64_t reg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + uint32_t(u) * 32u + lane;
+                reg[u] = 0ull;
+                if (e < total) {
+                    int lo = 0, hi = src.n_lists;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (offs[mid] <= e) lo = mid; else hi = mid;
+                    }
+                    reg[u] = __ldcg(row_keys + int64_t(lo) * src.cap + (e - offs[lo]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + uint32_t(u) * 32u + lane;
+                if (e < total) keys[e] = reg[u];
+            }
+        }
+        __syncwarp();
+        uint32_t n_win = total;
+        if (total > uint32_t(o.k)) {
+            // MSD radix select of the k-th largest key
+            uint64_t prefix = 0, mask = 0;
+            uint32_t need = uint32_t(o.k);
+            for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+                __syncwarp();
+                for (uint32_t t = lane; t < total; t += 32) {
+                    const uint64_t key = keys[t];
+                    if ((key & mask) == prefix) atomicAdd(&hist[uint32_t(key >> shift) & 255u], 1u);
+                }
+                __syncwarp();
+                uint32_t c[8], lane_sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+                uint32_t suf = lane_sum;                 // inclusive suffix sum towards the higher digits
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t t = __shfl_down_sync(0xffffffffu, suf, off);
+                    if (lane + off < 32) suf += t;
+                }
+                uint32_t running = suf - lane_sum;
+                bool found = false;
+                uint32_t d = 0, new_need = 0, bucket = 0;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) {
+                    if (!found && running + c[b] >= need) { found = true; d = lane * 8 + b; new_need = need - running; bucket = c[b]; }
+                    running += c[b];
+                }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, found);
+                __syncwarp();
+                if (ballot == 0) break;
+                const int srcl = 31 - __clz(int(ballot));
+                d = __shfl_sync(0xffffffffu, d, srcl);
+                need = __shfl_sync(0xffffffffu, new_need, srcl);
+                bucket = __shfl_sync(0xffffffffu, bucket, srcl);
+                prefix |= uint64_t(d) << shift;
+                mask |= 0xffull << shift;
+                if (bucket == need) break;               // digit bucket taken whole
+            }
+            // in-place stable compaction of the winners (write index never passes the read index)
+            uint32_t running = 0;
+            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const uint64_t key = t < total ? keys[t] : 0ull;
+                const bool keep = key != 0ull && (key & mask) >= prefix;
+                const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) keys[running + __popc(ballot & ((1u << lane) - 1u))] = key;
+                running += __popc(ballot);
+                __syncwarp();
+            }
+            n_win = running;
+        }
+        for (uint32_t t = n_win + lane; t < n_sort; t += 32) keys[t] = 0ull;
+        __syncwarp();
+        // bitonic sort, descending, of n_sort keys by one warp
+        for (uint32_t size = 2; size <= n_sort; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = lane; t < (n_sort >> 1); t += 32) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool desc = (lo & size) == 0;
+                    const uint64_t a = keys[lo], b = keys[hi];
+                    if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        const float scale = o.row_scale ? o.row_scale[row] : 1.0f;
+        for (int t = int(lane); t < o.k; t += 32) {
+            const uint64_t key = keys[t];
+            const bool ok = key != 0ull;
+            o.vals[int64_t(row) * o.k + t] = ok ? key_score(key) * scale : ANNCUR_PAD_VAL;
+            o.idx[int64_t(row) * o.k + t] = ok ? int64_t(key_index(key)) + o.idx_offset : int64_t(-1);
+        }
+        __syncwarp();
+    }
 }
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -285,12 +455,28 @@ int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, i
 int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
                          int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
                          int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int m_tiles, int64_t n_items,
-                         cudaStream_t stream) {
+                         uint32_t* big_rows, cudaStream_t stream) {
     if (n_lists > kMaxLists) { set_error("select_topk_keylists: %d lists per row > %d", n_lists, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
-    // a row's live candidates are few (hundreds): 128 threads per row; the REDO select is persistent over flagged rows
-    const int grid = flag_mode == 2 ? (n_rows < 2 * sm_count() ? n_rows : 2 * sm_count()) : 0;
-    return launch_select(KeyLists{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, m_tiles, n_items}, n_rows, k,
-                         idx_offset, row_scale, out_vals, out_idx, stream, 128, grid);
+    if (n_rows == 0) return ANNCUR_OK;
+    KeyLists src{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, m_tiles, n_items, nullptr};
+    if (flag_mode == 2) {
+        // REDO select: persistent CTA kernel over the (normally empty) list of flagged rows
+        const int grid = n_rows < 2 * sm_count() ? n_rows : 2 * sm_count();
+        return launch_select(src, n_rows, k, idx_offset, row_scale, out_vals, out_idx, stream, 128, grid);
+    }
+    // one warp per row; rows with too many live keys are passed on to the CTA kernel through big_rows
+    SelectOut o{out_vals, out_idx, idx_offset, row_scale, k, next_pow2(k < 2 ? 2 : k)};
+    ANNCUR_CUDA_OK(cudaMemsetAsync(big_rows, 0, sizeof(uint32_t), stream));
+    const size_t smem = size_t(kWarpSelWarps) * (kWarpSelCap * sizeof(uint64_t) + (256 + size_t(n_lists) + 1) * sizeof(uint32_t));
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(select_lists_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int grid = (n_rows + kWarpSelWarps - 1) / kWarpSelWarps;
+    if (grid > 3 * sm_count()) grid = 3 * sm_count();
+    select_lists_warp_kernel<<<grid, kWarpSelWarps * 32, smem, stream>>>(src, o, n_rows, big_rows);
+    ANNCUR_LAUNCH_OK("select_lists_warp_kernel");
+    src.flag_mode = 0;                                  // flags were written by the warp kernel
+    src.row_list = big_rows;
+    const int grid2 = n_rows < 2 * sm_count() ? n_rows : 2 * sm_count();
+    return launch_select(src, n_rows, k, idx_offset, row_scale, out_vals, out_idx, stream, 128, grid2);
 }
 
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,

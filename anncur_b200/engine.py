@@ -49,7 +49,8 @@ class _Workspace:
         self._bufs = {}
 
     def get(self, key, nbytes, device):
-        k = (key, device.index)
+        # one buffer per (purpose, device, stream): calls issued on different streams may run concurrently
+        k = (key, device.index, torch.cuda.current_stream(device).cuda_stream)
         buf = self._bufs.get(k)
         if buf is None or buf.numel() < nbytes:
             buf = None

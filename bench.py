@@ -53,6 +53,15 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi fields of the profiling recipe, read through NVML)
 # ---------------------------------------------------------------------------------------------------
@@ -241,7 +250,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world, shard):
@@ -469,7 +478,7 @@ def main():
                                 "gpu_vs_cpu_check": {"index_agreement": same, "max_rel_score_err_sorted_lists": rel}}
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
