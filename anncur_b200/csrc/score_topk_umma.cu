@@ -68,9 +68,11 @@ constexpr int FUSED_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
 
-template <int PASSES> struct StageCfg {
-    static constexpr int kStageBytes = PASSES == 3 ? 2 * (A_PLANE_BYTES + B_PLANE_BYTES) : (A_PLANE_BYTES + B_PLANE_BYTES);
-    static constexpr int kStages = PASSES == 3 ? 4 : 8;
+// CG = CTAs per MMA (1, or 2 = CTA pair: each CTA stages its own 128 queries and HALF of the 256-item tile)
+template <int PASSES, int CG> struct StageCfg {
+    static constexpr int kBBytes = B_PLANE_BYTES / CG;
+    static constexpr int kStageBytes = PASSES == 3 ? 2 * (A_PLANE_BYTES + kBBytes) : (A_PLANE_BYTES + kBBytes);
+    static constexpr int kStages = PASSES == 3 ? (CG == 2 ? 6 : 4) : (CG == 2 ? 10 : 8);
 };
 
 enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
@@ -129,6 +131,38 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// ---- CTA-pair (cta_group::2) forms.  Inside a pair a shared::cluster address with bit 24 cleared names the
+//      same offset in the even (leader) CTA's shared memory.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {          // arrive on the leader CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    // data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {           // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(uint16_t(3)) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -243,12 +277,12 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, uint32_t n
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int PASSES, bool BF16, int CPL>
+template <int PASSES, bool BF16, int CPL, int CG>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                         const FusedParams p) {
-    using Cfg = StageCfg<PASSES>;
+    using Cfg = StageCfg<PASSES, CG>;
     constexpr int NS = Cfg::kStages;
     constexpr uint32_t CAP = uint32_t(CPL) * 32u;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -275,46 +309,72 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
         }
-        for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS); }
+        // full: the leader's copy collects one arrival per CTA of the pair plus all TMA bytes; empty / tmem_full:
+        // one tcgen05.commit (multicast to both CTAs); tmem_empty: the leader's copy collects the epilogue warps
+        // of both CTAs
+        for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), CG * NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
-    const int total_items = p.n_chunks * p.m_tiles;
-    // a work item is skipped by all three roles when its query tile is not flagged (REDO launch only)
-    auto item_live = [&](int m_tile) { return p.mtile_flags == nullptr || __ldg(p.mtile_flags + m_tile) != 0u; };
+    // A CTA pair works on two adjacent query tiles (one per CTA) against the same item tiles.
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int unit = int(blockIdx.x) / CG, n_units = int(gridDim.x) / CG;          // CTA (pair) index / count
+    const int m_groups = (p.m_tiles + CG - 1) / CG;
+    const int total_items = p.n_chunks * m_groups;
+    // a work item is skipped by all roles (of both CTAs) when none of its query tiles is flagged (REDO launch only)
+    auto item_live = [&](int m_group) {
+        if (p.mtile_flags == nullptr) return true;
+        bool live = false;
+        for (int r = 0; r < CG; ++r) {
+            const int mt = m_group * CG + r;
+            if (mt < p.m_tiles && __ldg(p.mtile_flags + mt) != 0u) live = true;
+        }
+        return live;
+    };
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-                const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
-                if (!item_live(m_tile)) continue;
+            auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c1, int kb) {
+                if (CG == 2) tma_load_3d_pair(dst, map, bar, 0, c1, kb); else tma_load_3d(dst, map, bar, 0, c1, kb);
+            };
+            for (int w = unit; w < total_items; w += n_units) {
+                const int chunk = w / m_groups, m_tile = (w % m_groups) * CG + int(cta_rank);
+                if (!item_live(w % m_groups)) continue;
                 const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
+                    const int item0 = tile * BLOCK_N + int(cta_rank) * (BLOCK_N / CG);     // this CTA's share of the item tile
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag);
                         const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes;
-                        mbar_expect_tx(full_bar(stage), uint32_t(Cfg::kStageBytes));
+                        if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * Cfg::kStageBytes));
                         if (PASSES == 3) {
-                            tma_load_3d(sb, &tmA0, full_bar(stage), 0, m_tile * BLOCK_M, kb);
-                            tma_load_3d(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), 0, m_tile * BLOCK_M, kb);
-                            tma_load_3d(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), 0, tile * BLOCK_N, kb);
-                            tma_load_3d(sb + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &tmB1, full_bar(stage), 0, tile * BLOCK_N, kb);
+                            load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                            load(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), m_tile * BLOCK_M, kb);
+                            load(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
+                            load(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes, &tmB1, full_bar(stage), item0, kb);
                         } else {
-                            tma_load_3d(sb, &tmA0, full_bar(stage), 0, m_tile * BLOCK_M, kb);
-                            tma_load_3d(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), 0, tile * BLOCK_N, kb);
+                            load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                            load(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
                         }
+                        if (!leader) mbar_arrive_leader(full_bar(stage));
                         if (++stage == NS) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -322,15 +382,19 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            // instruction descriptor: D fp32, A/B f16 or bf16, both K-major, N = 256, M = 128
+        if (lane == 0 && leader) {
+            // instruction descriptor: D fp32, A/B f16 or bf16, both K-major, N = 256, M = 128 per CTA
             const uint32_t fmt = BF16 ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((BLOCK_M * CG) >> 4) << 24);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (CG == 2) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); };
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-                const int chunk = w / p.m_tiles;
-                if (!item_live(w % p.m_tiles)) continue;
+            for (int w = unit; w < total_items; w += n_units) {
+                const int chunk = w / m_groups;
+                if (!item_live(w % m_groups)) continue;
                 const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
@@ -349,20 +413,20 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                                 const uint64_t a_h = make_smem_desc_sw64(sb + koff);
                                 const uint64_t a_l = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
                                 const uint64_t b_h = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + koff);
-                                const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + B_PLANE_BYTES + koff);
-                                umma_f16(d_tmem, a_h, b_h, idesc, accum);
-                                umma_f16(d_tmem, a_h, b_l, idesc, 1u);
-                                umma_f16(d_tmem, a_l, b_h, idesc, 1u);
+                                const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
+                                mma(d_tmem, a_h, b_h, accum);
+                                mma(d_tmem, a_h, b_l, 1u);
+                                mma(d_tmem, a_l, b_h, 1u);
                             } else {
                                 const uint64_t a = make_smem_desc_sw64(sb + koff);
                                 const uint64_t b = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
-                                umma_f16(d_tmem, a, b, idesc, accum);
+                                mma(d_tmem, a, b, accum);
                             }
                         }
-                        umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                        commit(empty_bar(stage));                      // smem slot free (in both CTAs) once these MMAs retire
                         if (++stage == NS) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(tfull_bar(buf));                       // accumulator ready for the epilogue
+                    commit(tfull_bar(buf));                            // accumulator ready for the epilogue (of both CTAs)
                     if (++buf == 2) { buf = 0; acc_phase ^= 1u; }
                 }
             }
@@ -377,9 +441,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         int buf = 0; uint32_t acc_phase = 0;
         const uint32_t k = uint32_t(p.k);
         const bool sample = p.mode == MODE_SAMPLE;
-        for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-            const int chunk = w / p.m_tiles, m_tile = w % p.m_tiles;
-            if (!item_live(m_tile)) continue;
+        for (int w = unit; w < total_items; w += n_units) {
+            const int chunk = w / m_groups, m_tile = (w % m_groups) * CG + int(cta_rank);
+            if (!item_live(w % m_groups)) continue;
             const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
             const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
             const int row = m_tile * BLOCK_M + q * 32 + int(lane);
@@ -473,7 +537,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                         // the whole accumulator is in registers: hand the TMEM buffer back before the last group
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(buf));
+                        if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(buf)); else mbar_arrive(tempty_bar(buf)); }
                     }
                     if (!sample) make_room();
                     process(rb, tile, c + 1);
@@ -501,10 +565,11 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -794,6 +859,8 @@ static int binomial_tail_rank(int n, double p, double eps) {
     return j < 1 ? 1 : j;
 }
 
+static int cta_group_for(int m_tiles);
+
 struct FusedPlan {
     int num_kb, m_tiles, n_tiles, n_chunks;
     uint32_t cap;
@@ -808,6 +875,9 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     pl.num_kb = num_kb_for(k_dim);
     pl.m_tiles = (n_queries + BLOCK_M - 1) / BLOCK_M;
     pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
+    const int cg = cta_group_for(pl.m_tiles);                 // work is scheduled over CTA pairs when cg == 2
+    const int units = sms / cg > 0 ? sms / cg : 1;
+    const int m_groups = pl.m_tiles > 0 ? (pl.m_tiles + cg - 1) / cg : 1;
     // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row
     for (int G : {16, 8, 4}) {
         const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-6);
@@ -817,14 +887,14 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
             pl.sample_stride = G; pl.sample_rank = j; pl.s_items = int(s_items);
             pl.s_tiles = int((s_items + BLOCK_N - 1) / BLOCK_N);
             pl.n_smax = pl.s_tiles * (BLOCK_N / 32);
-            pl.s_chunks = choose_chunks(pl.m_tiles, pl.s_tiles, sms, 0.25);
+            pl.s_chunks = choose_chunks(m_groups, pl.s_tiles, units, 0.25);
             break;
         }
     }
     const bool sampled = pl.sample_stride != 0;
     // with sampled thresholds a row keeps ~1.25 j G survivors: enough chunks that one list holds twice its share
     const int c_min = sampled ? int((2.5 * pl.sample_rank * pl.sample_stride) / (1984.0 * EPI_HALVES)) + 1 : 1;
-    pl.n_chunks = choose_chunks(pl.m_tiles > 0 ? pl.m_tiles : 1, pl.n_tiles > 0 ? pl.n_tiles : 1, sms, sampled ? 0.5 : 2.0, c_min);
+    pl.n_chunks = choose_chunks(m_groups, pl.n_tiles > 0 ? pl.n_tiles : 1, units, sampled ? 0.5 : 2.0, c_min);
     // list capacity: room for 2k (streaming compaction keeps k) and for twice the expected survivors of a chunk
     uint32_t want = uint32_t(2 * k);
     if (sampled) {
@@ -925,12 +995,17 @@ int profile_read(double* ms_sum, int* launches) {
     return ANNCUR_OK;
 }
 
-template <int PASSES, bool BF16, int CPL>
+template <int PASSES, bool BF16, int CPL, int CG>
 static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-                        const FusedParams& fp, int grid, bool timed, cudaStream_t stream) {
-    using Cfg = StageCfg<PASSES>;
+                        const FusedParams& fp, bool timed, cudaStream_t stream) {
+    using Cfg = StageCfg<PASSES, CG>;
     const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4;
-    ANNCUR_CUDA_OK(cudaFuncSetAttribute(fused_score_topk_kernel<PASSES, BF16, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kernel = fused_score_topk_kernel<PASSES, BF16, CPL, CG>;
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // persistent: one CTA (pair) per SM (pair), never more CTAs than work items
+    const long long units = 1ll * ((fp.m_tiles + CG - 1) / CG) * fp.n_chunks;
+    const long long max_units = sm_count() / CG;
+    const int grid = int(units < max_units ? units : max_units) * CG;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     timed = timed && g_prof.on;
     if (timed) {
@@ -938,7 +1013,17 @@ static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
         ANNCUR_CUDA_OK(cudaEventCreate(&ev1));
         ANNCUR_CUDA_OK(cudaEventRecord(ev0, stream));
     }
-    fused_score_topk_kernel<PASSES, BF16, CPL><<<grid, FUSED_THREADS, smem, stream>>>(a0, a1, b0, b1, fp);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(FUSED_THREADS);
+    cfg.dynamicSmemBytes = size_t(smem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ANNCUR_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, fp));
     ANNCUR_LAUNCH_OK("fused_score_topk_kernel");
     if (timed) {
         ANNCUR_CUDA_OK(cudaEventRecord(ev1, stream));
@@ -947,17 +1032,28 @@ static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
     return ANNCUR_OK;
 }
 
-template <int PASSES, bool BF16>
+template <int PASSES, bool BF16, int CG>
 static int dispatch_cap(uint32_t cap, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                        const CUtensorMap& b1, const FusedParams& fp, int grid, bool timed, cudaStream_t stream) {
+                        const CUtensorMap& b1, const FusedParams& fp, bool timed, cudaStream_t stream) {
     switch (cap) {
-        case 256: return launch_fused<PASSES, BF16, 8>(a0, a1, b0, b1, fp, grid, timed, stream);
-        case 512: return launch_fused<PASSES, BF16, 16>(a0, a1, b0, b1, fp, grid, timed, stream);
-        case 1024: return launch_fused<PASSES, BF16, 32>(a0, a1, b0, b1, fp, grid, timed, stream);
-        case 2048: return launch_fused<PASSES, BF16, 64>(a0, a1, b0, b1, fp, grid, timed, stream);
+        case 256: return launch_fused<PASSES, BF16, 8, CG>(a0, a1, b0, b1, fp, timed, stream);
+        case 512: return launch_fused<PASSES, BF16, 16, CG>(a0, a1, b0, b1, fp, timed, stream);
+        case 1024: return launch_fused<PASSES, BF16, 32, CG>(a0, a1, b0, b1, fp, timed, stream);
+        case 2048: return launch_fused<PASSES, BF16, 64, CG>(a0, a1, b0, b1, fp, timed, stream);
     }
     set_error("score_topk: no kernel for candidate capacity %u", cap);
     return ANNCUR_E_UNSUPPORTED;
+}
+
+// CTAs per MMA: pairs (cta_group::2) whenever there are at least two query tiles to pair up.
+// ANNCUR_CTA_GROUP=1|2 overrides (testing).
+static int cta_group_for(int m_tiles) {
+    static int forced = [] {
+        const char* e = getenv("ANNCUR_CTA_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 1 || forced == 2) return forced;
+    return m_tiles >= 2 ? 2 : 1;
 }
 
 int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
@@ -1003,20 +1099,23 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
     ANNCUR_LAUNCH_OK("pack_queries_kernel");
 
+    const int cg = cta_group_for(pl.m_tiles);
+    const int b_box = BLOCK_N / cg;                       // a CTA of a pair stages half of each item tile
     CUtensorMap a0, a1, b0, b1;
     int rc;
     if ((rc = make_plane_map(&a0, q_h, n_queries, pl.num_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
-    if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, BLOCK_N, bf16)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, b_box, bf16)) != ANNCUR_OK) return rc;
     if (bf16) { a1 = a0; b1 = b0; }
     else {
         if ((rc = make_plane_map(&a1, q_l, n_queries, pl.num_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
-        if ((rc = make_plane_map(&b1, items + epb, n_items, pl.num_kb, BLOCK_N, false)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&b1, items + epb, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
     }
     auto launch = [&](const CUtensorMap& mb0, const CUtensorMap& mb1, const FusedParams& fp, bool timed) {
-        const long long items_total = 1ll * fp.m_tiles * fp.n_chunks;
-        const int grid = int(items_total < sm_count() ? items_total : sm_count());
-        return bf16 ? dispatch_cap<1, true>(pl.cap, a0, a1, mb0, mb1, fp, grid, timed, stream)
-                    : dispatch_cap<3, false>(pl.cap, a0, a1, mb0, mb1, fp, grid, timed, stream);
+        if (cg == 2)
+            return bf16 ? dispatch_cap<1, true, 2>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream)
+                        : dispatch_cap<3, false, 2>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream);
+        return bf16 ? dispatch_cap<1, true, 1>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream)
+                    : dispatch_cap<3, false, 1>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream);
     };
     FusedParams fp{};
     fp.n_queries = n_queries; fp.num_kb = pl.num_kb; fp.k = k; fp.m_tiles = pl.m_tiles;
@@ -1026,13 +1125,13 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         // SAMPLE: every G-th item through a strided view of the same planes, ONE tensor pass on the high halves
         // (the threshold is lowered by the row's error bound) -> 32-column group maxima -> thresholds
         CUtensorMap s0;
-        if ((rc = make_plane_map(&s0, items, n_items, pl.num_kb, BLOCK_N, bf16, pl.sample_stride)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&s0, items, n_items, pl.num_kb, b_box, bf16, pl.sample_stride)) != ANNCUR_OK) return rc;
         FusedParams sp = fp;
         sp.mode = MODE_SAMPLE; sp.n_items = pl.s_items; sp.n_tiles = pl.s_tiles; sp.n_chunks = pl.s_chunks;
-        const long long s_total = 1ll * sp.m_tiles * sp.n_chunks;
-        const int s_grid = int(s_total < sm_count() ? s_total : sm_count());
-        rc = bf16 ? launch_fused<1, true, 8>(a0, a0, s0, s0, sp, s_grid, false, stream)
-                  : launch_fused<1, false, 8>(a0, a0, s0, s0, sp, s_grid, false, stream);
+        if (cg == 2) rc = bf16 ? launch_fused<1, true, 8, 2>(a0, a0, s0, s0, sp, false, stream)
+                               : launch_fused<1, false, 8, 2>(a0, a0, s0, s0, sp, false, stream);
+        else rc = bf16 ? launch_fused<1, true, 8, 1>(a0, a0, s0, s0, sp, false, stream)
+                       : launch_fused<1, false, 8, 1>(a0, a0, s0, s0, sp, false, stream);
         if (rc != ANNCUR_OK) return rc;
         sample_threshold_kernel<<<qgrid, 256, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr);
         ANNCUR_LAUNCH_OK("sample_threshold_kernel");
