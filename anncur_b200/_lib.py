@@ -19,6 +19,7 @@ PROTOTYPES = {
     "anncur_last_error": (C.c_char_p, []),
     "anncur_pinv_workspace_bytes": (_sz, [_i, _i]),
     "anncur_pinv_f32": (_i, [_vp, _i, _i, _i, _d, _vp, _i, _vp, _vp, _sz, _vp]),
+    "anncur_singular_values_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "anncur_gemm_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "anncur_packed_items_bytes": (_sz, [_i64, _i, _i]),
     "anncur_pack_items": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),

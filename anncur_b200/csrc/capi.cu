@@ -62,6 +62,15 @@ int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* 
     return pinv_f32(A, m, n, lda, rcond, out, ldo, cond_out, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(m >= 0 && n >= 0, "singular_values: negative shape %d x %d", m, n);
+    if (m == 0 || n == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(A && sigma_out && workspace, "singular_values: null pointer");
+    ANNCUR_REQUIRE(lda >= n, "singular_values: lda %d < n %d", lda, n);
+    return singular_values_f32(A, m, n, lda, sigma_out, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
 int anncur_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int m, int n, int k,
                     void* stream) {
     ANNCUR_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative shape");

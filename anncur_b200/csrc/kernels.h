@@ -26,6 +26,8 @@ int recon_error(const float* Q, int64_t ldq, const float* E, int64_t lde, const 
 size_t pinv_workspace_bytes(int m, int n);
 int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 
 // rerank.cu
 int rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,

@@ -185,6 +185,17 @@ pinv_compose_kernel(const double* __restrict__ V, const double* __restrict__ G, 
     }
 }
 
+// sigma_j = |g_j| (unsorted), one warp per column
+__global__ void jacobi_sigma_kernel(const double* __restrict__ G, int len, int p, double* __restrict__ sigma) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= p) return;
+    const double* g = G + int64_t(j) * len;
+    double a = 0.0;
+    for (int r = lane_id(); r < len; r += 32) a = fma(g[r], g[r], a);
+    a = warp_sum(a);
+    if (lane_id() == 0) sigma[j] = sqrt(a);
+}
+
 __global__ void pinv_export_cond_kernel(const JacobiState* st, double* cond_out) {
     cond_out[0] = st->s_max;
     cond_out[1] = st->s_min_kept;
@@ -196,9 +207,7 @@ size_t pinv_workspace_bytes(int m, int n) {
     return align_up(sizeof(double) * (len * p + p * p + p), 256) + 256;
 }
 
-int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
-             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (m <= 0 || n <= 0) return ANNCUR_OK;   // empty anchor set: pinv is the empty n x m matrix
+static int jacobi_factor(const float* A, int m, int n, int lda, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (workspace_bytes < pinv_workspace_bytes(m, n)) {
         set_error("pinv workspace too small: %zu < %zu", workspace_bytes, pinv_workspace_bytes(m, n));
         return ANNCUR_E_WORKSPACE;
@@ -208,7 +217,6 @@ int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, in
     JacobiState* st = reinterpret_cast<JacobiState*>(workspace);
     double* G = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
     double* V = G + size_t(len) * p;
-    double* w = V + size_t(p) * p;
 
     jacobi_init_kernel<<<sm_count() * 4, 256, 0, stream>>>(A, m, n, lda, len, p, tall, G, V, st);
     ANNCUR_LAUNCH_OK("jacobi_init_kernel");
@@ -224,6 +232,20 @@ int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, in
             ANNCUR_LAUNCH_OK("jacobi_sweep_end_kernel");
         }
     }
+    return ANNCUR_OK;
+}
+
+int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return ANNCUR_OK;   // empty anchor set: pinv is the empty n x m matrix
+    int rc = jacobi_factor(A, m, n, lda, workspace, workspace_bytes, stream);
+    if (rc != ANNCUR_OK) return rc;
+    const bool tall = m >= n;
+    const int len = tall ? m : n, p = tall ? n : m;
+    JacobiState* st = reinterpret_cast<JacobiState*>(workspace);
+    double* G = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+    double* V = G + size_t(len) * p;
+    double* w = V + size_t(p) * p;
     jacobi_weights_kernel<<<1, JAC_THREADS, 0, stream>>>(G, len, p, rcond, w, st);
     ANNCUR_LAUNCH_OK("jacobi_weights_kernel");
     dim3 grid((len + PT - 1) / PT, (p + PT - 1) / PT);
@@ -234,6 +256,20 @@ int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, in
         pinv_export_cond_kernel<<<1, 1, 0, stream>>>(st, cond_out);
         ANNCUR_LAUNCH_OK("pinv_export_cond_kernel");
     }
+    return ANNCUR_OK;
+}
+
+// Singular values of A (m x n fp32) in fp64, unsorted: the same Jacobi factorisation without the inverse.
+// Replaces the SVD inside np.linalg.matrix_rank (eval/compute_m2e_matrix_ranks.py:44-53).
+int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return ANNCUR_OK;
+    int rc = jacobi_factor(A, m, n, lda, workspace, workspace_bytes, stream);
+    if (rc != ANNCUR_OK) return rc;
+    const int len = m >= n ? m : n, p = m >= n ? n : m;
+    const double* G = reinterpret_cast<const double*>(reinterpret_cast<const char*>(workspace) + 256);
+    jacobi_sigma_kernel<<<(p + 7) / 8, 256, 0, stream>>>(G, len, p, sigma_out);
+    ANNCUR_LAUNCH_OK("jacobi_sigma_kernel");
     return ANNCUR_OK;
 }
 

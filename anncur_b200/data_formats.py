@@ -1,0 +1,142 @@
+"""On-disk formats either side of the search path, host-side only:
+
+* the cross-encoder score-matrix pickle            eval/run_cross_encoder_for_ment_ent_matrix_zeshel.py:230-240
+* its train / train_train / train_dev / test splits  utils/split_zeshel_ment2ent_for_cur_exps.py:25-129 (adds ``ment_idxs``)
+* the retrieval / anchor grids of the fixed-split eval  eval/run_retrieval_eval_wrt_exact_crossenc_w_fixed_train_test_splits.py:238-251
+* the result JSON                                   ..._w_fixed_train_test_splits.py:429, :494-500
+
+so that real ZeShEL matrices produced by the reference feed this engine and the reference's compile / plot
+scripts read what it writes.  Nothing here computes scores; ``run_cur_method`` hands the matrices to
+``eval_retrieval.fixed_split_cur_eval`` (GPU)."""
+import json
+import os
+import pickle
+from pathlib import Path
+
+import numpy as np
+import torch
+
+M2E_KEYS = ("ment_to_ent_scores", "test_data", "mention_tokens_list", "entity_id_list", "entity_tokens_list", "arg_dict")
+SPLIT_NAMES = ("train_dev", "train_train", "train", "test")          # order in which the reference writes them
+
+
+def make_m2e_dict(ment_to_ent_scores, test_data, mention_tokens_list, entity_id_list=(), entity_tokens_list=(),
+                  arg_dict=None, ment_idxs=None):
+    """The dict the reference pickles (:230-240); ``ment_idxs`` only in split files (split script :35-43)."""
+    scores = torch.as_tensor(ment_to_ent_scores)
+    d = {"ment_to_ent_scores": scores, "ment_to_ent_scores.shape": scores.shape, "test_data": list(test_data),
+         "mention_tokens_list": list(mention_tokens_list), "entity_id_list": list(entity_id_list),
+         "entity_tokens_list": list(entity_tokens_list), "arg_dict": dict(arg_dict or {})}
+    if ment_idxs is not None:
+        d.pop("ment_to_ent_scores.shape")
+        d["ment_idxs"] = list(ment_idxs)
+    return d
+
+
+def save_m2e_pickle(path, m2e_dict):
+    Path(os.path.dirname(os.path.abspath(path))).mkdir(exist_ok=True, parents=True)
+    with open(path, "wb") as fout:
+        pickle.dump(m2e_dict, fout)
+
+
+def load_m2e_pickle(path, require_ment_idxs=False):
+    """Read a score-matrix pickle written by the reference (or by ``save_m2e_pickle``).  The matrix comes back
+    as a CPU fp32 torch tensor whatever it was stored as; the other fields are passed through."""
+    with open(path, "rb") as fin:
+        d = pickle.load(fin)
+    missing = [k for k in M2E_KEYS if k not in d]
+    if missing:
+        raise KeyError(f"{path}: not a ment_to_ent score dump, missing keys {missing}")
+    if require_ment_idxs and "ment_idxs" not in d:
+        raise KeyError(f"{path}: split files carry 'ment_idxs' (utils/split_zeshel_ment2ent_for_cur_exps.py:39)")
+    scores = d["ment_to_ent_scores"]
+    scores = scores if torch.is_tensor(scores) else torch.as_tensor(np.asarray(scores))
+    d["ment_to_ent_scores"] = scores.detach().to("cpu", torch.float32)
+    assert d["ment_to_ent_scores"].dim() == 2
+    return d
+
+
+def split_indices(n_ments, num_train_ment_vals, num_splits, seed, dev_frac):
+    """The index sets of utils/split_zeshel_ment2ent_for_cur_exps.py:80-92 with its exact RNG call order (ONE
+    generator; per (num_train, split): train draw, then the train-dev draw).  Yields
+    (num_train_ments, split_iter, {"train", "test", "train_dev", "train_train"} -> sorted index lists)."""
+    assert 0 <= dev_frac < 1
+    rng = np.random.default_rng(seed=seed)
+    for num_train_ments in num_train_ment_vals:
+        for split_iter in range(num_splits):
+            if num_train_ments > n_ments:
+                continue
+            train = sorted(rng.choice(n_ments, size=num_train_ments, replace=False))
+            test = sorted(list(set(range(n_ments)) - set(train)))
+            train_dev = sorted(rng.choice(a=train, size=int(num_train_ments * dev_frac), replace=False))
+            train_train = sorted(list(set(train) - set(train_dev)))
+            yield num_train_ments, split_iter, {"train": [int(i) for i in train], "test": [int(i) for i in test],
+                                                "train_dev": [int(i) for i in train_dev],
+                                                "train_train": [int(i) for i in train_train]}
+
+
+def write_splits(m2e_dict, num_train_ment_vals, num_splits, seed, dev_frac, base_out_dir):
+    """Write the reference's directory layout ``{base}/nm_train={n}/split_idx={i}/{split}.pkl`` (:92-128); empty
+    index lists are skipped like the reference does (:28-30).  Returns the files written."""
+    scores = torch.as_tensor(m2e_dict["ment_to_ent_scores"])
+    data, toks = m2e_dict["test_data"], m2e_dict["mention_tokens_list"]
+    assert scores.shape[0] == len(data) == len(toks)
+    written = []
+    for n_train, split_iter, idx in split_indices(scores.shape[0], num_train_ment_vals, num_splits, seed, dev_frac):
+        out_dir = f"{base_out_dir}/nm_train={n_train}/split_idx={split_iter}"
+        for name in SPLIT_NAMES:
+            ment_idxs = idx[name]
+            if len(ment_idxs) == 0:
+                continue
+            d = make_m2e_dict(scores[ment_idxs, :], [data[i] for i in ment_idxs], [toks[i] for i in ment_idxs],
+                              arg_dict=m2e_dict["arg_dict"], ment_idxs=ment_idxs)
+            save_m2e_pickle(f"{out_dir}/{name}.pkl", d)
+            written.append(f"{out_dir}/{name}.pkl")
+    return written
+
+
+def retrieval_grids(n_ent, method="cur"):
+    """top_k / k_retvr / n_ent_anchors grids exactly as ..._w_fixed_train_test_splits.py:238-251 builds them
+    (both grids contain 0 = int(1 * 0.1), and n_ent itself)."""
+    top_k_vals = [1, 10, 50, 100]
+    base = [1, 10, 50, 100, 200, 500, 1000]
+    cur = base + [int(k * frac) for k in base for frac in np.arange(0.1, 1.0, 0.1)]
+    top_k_retr_vals = cur if ("cur" in method or "fixed_anc_ent" in method) else base
+    top_k_retr_vals = sorted(list(set(top_k_retr_vals)))
+    anchors_base = [10, 50, 100, 200, 500, 1000, 2000]
+    n_ent_anchors_vals = [v for v in anchors_base if v < n_ent] + [n_ent]
+    n_ent_anchors_vals = sorted(list(set(n_ent_anchors_vals + cur)))
+    return top_k_vals, top_k_retr_vals, n_ent_anchors_vals
+
+
+def run_cur_method(test_data_file, train_data_file, seed, *, n_ent_anchors_vals=None, top_k_retr_vals=None,
+                   precision="f32x3"):
+    """``run_eval_method(curr_method="cur", ...)`` (:209-443) on the GPU: load the two split pickles, replay the
+    anchor draws, build one index per k_i, retrieve once at the largest k_r and evaluate every (k, k_r).
+    Returns (eval_res, retrieval_params) in the reference's layout.  The optional grids restrict the sweep (the
+    anchor draws of skipped k_i values are still replayed so that the remaining ones see the reference's anchors)."""
+    from .eval_retrieval import fixed_split_cur_eval
+    test = load_m2e_pickle(test_data_file, require_ment_idxs=True)
+    train = load_m2e_pickle(train_data_file)
+    A_test, A_train = test["ment_to_ent_scores"], train["ment_to_ent_scores"]
+    assert A_train.shape[1] == A_test.shape[1], "Train and test entities differ! Use entity_id_list from data dump to resolve this"
+    n_ent = A_test.shape[1]
+    top_k_vals, kr_all, ki_all = retrieval_grids(n_ent, "cur")
+    kr = [v for v in kr_all if top_k_retr_vals is None or v in set(top_k_retr_vals)]
+    keep_ki = None if n_ent_anchors_vals is None else set(n_ent_anchors_vals)
+    res = fixed_split_cur_eval(A_train, A_test, ki_all, top_k_vals, kr, seed, precision=precision, only_k_i=keep_ki)
+    params = {"top_k_retr_vals": kr_all, "top_k_vals": top_k_vals, "n_ent_anchors_vals": ki_all}
+    return res, params
+
+
+def write_result_json(res_dir, eval_method, misc, eval_res_by_seed, arg_dict, retriever_params):
+    """``{res_dir}/method={eval_method}_{misc}.json`` with the reference's top-level layout (:494-500):
+    ``seed=<s>`` -> results, ``other_args`` -> CLI arguments + ``retriever_params``."""
+    out = {f"seed={s}": r for s, r in eval_res_by_seed.items()}
+    out["other_args"] = dict(arg_dict)
+    out["other_args"]["retriever_params"] = retriever_params
+    res_file = f"{res_dir}/method={eval_method}_{misc}.json"
+    Path(os.path.dirname(res_file)).mkdir(exist_ok=True, parents=True)
+    with open(res_file, "w") as fout:
+        json.dump(out, fout, indent=4)
+    return res_file

@@ -103,6 +103,31 @@ def pinv(A, rcond=1e-15, return_cond=False):
     return (out, cond) if return_cond else out
 
 
+def singular_values(A):
+    """Singular values of an (m x n) fp32 matrix, descending fp64 (Jacobi; eval/compute_m2e_matrix_ranks.py:44-53)."""
+    lib = _lib.load()
+    A = _f32(A)
+    assert A.dim() == 2
+    m, n = A.shape
+    out = torch.zeros(min(m, n), dtype=torch.float64, device=A.device)
+    if m > 0 and n > 0:
+        nbytes = lib.anncur_pinv_workspace_bytes(m, n)
+        ws = WORKSPACE.get("pinv", nbytes, A.device)
+        with torch.cuda.device(A.device):
+            _lib.check(lib.anncur_singular_values_f32(_ptr(A), m, n, _ld(A), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return torch.sort(out, descending=True).values
+
+
+def matrix_rank(A, tol=None):
+    """np.linalg.matrix_rank(A): number of singular values above max(m, n) * eps(fp32) * sigma_max (or ``tol``)."""
+    s = singular_values(A)
+    if s.numel() == 0:
+        return 0
+    if tol is None:
+        tol = float(s[0]) * max(A.shape) * float(torch.finfo(torch.float32).eps)
+    return int((s > tol).sum().item())
+
+
 # ---- K2 -------------------------------------------------------------------------------------------
 def gemm(A, B):
     """A (m x k) @ B (k x n) in fp32 FFMA (eval/matrix_approx_zeshel.py:61,65,74,79,85,97,118)."""

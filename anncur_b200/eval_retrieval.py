@@ -150,10 +150,11 @@ def run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors
 
 
 def fixed_split_cur_eval(train_scores, test_scores, n_ent_anchors_vals, top_k_vals, top_k_retvr_vals, seed,
-                         *, precision="f32x3"):
+                         *, precision="f32x3", only_k_i=None):
     """The ``cur`` method of run_eval_method (..._w_fixed_train_test_splits.py:286-303 + :403-429) end to end on
     the GPU: ONE numpy Generator replayed across the k_i grid, every training row an anchor query, and for each
-    (k_r, k_i) the all-top-k evaluation.  Returns {f"top_k={k}": {f"k_retvr={k_r}": {f"anc_n_e={k_i}": metrics}}}
+    (k_r, k_i) the all-top-k evaluation.  Returns {f"top_k={k}": {f"k_retvr={k_r}": {f"anc_n_m={n_train}_anc_n_e={k_i}": metrics}}}
+    (the reference's key layout, :429)
     restricted to the combinations the reference evaluates (k <= k_r, k_r <= N)."""
     engine.require_cuda()
     train = engine._f32(train_scores)
@@ -164,20 +165,26 @@ def fixed_split_cur_eval(train_scores, test_scores, n_ent_anchors_vals, top_k_va
     max_kr = max([kr for kr in top_k_retvr_vals if kr <= n_ents] + [0])
     for k_i in n_ent_anchors_vals:
         anc = sorted(rng.choice(n_ents, size=k_i, replace=False))
-        anc_t = torch.as_tensor(np.asarray(anc, dtype=np.int64), device=train.device)
-        cur = CURApprox(row_idxs=np.arange(n_train), col_idxs=anc, rows=train, cols=train[:, anc_t],
-                        approx_preference="rows", precision=precision)
+        if only_k_i is not None and k_i not in only_k_i:
+            continue                                   # draw replayed, grid point not evaluated
         if max_kr == 0:
             continue
-        # one retrieval at the largest k_r: every smaller k_r list is a prefix of it
-        Q = test[:, anc_t]
+        n_test = test.shape[0]
         if k_i == 0:
-            continue
-        v, i = cur.topk_in_row(Q, max_kr)
+            # empty anchor set (in the reference's grid): E is 0 x N, every approximate score is 0, and the retrieved
+            # list is a pure tie -- ours is items 0..k_r-1 (ties -> lower index; torch.topk leaves the order open)
+            i = torch.arange(max_kr, device=test.device, dtype=torch.int64).repeat(n_test, 1)
+            v = torch.zeros((n_test, max_kr), device=test.device)
+        else:
+            anc_t = torch.as_tensor(np.asarray(anc, dtype=np.int64), device=train.device)
+            cur = CURApprox(row_idxs=np.arange(n_train), col_idxs=anc, rows=train, cols=train[:, anc_t],
+                            approx_preference="rows", precision=precision)
+            # one retrieval at the largest k_r: every smaller k_r list is a prefix of it
+            v, i = cur.topk_in_row(test[:, anc_t], max_kr)
         for k_r in top_k_retvr_vals:
             if k_r > n_ents or k_r == 0:
                 continue
             res = eval_approx_score_mat_for_all_topk(test, None, top_k_vals, k_r, approx_topk=(v[:, :k_r].contiguous(), i[:, :k_r].contiguous()))
             for k, metrics in res.items():
-                out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_e={k_i}"] = metrics
+                out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_m={n_train}_anc_n_e={k_i}"] = metrics
     return out

@@ -416,14 +416,20 @@ def main():
     alg_bytes = e_bytes + 4 * B * k_i + 12 * B * k
     tf = flops / (fused_ms_avg * 1e-3) / 1e12 if fused_n else None
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    # dram__bytes_read.sum + dram__bytes_write.sum of the MAIN kernel, one `ncu --set full` capture per (workload, kind)
+    # (profiles/r1_ncu_fused_c2_f32x3_v8_details.txt); null where no capture was taken
+    NCU_TRAFFIC = {("c2", "f32x3"): 238.13e6 + 16.71e6}
     roofline = {
         "kernel": "fused_score_topk_kernel (tcgen05 score GEMM + streaming top-k)",
         "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (tf / peak_tf) if tf else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": NCU_TRAFFIC.get((args.workload, args.precision)) if world == 1 else None, "peak_source": peak_src,
         "launch_ms": fused_ms_avg, "launches_timed": fused_n, "share_of_step": fused_ms / ms_total if ms_total else None,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
         "tensor_passes": 3 if args.precision == "f32x3" else 1,
-        "note": "flops counted once; the fp32-grade kind issues 3 f16 tensor passes per product, so its ceiling is peak/3",
+        "tensor_pipe_tflops": (tf * (3 if args.precision == "f32x3" else 1)) if tf else None,
+        "tensor_pipe_frac": (tf * (3 if args.precision == "f32x3" else 1) / peak_tf) if tf else None,
+        "note": "achieved/frac count the algorithmic flops 2*B*k_i*N once; the fp32-grade kind issues 3 f16 tensor passes per "
+                "product (h.h + h.l + l.h), so the tensor pipe itself runs at tensor_pipe_tflops (frac of the same measured peak)",
         "hbm_gbs_achieved": alg_bytes / (fused_ms_avg * 1e-3) / 1e9 if fused_n else None,
         "hbm_gbs_peak": peaks.get("hbm_gbs"),
     }

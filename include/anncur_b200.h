@@ -66,6 +66,12 @@ ANNCUR_API size_t anncur_pinv_workspace_bytes(int m, int n);
 ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo,
                     double* cond_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Singular values of A (m x n fp32) as min(m, n) UNSORTED fp64 numbers (device): the same Jacobi factorisation
+ * without the inverse.  Replaces the SVD inside np.linalg.matrix_rank at eval/compute_m2e_matrix_ranks.py:44-53
+ * (rank = #{sigma > max(m, n) * eps_fp32 * sigma_max}, counted by the caller).  Workspace: anncur_pinv_workspace_bytes. */
+ANNCUR_API int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2 / dense products -------------------------------------------------------------------
  * C[m x n] = A[m x k] . B[k x n], fp32 FFMA accumulate.  Replaces `U @ R`
  * (eval/matrix_approx_zeshel.py:65), `C @ U` (:61) and the dense getters get_rows/get_cols/get/

@@ -118,11 +118,12 @@ def test_fixed_split_eval_dropin_matches_reference_golden(golden_dir):
                 _close_dict(eval_approx_score_mat(test, approx, min(top_k_vals), k_r), ref[key], atol=1e-6)
     # whole pipeline (anchor replay + index build + fused retrieval + rerank) against the same golden numbers
     full = fixed_split_cur_eval(torch.from_numpy(g["train"]), test, k_i_vals, top_k_vals, k_r_vals, int(g["seed"]))
+    n_train = g["train"].shape[0]
     for k_i in k_i_vals:
         for k_r in k_r_vals:
             want = ref[f"all_topk|k_i={k_i}|k_r={k_r}"]
             for k in want:
-                _close_dict(full[f"top_k={k}"][f"k_retvr={k_r}"][f"anc_n_e={k_i}"], want[k], atol=3e-3)
+                _close_dict(full[f"top_k={k}"][f"k_retvr={k_r}"][f"anc_n_m={n_train}_anc_n_e={k_i}"], want[k], atol=3e-3)
 
 
 def test_compute_overlap_dropin_strings(golden_dir):

@@ -165,3 +165,53 @@ def test_fused_c2_config_sharded_merge_property(eng):
         cv.append(pv), ci.append(pi)
     mv, mi = eng.merge_topk(torch.cat(cv, 1), torch.cat(ci, 1), k)
     assert torch.equal(mi, i) and torch.allclose(mv, v, rtol=1e-5, atol=1e-5)
+
+
+def test_search_host_equals_device_path(eng):
+    """anncur_search_host (host buffers: H2D, kernels, D2H on the stream) == anncur_score_topk (device buffers)."""
+    Q, E = _rand((300, 77), 31), _rand((77, 70000), 32)
+    packed = eng.PackedItems(E.cuda(), "f32x3")
+    dv, di = eng.score_topk(Q.cuda(), packed, 50, idx_offset=7)
+    for pin in (False, True):
+        Qh = torch.zeros(300, 80)                         # row stride 80 > k_dim 77
+        Qh[:, :77] = Q
+        Qh = Qh.pin_memory() if pin else Qh
+        vh = torch.empty((300, 50), dtype=torch.float32)
+        ih = torch.empty((300, 50), dtype=torch.int64)
+        if pin:
+            vh, ih = vh.pin_memory(), ih.pin_memory()
+        eng.search_host(Qh[:, :77], packed, 50, vh, ih, idx_offset=7)
+        torch.cuda.synchronize()
+        assert torch.equal(ih, di.cpu()) and torch.equal(vh, dv.cpu())
+
+
+@pytest.mark.parametrize("group", ["1", "2"])
+def test_fused_both_cta_group_modes_in_subprocess(group):
+    """The CTA-pair (cta_group::2) and single-CTA instantiations of the fused kernel give the oracle's answer;
+    the mode is chosen per process (ANNCUR_CTA_GROUP), hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from anncur_b200 import engine as eng
+from oracle import cur_oracle as O
+from tests.parity import assert_scores_close, assert_topk_sets_match
+rng = np.random.default_rng(5)
+for (B, K, N, k, kind) in [(700, 96, 90000, 100, "f32x3"), (129, 500, 3000, 10, "f32x3"), (513, 64, 70000, 40, "bf16")]:
+    Q = torch.from_numpy(rng.standard_normal((B, K), dtype=np.float32)); E = torch.from_numpy(rng.standard_normal((K, N), dtype=np.float32))
+    v, i = eng.score_topk(Q.cuda(), eng.PackedItems(E.cuda(), kind), k)
+    dense = (Q.double() @ E.double()).numpy(); ref = O.score_topk(Q, E, k)
+    if kind == "f32x3":
+        assert_topk_sets_match(i.cpu().numpy(), ref.indices.numpy(), full_scores=dense)
+        assert_scores_close(v.cpu().numpy(), np.take_along_axis(dense, i.cpu().numpy(), 1))
+    else:
+        rec = np.mean([len(set(i[r].tolist()) & set(ref.indices[r].tolist())) / k for r in range(B)])
+        assert rec > 0.9, rec
+print("OK")
+""" % root
+    env = dict(os.environ, ANNCUR_CTA_GROUP=group)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]

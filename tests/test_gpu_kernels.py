@@ -167,3 +167,14 @@ def test_adaptive_round_matches_oracle_restatement(eng):
         assert all(s[j] >= kth - tau for j in got) and len(set(got.tolist())) == n_next
         assert not set(got.tolist()) & set(anchors[q].tolist())
         assert np.allclose(val[q].cpu().numpy(), s[got], atol=10 * tau)
+
+
+def test_singular_values_and_matrix_rank(eng):
+    """eval/compute_m2e_matrix_ranks.py:44-53: np.linalg.matrix_rank of a score matrix."""
+    rng = np.random.default_rng(0)
+    for (m, n, r) in [(60, 200, 13), (300, 90, 90), (128, 128, 40)]:
+        A = (rng.standard_normal((m, r)) @ rng.standard_normal((r, n))).astype(np.float32)
+        s = eng.singular_values(torch.from_numpy(A)).cpu().numpy()
+        ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+        assert np.allclose(s[:r], ref[:r], rtol=1e-6, atol=1e-6 * ref[0])
+        assert eng.matrix_rank(torch.from_numpy(A)) == np.linalg.matrix_rank(A) == r
