@@ -668,20 +668,45 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     const uint32_t lane = lane_id();
     const float* q = Q + int64_t(row) * ldq;
     float scale = 1.f;
-    if (!BF16) {
-        float m = 0.f;
-        for (int kidx = lane; kidx < k_dim; kidx += 32) {
-            float x = fabsf(q[kidx]);
-            if (x <= FLT_MAX) m = fmaxf(m, x);
-        }
-        scale = pow2_scale_for(warp_max_f(m));
-    }
     float bound = 0.f;
-    for (int kb = 0; kb < num_kb; ++kb) {
-        int kidx = kb * 32 + int(lane);
-        float x = kidx < k_dim ? q[kidx] * scale : 0.f;
-        split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
-        if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+    constexpr int RC = 16;                       // rows of up to 512 anchors are read once and kept in registers
+    if (num_kb <= RC) {
+        float xr[RC];
+#pragma unroll
+        for (int u = 0; u < RC; ++u) {
+            const int kidx = u * 32 + int(lane);
+            xr[u] = (u < num_kb && kidx < k_dim) ? q[kidx] : 0.f;
+        }
+        if (!BF16) {
+            float m = 0.f;
+#pragma unroll
+            for (int u = 0; u < RC; ++u) { const float x = fabsf(xr[u]); if (x <= FLT_MAX) m = fmaxf(m, x); }
+            scale = pow2_scale_for(warp_max_f(m));
+        }
+#pragma unroll
+        for (int u = 0; u < RC; ++u) {
+            if (u < num_kb) {
+                const int kidx = u * 32 + int(lane);
+                const float x = xr[u] * scale;
+                split_store<BF16>(x, plane_h, plane_l, (int64_t(u) * n_queries + row) * 32 + lane);
+                if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+            }
+        }
+    } else {
+        if (!BF16) {
+            float m = 0.f;
+            for (int kidx = lane; kidx < k_dim; kidx += 32) {
+                float x = fabsf(q[kidx]);
+                if (x <= FLT_MAX) m = fmaxf(m, x);
+            }
+            scale = pow2_scale_for(warp_max_f(m));
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+            int kidx = kb * 32 + int(lane);
+            float x = kidx < k_dim ? q[kidx] * scale : 0.f;
+            split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
+            if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+        }
     }
     if (!BF16) {
         // SAMPLE scores use the high fp16 halves only.  Each product q_i e_i is then off by q_i e_i (eps_q + eps_e)
@@ -725,9 +750,24 @@ sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_querie
     const uint32_t lane = lane_id();
     uint32_t* hist = hist_all[threadIdx.x >> 5];
     const float* v = smax + int64_t(row) * n_smax;
-    uint32_t prefix = 0, mask = 0, need = uint32_t(j);
+    uint32_t need = uint32_t(j);
     bool have = n_smax >= j;
-    for (int shift = 24; have && shift >= 0; shift -= 8) {
+    // group maxima of one row lie in a narrow band: start at the first byte in which largest and smallest differ
+    uint32_t kmax = 0u, kmin = 0xffffffffu;
+    for (int t = int(lane); t < n_smax; t += 32) {
+        const uint32_t key = float_to_ordered(__ldcg(v + t));
+        kmax = max(kmax, key);
+        kmin = min(kmin, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    }
+    const int first_shift = (31 - __clz(int((kmax ^ kmin) | 1u))) & ~7;
+    uint32_t mask = first_shift >= 24 ? 0u : ~((1u << (first_shift + 8)) - 1u);
+    uint32_t prefix = kmax & mask;
+    for (int shift = first_shift; have && shift >= 0; shift -= 8) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
         __syncwarp();

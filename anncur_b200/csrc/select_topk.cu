@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(Src src, Se
 // hide each other's memory latency.  Rows with more than kWarpSelCap live keys (streaming-mode overflow,
 // adversarial inputs) are appended to a list and handled by the CTA-per-row kernel afterwards.
 constexpr int kWarpSelCap = 1024;
-constexpr int kWarpSelWarps = 8;
+constexpr int kWarpSelWarps = 2;        // small CTAs (18 KB smem): they fit beside a resident fused-kernel CTA of another stream
 
 __global__ void __launch_bounds__(kWarpSelWarps * 32)
 select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __restrict__ big_rows /* [0] = count, then rows */) {
@@ -351,10 +351,22 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
         __syncwarp();
         uint32_t n_win = total;
         if (total > uint32_t(o.k)) {
-            // MSD radix select of the k-th largest key
-            uint64_t prefix = 0, mask = 0;
+            // MSD radix select of the k-th largest key.  The candidates all passed the same threshold, so their
+            // leading bytes coincide: start at the first byte in which the row's largest and smallest key differ.
+            uint64_t kmax = 0ull, kmin = ~0ull;
+            for (uint32_t t = lane; t < total; t += 32) {
+                const uint64_t key = keys[t];
+                kmax = key > kmax ? key : kmax;
+                kmin = key < kmin ? key : kmin;
+            }
+            kmin = warp_min_u64(kmin);
+            kmax = ~warp_min_u64(~kmax);
+            const int top_bit = 63 - __clzll((long long)((kmax ^ kmin) | 1ull));
+            const int first_shift = top_bit & ~7;
+            uint64_t mask = first_shift >= 56 ? 0ull : ~((1ull << (first_shift + 8)) - 1ull);
+            uint64_t prefix = kmax & mask;
             uint32_t need = uint32_t(o.k);
-            for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int shift = first_shift; shift >= 0; shift -= 8) {
 #pragma unroll
                 for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
                 __syncwarp();
@@ -470,7 +482,7 @@ int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lis
     const size_t smem = size_t(kWarpSelWarps) * (kWarpSelCap * sizeof(uint64_t) + (256 + size_t(n_lists) + 1) * sizeof(uint32_t));
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(select_lists_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int grid = (n_rows + kWarpSelWarps - 1) / kWarpSelWarps;
-    if (grid > 3 * sm_count()) grid = 3 * sm_count();
+    if (grid > 12 * sm_count()) grid = 12 * sm_count();
     select_lists_warp_kernel<<<grid, kWarpSelWarps * 32, smem, stream>>>(src, o, n_rows, big_rows);
     ANNCUR_LAUNCH_OK("select_lists_warp_kernel");
     src.flag_mode = 0;                                  // flags were written by the warp kernel

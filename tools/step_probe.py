@@ -19,6 +19,7 @@ ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--precision", default="f32x3")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--streams", type=int, default=1)
 a = ap.parse_args()
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
@@ -28,16 +29,25 @@ W = torch.randn(a.ki, r, device=dev)
 E = (W @ Y.t()) / r ** 0.5 + 0.05 * torch.randn(a.ki, a.n, device=dev)
 Q = [torch.randn(a.b, r, device=dev) @ W.t() / r ** 0.5 + 0.05 * torch.randn(a.b, a.ki, device=dev) for _ in range(2)]
 packed = engine.PackedItems(E, a.precision)
-ov = torch.empty((a.b, a.k), dtype=torch.float32, device=dev)
-oi = torch.empty((a.b, a.k), dtype=torch.int64, device=dev)
-for j in range(a.warmup):
-    engine.score_topk(Q[j % 2], packed, a.k, out=(ov, oi))
+ov = [torch.empty((a.b, a.k), dtype=torch.float32, device=dev) for _ in range(a.streams)]
+oi = [torch.empty((a.b, a.k), dtype=torch.int64, device=dev) for _ in range(a.streams)]
+streams = [torch.cuda.Stream() for _ in range(a.streams)] if a.streams > 1 else [torch.cuda.current_stream()]
+def step(j):
+    s = j % a.streams
+    with torch.cuda.stream(streams[s]):
+        engine.score_topk(Q[j % 2], packed, a.k, out=(ov[s], oi[s]))
+for j in range(a.warmup * a.streams):
+    step(j)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 engine.profile_enable(True)
 e0.record()
+for s_ in streams[1:] if a.streams > 1 else []:
+    s_.wait_stream(torch.cuda.current_stream())
 for j in range(a.steps):
-    engine.score_topk(Q[j % 2], packed, a.k, out=(ov, oi))
+    step(j)
+for s_ in streams if a.streams > 1 else []:
+    torch.cuda.current_stream().wait_stream(s_)
 e1.record()
 torch.cuda.synchronize()
 ms, n = engine.profile_read()
