@@ -73,6 +73,27 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx)
 __host__ __device__ __forceinline__ float key_score(uint64_t key) { return ordered_to_float(uint32_t(key >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_index(uint64_t key) { return ~uint32_t(key); }
 
+// Survivor lists of the fused kernel hold RAW entries -- low word = fp32 score bits, high word = item index -- so that a
+// push is a plain 64-bit store of two registers; the readers (list compaction, select kernels) turn them into keys.
+__host__ __device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) {
+    return (uint64_t(float_to_ordered(
+#ifdef __CUDA_ARCH__
+        __uint_as_float(uint32_t(raw))
+#else
+        [](uint32_t u) { union { float f; uint32_t u; } c; c.u = u; return c.f; }(uint32_t(raw))
+#endif
+        )) << 32) | uint64_t(~uint32_t(raw >> 32));
+}
+__host__ __device__ __forceinline__ uint64_t key_to_raw(uint64_t key) {
+    const float score = key_score(key);
+#ifdef __CUDA_ARCH__
+    const uint32_t bits = __float_as_uint(score);
+#else
+    union { float f; uint32_t u; } c; c.f = score; const uint32_t bits = c.u;
+#endif
+    return (uint64_t(key_index(key)) << 32) | uint64_t(bits);
+}
+
 #define ANNCUR_PAD_VAL (-FLT_MAX)
 
 #ifdef __CUDACC__

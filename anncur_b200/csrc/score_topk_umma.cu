@@ -219,7 +219,7 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, uint32_t n
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
         uint32_t t = uint32_t(i) * 32u + lane;
-        key[i] = t < n ? __ldcg(list + t) : 0ull;
+        key[i] = t < n ? raw_to_key(__ldcg(list + t)) : 0ull;
     }
     uint64_t prefix = 0, mask = 0;
     uint32_t need = k;
@@ -268,7 +268,7 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, uint32_t n
         const bool keep = key[i] != 0ull && (key[i] & mask) >= prefix;
         const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            list[running + __popc(ballot & ((1u << lane) - 1u))] = key[i];
+            list[running + __popc(ballot & ((1u << lane) - 1u))] = key_to_raw(key[i]);
             kth = key[i] < kth ? key[i] : kth;
         }
         running += __popc(ballot);
@@ -458,14 +458,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             // one 32-column group of this thread's row, already in registers
             auto process = [&](const uint32_t (&r)[32], int tile, int c) {
                 const int col0 = tile * BLOCK_N + c * 32;
-                float g[4];
+                float g[4], g4[8];
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
                     float m01 = fmaxf(__uint_as_float(r[gi * 8 + 0]), __uint_as_float(r[gi * 8 + 1]));
                     float m23 = fmaxf(__uint_as_float(r[gi * 8 + 2]), __uint_as_float(r[gi * 8 + 3]));
                     float m45 = fmaxf(__uint_as_float(r[gi * 8 + 4]), __uint_as_float(r[gi * 8 + 5]));
                     float m67 = fmaxf(__uint_as_float(r[gi * 8 + 6]), __uint_as_float(r[gi * 8 + 7]));
-                    g[gi] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+                    g4[gi * 2] = fmaxf(m01, m23);
+                    g4[gi * 2 + 1] = fmaxf(m45, m67);
+                    g[gi] = fmaxf(g4[gi * 2], g4[gi * 2 + 1]);
                 }
                 if (sample) {
                     float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
@@ -478,17 +480,25 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     if (row_ok) smax_row[tile * (BLOCK_N / 32) + c] = m;
                     return;
                 }
+                // survivors: test 4-column sub-groups (their maxima fall out of the tree above), push RAW entries
+                const bool ragged = col0 + 32 > p.n_items;                  // only the last tile of the item set
 #pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                    if (g[gi] > thr) {
+                for (int h4 = 0; h4 < 8; ++h4) {
+                    if (g4[h4] > thr) {
+                        // branch-free inside: slot of element j = cnt + (survivors among elements < j)
+                        bool keep[4];
+                        uint32_t slot[4];
+                        uint32_t run = cnt;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float v = __uint_as_float(r[gi * 8 + j]);
-                            if (v > thr && col0 + gi * 8 + j < p.n_items) {
-                                list[cnt] = make_key(v, uint32_t(col0 + gi * 8 + j));
-                                ++cnt;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            keep[j] = __uint_as_float(r[h4 * 4 + j]) > thr && (!ragged || col0 + h4 * 4 + j < p.n_items);
+                            slot[j] = run;
+                            run += keep[j] ? 1u : 0u;
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (keep[j]) list[slot[j]] = (uint64_t(uint32_t(col0 + h4 * 4 + j)) << 32) | uint64_t(r[h4 * 4 + j]);
+                        cnt = run;
                     }
                 }
             };
@@ -513,8 +523,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             };
 
             for (int tile = t0; tile < t1; ++tile) {
-                // refresh the cross-chunk bound (exclusive) before blocking on the accumulator
-                if (!sample) {
+                // the cross-chunk bound (exclusive): fixed for the whole pass when it was sampled, refreshed per tile
+                // in streaming mode (other chunks of the row tighten it as they compact)
+                if (!sample && (tile == t0 || p.close_compact != 0)) {
                     thr = INFINITY;
                     if (row_ok) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
                 }

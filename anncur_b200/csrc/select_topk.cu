@@ -30,7 +30,7 @@ struct DenseRow {
 
 struct KeyLists {
     static constexpr bool kIsLists = true;
-    const uint64_t* keys;     // [row][n_lists][cap]
+    const uint64_t* keys;     // [row][n_lists][cap] RAW entries (common.cuh: raw_to_key)
     const uint32_t* counts;   // [row][n_lists]
     int n_lists;
     int cap;
@@ -49,7 +49,7 @@ struct KeyLists {
     __device__ uint64_t key(int row, int64_t j) const {
         int list = int(j / cap), pos = int(j % cap);
         uint32_t c = __ldg(counts + int64_t(row) * n_lists + list);
-        return pos < int(c) ? __ldcg(keys + (int64_t(row) * n_lists + list) * cap + pos) : 0ull;
+        return pos < int(c) ? raw_to_key(__ldcg(keys + (int64_t(row) * n_lists + list) * cap + pos)) : 0ull;
     }
 };
 
@@ -216,7 +216,7 @@ __device__ __forceinline__ void select_one_row(const Src& src, const SelectOut& 
             for (int l = warp; l < src.n_lists; l += n_warps) {
                 const uint32_t base = offs[l], cnt = offs[l + 1] - offs[l];
                 const uint64_t* p = src.keys + (int64_t(row) * src.n_lists + l) * src.cap;
-                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = __ldcg(p + t);
+                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = raw_to_key(__ldcg(p + t));
             }
             if (select_first) {
                 uint64_t* dest = sel + kSmemSortCap / 2;
@@ -339,7 +339,7 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
                         const int mid = (lo + hi) >> 1;
                         if (offs[mid] <= e) lo = mid; else hi = mid;
                     }
-                    reg[u] = __ldcg(row_keys + int64_t(lo) * src.cap + (e - offs[lo]));
+                    reg[u] = raw_to_key(__ldcg(row_keys + int64_t(lo) * src.cap + (e - offs[lo])));
                 }
             }
 #pragma unroll
