@@ -43,6 +43,9 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
                      int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
                      int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// smallest j with P[Binomial(n, p) >= j] <= eps (rank used by the sampled thresholds)
+int binomial_tail_rank(int n, double p, double eps);
+
 int profile_enable(int on);
 int profile_read(double* ms_sum, int* launches);
 

@@ -890,7 +890,7 @@ static int choose_chunks(int m_tiles, int n_tiles, int sms, double warmup_tiles,
 }
 
 // smallest j with P[Binomial(n, p) >= j] <= eps
-static int binomial_tail_rank(int n, double p, double eps) {
+int binomial_tail_rank(int n, double p, double eps) {
     if (n <= 0) return 1;
     // pmf by recurrence from the mode outwards is overkill here: n <= 1023, plain forward recurrence in log space
     std::vector<double> pmf(size_t(n) + 1);

@@ -459,8 +459,107 @@ static int launch_select(const Src& src, int n_rows, int k, int64_t idx_offset, 
     return ANNCUR_OK;
 }
 
+// ---- dense rows, sampled threshold: ~1.06 passes over the row instead of one pass per radix digit -----------------
+// Pass A reads one float4 out of every G (a 1/G sample), keeps the maxima of <= kDsGroups contiguous runs of the sample
+// and takes their j-th largest as threshold (<= the j-th best sampled value; j = binomial_tail_rank(k-1, 1/G), so at
+// least k elements of the row reach it except with probability ~1e-6).  Pass B streams the row once and collects
+// the elements >= threshold in shared memory, then selects / sorts them.  A row that collects fewer than
+// min(k, n) or more than kDsCap elements falls back to the radix path, so the result never depends on the sample.
+constexpr int kDsThreads = 256;
+constexpr int kDsGroups = 512;
+constexpr int kDsCap = 4096;        // >= kSmemSortCap: the region doubles as the fallback path's scratch
+constexpr int kDsStride = 16;          // G
+
+__global__ void __launch_bounds__(kDsThreads)
+topk_dense_sampled_kernel(DenseRow src, SelectOut o, int rank_j, int n_sort_j) {
+    extern __shared__ __align__(16) uint64_t ds_smem[];
+    uint64_t* list = ds_smem;                         // kDsCap keys (also the fallback's scratch)
+    uint64_t* grp = ds_smem + kDsCap;                 // kDsGroups keys
+    uint64_t* dest = grp + kDsGroups;                 // max(n_sort, n_sort_j) keys
+    __shared__ uint32_t s_count;
+    __shared__ float s_thr;
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* rp = src.S + int64_t(row) * src.lds;
+    const int64_t n = src.n_cols;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
+    const int64_t n4 = vec_ok ? n / 4 : 0;                         // float4 units of the row (tail handled separately)
+    const int64_t n_s4 = n4 / kDsStride;                           // sampled float4 units: unit u -> float4 index u * G
+    bool fallback = n_s4 < int64_t(4 * rank_j);
+    if (!fallback) {
+        // ---- pass A: group maxima of the sample ------------------------------------------------------------------
+        const int n_groups = int(n_s4 < kDsGroups ? n_s4 : kDsGroups);
+        const int64_t per = (n_s4 + n_groups - 1) / n_groups;
+        for (int g = tid; g < n_groups; g += kDsThreads) {
+            float m = -INFINITY;
+            const int64_t u1 = (int64_t(g) + 1) * per < n_s4 ? (int64_t(g) + 1) * per : n_s4;
+            for (int64_t u = int64_t(g) * per; u < u1; ++u) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(rp) + u * kDsStride);
+                m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            }
+            grp[g] = make_key(m, uint32_t(g));
+        }
+        SelectOut oj = o;
+        oj.k = rank_j;
+        oj.n_sort = n_sort_j;
+        radix_select_collect_sort([&](int64_t j) { return grp[j]; }, int64_t(n_groups), oj, dest);
+        if (tid == 0) { s_thr = key_score(dest[rank_j - 1]); s_count = 0; }
+        __syncthreads();
+        const float thr = s_thr;
+        // ---- pass B: one streaming pass, survivors to shared memory -----------------------------------------------
+        auto push = [&](float v, int64_t j) {
+            if (v >= thr) {
+                const uint32_t pos = atomicAdd(&s_count, 1u);
+                if (pos < uint32_t(kDsCap)) list[pos] = make_key(v, uint32_t(j));
+            }
+        };
+        constexpr int UN = 8;                         // independent 16-byte loads in flight per thread
+        for (int64_t u0 = tid; u0 < n4; u0 += int64_t(kDsThreads) * UN) {
+            float4 v[UN];
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int64_t u = u0 + int64_t(i) * kDsThreads;
+                v[i] = u < n4 ? __ldg(reinterpret_cast<const float4*>(rp) + u) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int64_t u = u0 + int64_t(i) * kDsThreads;
+                if (fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)) >= thr && u < n4) {
+                    push(v[i].x, 4 * u); push(v[i].y, 4 * u + 1); push(v[i].z, 4 * u + 2); push(v[i].w, 4 * u + 3);
+                }
+            }
+        }
+        for (int64_t j = 4 * n4 + tid; j < n; j += kDsThreads) push(__ldg(rp + j), j);
+        __syncthreads();
+        const uint32_t cnt = s_count;
+        const int64_t need = n < int64_t(o.k) ? n : int64_t(o.k);
+        fallback = cnt > uint32_t(kDsCap) || int64_t(cnt) < need;
+        if (!fallback) {
+            radix_select_collect_sort([&](int64_t j) { return list[j]; }, int64_t(cnt), o, dest);
+            write_sorted(dest, row, o);
+            return;
+        }
+    }
+    __syncthreads();
+    select_one_row(src, o, row, ds_smem);           // exact radix path (reads the row once per digit)
+}
+
 int select_topk_dense(const float* S, int64_t lds, int n_rows, int64_t n_cols, int k, int64_t idx_offset,
                       float* out_vals, int64_t* out_idx, cudaStream_t stream) {
+    if (n_rows == 0) return ANNCUR_OK;
+    if (n_cols >= 32768 && k <= 2048) {
+        const int rank_j = binomial_tail_rank(k - 1, 1.0 / kDsStride, 1e-6);
+        if (4 * rank_j <= kDsGroups) {
+            SelectOut o{out_vals, out_idx, idx_offset, nullptr, k, next_pow2(k < 2 ? 2 : k)};
+            const int n_sort_j = next_pow2(rank_j < 2 ? 2 : rank_j);
+            const int n_dest = o.n_sort > n_sort_j ? o.n_sort : n_sort_j;
+            const size_t smem = sizeof(uint64_t) * size_t(kDsCap + kDsGroups + n_dest);
+            ANNCUR_CUDA_OK(cudaFuncSetAttribute(topk_dense_sampled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            topk_dense_sampled_kernel<<<n_rows, kDsThreads, smem, stream>>>(DenseRow{S, lds, n_cols}, o, rank_j, n_sort_j);
+            ANNCUR_LAUNCH_OK("topk_dense_sampled_kernel");
+            return ANNCUR_OK;
+        }
+    }
     return launch_select(DenseRow{S, lds, n_cols}, n_rows, k, idx_offset, nullptr, out_vals, out_idx, stream);
 }
 

@@ -178,3 +178,27 @@ def test_singular_values_and_matrix_rank(eng):
         ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
         assert np.allclose(s[:r], ref[:r], rtol=1e-6, atol=1e-6 * ref[0])
         assert eng.matrix_rank(torch.from_numpy(A)) == np.linalg.matrix_rank(A) == r
+
+
+def test_topk_rows_large_rows_sampled_path(eng):
+    """Rows long enough for the sampled-threshold kernel (>= 32768 columns): random, sorted ascending / descending,
+    heavy ties (falls back to the radix path), unaligned row starts, k from 1 to 1000."""
+    rng = np.random.default_rng(3)
+    S = torch.from_numpy(rng.standard_normal((37, 100003), dtype=np.float32))
+    S[1] = torch.arange(100003, dtype=torch.float32)               # ascending
+    S[2] = -torch.arange(100003, dtype=torch.float32)              # descending
+    S[3] = 0.0                                                     # all ties -> indices 0..k-1
+    S[4, :50000] = 7.0                                             # 50000-way tie at the top
+    S[5, 99990:] = 100.0                                           # winners in the scalar tail
+    for k in (1, 10, 100, 1000):
+        v, i = eng.topk_rows(S.cuda(), k)
+        ref = torch.topk(S, k, dim=1)
+        assert torch.equal(v.cpu(), ref.values)
+        assert torch.equal(torch.gather(S, 1, i.cpu()), v.cpu())
+        assert (i[3].cpu() == torch.arange(k)).all() and (i[4].cpu() == torch.arange(k)).all()
+        assert all(len(set(r.tolist())) == k for r in i.cpu())
+    # row stride that breaks 16-byte alignment of odd rows
+    big = torch.from_numpy(rng.standard_normal((6, 50001), dtype=np.float32)).cuda()
+    v, i = eng.topk_rows(big[:, 1:], 64)
+    ref = torch.topk(big[:, 1:].cpu(), 64, dim=1)
+    assert torch.equal(v.cpu(), ref.values) and torch.equal(i.cpu(), ref.indices)
