@@ -7,6 +7,7 @@
 // Columns of G and V are stored contiguously (k-major), one CTA per column pair per round of a
 // round-robin tournament; everything stays on the device and on the caller's stream (a converged
 // flag turns the remaining round launches into no-ops instead of synchronising with the host).
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -51,10 +52,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-__global__ void __launch_bounds__(JAC_THREADS)
-jacobi_round_kernel(double* __restrict__ G, double* __restrict__ V, int len, int p, int p_even, int round,
-                    double tol, JacobiState* st) {
-    if (st->converged) return;
+// one column pair of one tournament round (the whole CTA works on it)
+__device__ __forceinline__ void jacobi_pair(double* __restrict__ G, double* __restrict__ V, int len, int p, int p_even,
+                                            int round, double tol, JacobiState* st) {
     __shared__ double red[JAC_THREADS / 32];
     __shared__ double cs[2];
     // round-robin tournament (circle method): player p_even-1 is fixed, the rest rotate
@@ -71,8 +71,19 @@ jacobi_round_kernel(double* __restrict__ G, double* __restrict__ V, int len, int
         double x = gi[r], y = gj[r];
         a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
     }
-    a = block_sum(a, red); b = block_sum(b, red); g = block_sum(g, red);
+    // one block reduction for the three sums
+    __shared__ double red3[3][JAC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red3[0][threadIdx.x >> 5] = a; red3[1][threadIdx.x >> 5] = b; red3[2][threadIdx.x >> 5] = g; }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        a = b = g = 0.0;
+        for (int w = 0; w < JAC_THREADS / 32; ++w) { a += red3[0][w]; b += red3[1][w]; g += red3[2][w]; }
         double c = 1.0, s = 0.0;
         if (a > 0.0 && b > 0.0) {
             double off = fabs(g) / sqrt(a * b);
@@ -103,12 +114,40 @@ jacobi_round_kernel(double* __restrict__ G, double* __restrict__ V, int len, int
     }
 }
 
-__global__ void jacobi_sweep_end_kernel(JacobiState* st, double tol) {
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobi_round_kernel(double* __restrict__ G, double* __restrict__ V, int len, int p, int p_even, int round,
+                    double tol, JacobiState* st) {
     if (st->converged) return;
+    jacobi_pair(G, V, len, p, p_even, round, tol, st);
+}
+
+__device__ __forceinline__ void jacobi_sweep_end(JacobiState* st, double tol) {
     double off = __longlong_as_double((long long)st->max_off_bits);
     st->sweeps_done += 1;
     if (off <= tol) st->converged = 1;
     st->max_off_bits = 0ull;
+}
+
+__global__ void jacobi_sweep_end_kernel(JacobiState* st, double tol) {
+    if (st->converged) return;
+    jacobi_sweep_end(st, tol);
+}
+
+// All sweeps in ONE cooperative launch: one CTA per column pair, a grid-wide barrier between the rounds of the
+// tournament instead of a kernel boundary (the factorisation is launch-latency-bound: ~10 sweeps x (p - 1) rounds of
+// microsecond-sized work).  Used when p_even / 2 CTAs are co-resident; the multi-launch path above is the fallback.
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobi_coop_kernel(double* __restrict__ G, double* __restrict__ V, int len, int p, int p_even, double tol, JacobiState* st) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+        for (int round = 0; round < p_even - 1; ++round) {
+            jacobi_pair(G, V, len, p, p_even, round, tol, st);
+            grid.sync();
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) jacobi_sweep_end(st, tol);
+        grid.sync();
+        if (*reinterpret_cast<volatile int*>(&st->converged)) break;
+    }
 }
 
 // sigma_j^2 -> weights 1/sigma_j^2 with numpy's cutoff; one CTA, p threads strided
@@ -221,7 +260,24 @@ static int jacobi_factor(const float* A, int m, int n, int lda, void* workspace,
     jacobi_init_kernel<<<sm_count() * 4, 256, 0, stream>>>(A, m, n, lda, len, p, tall, G, V, st);
     ANNCUR_LAUNCH_OK("jacobi_init_kernel");
     const double tol = fmax(1e-15, 4.0 * sqrt(double(len)) * 1.1102230246251565e-16);
+    bool coop_done = false;
     if (p > 1) {
+        const int p_even = (p + 1) & ~1;
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, JAC_THREADS, 0);
+        if (coop && int64_t(per_sm) * sm_count() >= p_even / 2) {
+            int len_ = len, p_ = p, pe_ = p_even;
+            double tol_ = tol;
+            void* args[] = {&G, &V, &len_, &p_, &pe_, &tol_, &st};
+            cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jacobi_coop_kernel), dim3(p_even / 2),
+                                                        dim3(JAC_THREADS), args, 0, stream);
+            if (e == cudaSuccess) { count_launch(1); coop_done = true; }
+            else cudaGetLastError();                    // not launchable here: fall back to one launch per round
+        }
+    }
+    if (p > 1 && !coop_done) {
         const int p_even = (p + 1) & ~1;
         for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
             for (int round = 0; round < p_even - 1; ++round) {
