@@ -197,6 +197,27 @@ int anncur_merge_topk(const float* cand_vals, const int64_t* cand_idx, int n_row
     return select_topk_pairs(cand_vals, cand_idx, n_rows, n_cand, k, out_vals, out_idx, cudaStream_t(stream));
 }
 
+int anncur_topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint64_t* keys, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0 && k >= 1, "topk_to_keys: bad shape");
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(vals && idx && keys, "topk_to_keys: null pointer");
+    return topk_to_keys(vals, idx, n_rows, k, keys, cudaStream_t(stream));
+}
+
+size_t anncur_merge_topk_keys_workspace_bytes(int n_rows) { return align_up(sizeof(uint32_t) * (size_t(n_rows > 0 ? n_rows : 0) + 1), 256); }
+
+int anncur_merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out, float* out_vals,
+                           int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_shards >= 1 && n_rows >= 0 && k_in >= 1, "merge_topk_keys: bad shape");
+    ANNCUR_REQUIRE(k_out >= 1 && k_out <= ANNCUR_MAX_K, "merge_topk_keys: k = %d outside [1, %d]", k_out, ANNCUR_MAX_K);
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(keys && out_vals && out_idx && workspace, "merge_topk_keys: null pointer");
+    ANNCUR_REQUIRE(k_out <= 1024, "merge_topk_keys: k_out = %d > 1024", k_out);
+    if (workspace_bytes < anncur_merge_topk_keys_workspace_bytes(n_rows)) { set_error("merge_topk_keys workspace too small"); return ANNCUR_E_WORKSPACE; }
+    return merge_topk_keys(keys, n_shards, n_rows, k_in, k_out, out_vals, out_idx, reinterpret_cast<uint32_t*>(workspace),
+                           cudaStream_t(stream));
+}
+
 int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,
                           int k_retr, const int64_t* exact_idx, int k_max, const int* k_list_host, int n_k,
                           int64_t* out_rr_idx, float* out_rr_vals, int32_t* out_common, void* stream) {

@@ -13,6 +13,9 @@ int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lis
                          int64_t idx_offset, const float* row_scale, float* out_vals, int64_t* out_idx,
                          int flag_mode, uint32_t* thr_shared, uint32_t* mtile_flags, int m_tiles, int64_t n_items,
                          uint32_t* big_rows, cudaStream_t stream);
+int topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint64_t* keys, cudaStream_t stream);
+int merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out, float* out_vals, int64_t* out_idx,
+                    uint32_t* scratch_rows, cudaStream_t stream);
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
                       int64_t* out_idx, cudaStream_t stream);
 

@@ -43,13 +43,23 @@ struct KeyLists {
     int m_tiles;
     int64_t n_items;
     const uint32_t* row_list; // optional: [0] = count, then the rows to process (CTA kernel, after the warp kernel)
+    // addressing: entry (row, list, pos) lives at keys[row * row_stride + list * list_stride + pos].  Fused-kernel lists:
+    // list_stride = cap, row_stride = n_lists * cap, RAW entries, lengths in `counts`.  All-gathered per-shard top-k
+    // lists ([shard][row][k] keys): list_stride = n_rows * k, row_stride = k, entries are keys, every list holds `cap`.
+    int64_t list_stride, row_stride;
+    int raw;
+    __device__ uint32_t count(int row, int list) const {
+        return counts ? min(__ldcg(counts + int64_t(row) * n_lists + list), uint32_t(cap)) : uint32_t(cap);
+    }
+    __device__ const uint64_t* list_ptr(int row, int list) const { return keys + int64_t(row) * row_stride + int64_t(list) * list_stride; }
+    __device__ uint64_t load(const uint64_t* p) const { const uint64_t v = __ldcg(p); return raw ? raw_to_key(v) : v; }
     __device__ uint32_t* n_flagged() const { return mtile_flags + m_tiles; }
     __device__ uint32_t* flagged_rows() const { return mtile_flags + m_tiles + 1; }
     __device__ int64_t size(int) const { return int64_t(n_lists) * cap; }
     __device__ uint64_t key(int row, int64_t j) const {
         int list = int(j / cap), pos = int(j % cap);
-        uint32_t c = __ldg(counts + int64_t(row) * n_lists + list);
-        return pos < int(c) ? raw_to_key(__ldcg(keys + (int64_t(row) * n_lists + list) * cap + pos)) : 0ull;
+        uint32_t c = count(row, list);
+        return pos < int(c) ? load(list_ptr(row, list) + pos) : 0ull;
     }
 };
 
@@ -174,7 +184,7 @@ __device__ __forceinline__ void select_one_row(const Src& src, const SelectOut& 
             const int l0 = tid * per, l1 = min(l0 + per, src.n_lists);
             uint32_t local = 0;
             for (int l = l0; l < l1; ++l) {
-                const uint32_t c = min(__ldcg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
+                const uint32_t c = src.count(row, l);
                 offs[l] = local;                       // exclusive within this thread's block, fixed up below
                 local += c;
             }
@@ -215,8 +225,8 @@ __device__ __forceinline__ void select_one_row(const Src& src, const SelectOut& 
             const int warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
             for (int l = warp; l < src.n_lists; l += n_warps) {
                 const uint32_t base = offs[l], cnt = offs[l + 1] - offs[l];
-                const uint64_t* p = src.keys + (int64_t(row) * src.n_lists + l) * src.cap;
-                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = raw_to_key(__ldcg(p + t));
+                const uint64_t* p = src.list_ptr(row, l);
+                for (uint32_t t = lane; t < cnt; t += 32) sel[base + t] = src.load(p + t);
             }
             if (select_first) {
                 uint64_t* dest = sel + kSmemSortCap / 2;
@@ -293,7 +303,7 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
     for (int row = blockIdx.x * kWarpSelWarps + warp; row < n_rows; row += gridDim.x * kWarpSelWarps) {
         // list lengths -> exclusive offsets in shared memory (one parallel read of the counts, then a warp scan)
         for (int l = int(lane); l < src.n_lists; l += 32)
-            offs[l + 1] = min(__ldcg(src.counts + int64_t(row) * src.n_lists + l), uint32_t(src.cap));
+            offs[l + 1] = src.count(row, l);
         __syncwarp();
         uint32_t carry = 0;
         for (int base = 0; base < src.n_lists; base += 32) {
@@ -326,7 +336,7 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
             continue;
         }
         // gather: flat element e -> (list, position) by binary search in the offsets; four loads in flight per lane
-        const uint64_t* row_keys = src.keys + int64_t(row) * src.n_lists * src.cap;
+
         for (uint32_t e0 = 0; e0 < total; e0 += 128) {
             uint64_t reg[4];
 #pragma unroll
@@ -339,7 +349,7 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
                         const int mid = (lo + hi) >> 1;
                         if (offs[mid] <= e) lo = mid; else hi = mid;
                     }
-                    reg[u] = raw_to_key(__ldcg(row_keys + int64_t(lo) * src.cap + (e - offs[lo])));
+                    reg[u] = src.load(src.list_ptr(row, lo) + (e - offs[lo]));
                 }
             }
 #pragma unroll
@@ -569,7 +579,8 @@ int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lis
                          uint32_t* big_rows, cudaStream_t stream) {
     if (n_lists > kMaxLists) { set_error("select_topk_keylists: %d lists per row > %d", n_lists, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
     if (n_rows == 0) return ANNCUR_OK;
-    KeyLists src{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, m_tiles, n_items, nullptr};
+    KeyLists src{keys, counts, n_lists, cap, flag_mode, thr_shared, mtile_flags, m_tiles, n_items, nullptr,
+                 int64_t(cap), int64_t(n_lists) * cap, 1};
     if (flag_mode == 2) {
         // REDO select: persistent CTA kernel over the (normally empty) list of flagged rows
         const int grid = n_rows < 2 * sm_count() ? n_rows : 2 * sm_count();
@@ -588,6 +599,41 @@ int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lis
     src.row_list = big_rows;
     const int grid2 = n_rows < 2 * sm_count() ? n_rows : 2 * sm_count();
     return launch_select(src, n_rows, k, idx_offset, row_scale, out_vals, out_idx, stream, 128, grid2);
+}
+
+// (val, idx) top-k lists -> 64-bit keys (padding idx < 0 -> key 0): the exchange format of the item-sharded search
+__global__ void topk_to_keys_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int64_t n, uint64_t* __restrict__ keys) {
+    for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx[t];
+        keys[t] = i < 0 ? 0ull : make_key(vals[t], uint32_t(i));
+    }
+}
+
+int topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint64_t* keys, cudaStream_t stream) {
+    const int64_t n = int64_t(n_rows) * k;
+    if (n == 0) return ANNCUR_OK;
+    topk_to_keys_kernel<<<unsigned((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, stream>>>(vals, idx, n, keys);
+    ANNCUR_LAUNCH_OK("topk_to_keys_kernel");
+    return ANNCUR_OK;
+}
+
+// Best k_out of n_shards sorted key lists per row, keys laid out [shard][row][k_in] (the all-gather's output as is).
+int merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out, float* out_vals, int64_t* out_idx,
+                    uint32_t* scratch_rows, cudaStream_t stream) {
+    if (n_rows == 0) return ANNCUR_OK;
+    if (n_shards > kMaxLists) { set_error("merge_topk_keys: %d shards > %d", n_shards, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
+    KeyLists src{keys, nullptr, n_shards, k_in, 0, nullptr, nullptr, 0, 0, nullptr, int64_t(n_rows) * k_in, int64_t(k_in), 0};
+    SelectOut o{out_vals, out_idx, 0, nullptr, k_out, next_pow2(k_out < 2 ? 2 : k_out)};
+    ANNCUR_CUDA_OK(cudaMemsetAsync(scratch_rows, 0, sizeof(uint32_t), stream));
+    const size_t smem = size_t(kWarpSelWarps) * (kWarpSelCap * sizeof(uint64_t) + (256 + size_t(n_shards) + 1) * sizeof(uint32_t));
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(select_lists_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int grid = (n_rows + kWarpSelWarps - 1) / kWarpSelWarps;
+    if (grid > 12 * sm_count()) grid = 12 * sm_count();
+    select_lists_warp_kernel<<<grid, kWarpSelWarps * 32, smem, stream>>>(src, o, n_rows, scratch_rows);
+    ANNCUR_LAUNCH_OK("select_lists_warp_kernel");
+    src.row_list = scratch_rows;                        // rows with more than kWarpSelCap candidates (n_shards * k_in large)
+    const int grid2 = n_rows < 2 * sm_count() ? n_rows : 2 * sm_count();
+    return launch_select(src, n_rows, k_out, 0, nullptr, out_vals, out_idx, stream, 128, grid2);
 }
 
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,

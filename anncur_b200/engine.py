@@ -259,6 +259,35 @@ def merge_topk(cand_vals, cand_idx, k):
     return vals, idx
 
 
+def topk_to_keys(vals, idx):
+    """(fp32 [n x k], int64 [n x k] global indices < 2^32) -> int64 tensor of 64-bit candidate keys [n x k]."""
+    lib = _lib.load()
+    vals = _f32(vals).contiguous()
+    idx = idx.to(device=vals.device, dtype=torch.int64).contiguous()
+    n, k = vals.shape
+    keys = torch.empty((n, k), dtype=torch.int64, device=vals.device)
+    if n > 0:
+        with torch.cuda.device(vals.device):
+            _lib.check(lib.anncur_topk_to_keys(_ptr(vals), _ptr(idx), n, k, _ptr(keys), _stream()))
+    return keys
+
+
+def merge_topk_keys(keys, k):
+    """keys: int64 [n_shards x n_rows x k_in] (the all-gathered buffer as is) -> best k per row (vals, idx)."""
+    lib = _lib.load()
+    assert keys.is_cuda and keys.dtype == torch.int64 and keys.dim() == 3 and keys.is_contiguous()
+    P, n, k_in = keys.shape
+    vals = torch.empty((n, k), dtype=torch.float32, device=keys.device)
+    idx = torch.empty((n, k), dtype=torch.int64, device=keys.device)
+    if n > 0:
+        nbytes = lib.anncur_merge_topk_keys_workspace_bytes(n)
+        ws = WORKSPACE.get("merge_keys", nbytes, keys.device)
+        with torch.cuda.device(keys.device):
+            _lib.check(lib.anncur_merge_topk_keys(_ptr(keys), P, n, k_in, int(k), _ptr(vals), _ptr(idx), _ptr(ws), ws.numel(),
+                                                  _stream()))
+    return vals, idx
+
+
 # ---- K5 + K6 --------------------------------------------------------------------------------------
 def rerank_overlap(exact, retr_idx, exact_idx, k_list):
     """Exact-score rerank of retrieved items + |exact[:k] & reranked[:k]| for each k in k_list.

@@ -52,8 +52,10 @@ class ShardedIndex:
             self._packed = packed if packed is not None else engine.PackedItems(E_local, precision)
             local_search = lambda Q, k: engine.score_topk(Q, self._packed, k, idx_offset=self.lo)   # noqa: E731
             merge = merge or engine.merge_topk
+            self._key_path = self.n_items_total < 2 ** 32          # 8-byte keys on the wire, merged as gathered
         self._local_search = local_search
         self._merge = merge
+        self._key_path = getattr(self, "_key_path", False)
 
     @classmethod
     def from_full(cls, E_full, **kw):
@@ -72,6 +74,12 @@ class ShardedIndex:
         vals, idx = self.local_topk(Q, k)
         if self.world_size == 1:
             return vals, idx
+        if self._key_path:
+            from . import engine
+            mine = engine.topk_to_keys(vals, idx)
+            gathered = torch.empty((self.world_size,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)   # [P, B, k]: merged as is
+            return engine.merge_topk_keys(gathered, k)
         mine = pack_candidates(vals, idx)
         B = mine.shape[0]
         gathered = torch.empty((self.world_size * B, mine.shape[1]), dtype=mine.dtype, device=mine.device)

@@ -133,6 +133,16 @@ ANNCUR_API int anncur_topk_rows_f32(const float* S, int64_t lds, int n_rows, int
 ANNCUR_API int anncur_merge_topk(const float* cand_vals, const int64_t* cand_idx, int n_rows, int n_cand,
                       int k, float* out_vals, int64_t* out_idx, void* stream);
 
+/* Key form of the same merge, the exchange format of the item-sharded search: a candidate is one
+ * 64-bit key = (order-preserving image of the fp32 score) << 32 | ~(uint32 global item index), so one unsigned compare
+ * is the library's total order and a rank ships 8 bytes per candidate.  anncur_topk_to_keys converts a (vals, idx)
+ * top-k result (global indices < 2^32; idx < 0 = padding -> key 0); anncur_merge_topk_keys takes the all-gathered
+ * buffer AS IS -- keys[shard][row][k_in] -- and writes the best k_out per row (k_out <= 1024). */
+ANNCUR_API int anncur_topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint64_t* keys, void* stream);
+ANNCUR_API size_t anncur_merge_topk_keys_workspace_bytes(int n_rows);
+ANNCUR_API int anncur_merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out,
+                           float* out_vals, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K5+K6: rerank the retrieved items by exact score, then overlap with the exact top-k -----
  * Replaces the per-query loop body at eval/run_retrieval_eval_wrt_exact_crossenc.py:108-113 /
  * ..._w_fixed_train_test_splits.py:91-96 (temp = -1e14; temp[idx] = exact[idx]; temp.topk) and

@@ -202,3 +202,24 @@ def test_topk_rows_large_rows_sampled_path(eng):
     v, i = eng.topk_rows(big[:, 1:], 64)
     ref = torch.topk(big[:, 1:].cpu(), 64, dim=1)
     assert torch.equal(v.cpu(), ref.values) and torch.equal(i.cpu(), ref.indices)
+
+
+def test_merge_topk_keys_equals_pair_merge(eng):
+    """Key-form exchange of the item-sharded search: keys[shard][row][k] merged as gathered == the (vals, idx) merge."""
+    rng = np.random.default_rng(11)
+    P, n, k = 8, 333, 100
+    vals = torch.from_numpy(rng.standard_normal((P, n, k), dtype=np.float32)).sort(dim=2, descending=True).values
+    vals[:, :, 50:] = vals[:, :, 49:50]                        # ties inside and across shards
+    idx = torch.stack([torch.stack([torch.from_numpy(rng.choice(1_000_000, k, replace=False)) + p * 1_000_000 for _ in range(n)])
+                       for p in range(P)]).to(torch.int64)
+    idx[3, :, 90:] = -1                                         # a shard that holds fewer than k items: padding
+    keys = torch.stack([eng.topk_to_keys(vals[p].cuda(), idx[p].cuda()) for p in range(P)]).contiguous()
+    for k_out in (1, 100, 500):
+        mv, mi = eng.merge_topk_keys(keys, k_out)
+        cv = vals.permute(1, 0, 2).reshape(n, P * k)
+        ci = idx.permute(1, 0, 2).reshape(n, P * k)
+        rv, ri = eng.merge_topk(cv.cuda(), ci.cuda(), k_out)
+        assert torch.equal(mv, rv) and torch.equal(mi, ri)
+    ov, oi = O.merge_topk(vals.numpy(), idx.numpy(), 100)
+    mv, mi = eng.merge_topk_keys(keys, 100)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mv.cpu().numpy(), ov)

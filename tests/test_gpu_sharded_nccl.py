@@ -1,0 +1,55 @@
+"""GPU, >= 2 devices (skipped otherwise): the item-sharded search over NCCL equals the single-GPU answer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from anncur_b200 import engine
+        from anncur_b200.sharded import ShardedIndex
+        rng = np.random.default_rng(4)
+        E = torch.from_numpy(rng.standard_normal((96, 150_001), dtype=np.float32)).cuda()
+        Q = torch.from_numpy(rng.standard_normal((300, 96), dtype=np.float32)).cuda()
+        ok = 1
+        for k in (10, 100):
+            v, i = ShardedIndex.from_full(E).search(Q, k)
+            rv, ri = engine.score_topk(Q, engine.PackedItems(E), k)
+            ok &= int(torch.equal(i, ri) and torch.allclose(v, rv, rtol=1e-5, atol=1e-5))
+        out = torch.tensor([ok], device="cuda")
+        dist.all_reduce(out, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(int(out.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_item_sharded_search_over_nccl_equals_single_gpu():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
