@@ -16,7 +16,7 @@
 //   rows*64-byte span and lands in shared memory in the canonical K-major SWIZZLE_64B layout.
 //
 // Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
-//   warp 0      TMA producer  (4-stage ring: Q tile 128 x 32 and E tile 256 x 32 per plane)
+//   warp 0      TMA producer  (ring of 6 stages x 1 k-block, fp32-grade; 3 stages x 4 k-blocks, one-pass kinds)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator 128 x 256 fp32,
 //               double-buffered in the 512 TMEM columns
 //   warps 2-9   epilogue: thread = one query row x one half of the tile's columns (two warps per TMEM
@@ -71,8 +71,15 @@ constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s: tra
 // CG = CTAs per MMA (1, or 2 = CTA pair: each CTA stages its own 128 queries and HALF of the 256-item tile)
 template <int PASSES, int CG> struct StageCfg {
     static constexpr int kBBytes = B_PLANE_BYTES / CG;
-    static constexpr int kStageBytes = PASSES == 3 ? 2 * (A_PLANE_BYTES + kBBytes) : (A_PLANE_BYTES + kBBytes);
-    static constexpr int kStages = PASSES == 3 ? (CG == 2 ? 6 : 4) : (CG == 2 ? 10 : 8);
+    // one k-block (32 wide) of operands: A (+ its low half) and this CTA's share of B (+ its low half)
+    static constexpr int kSubBytes = PASSES == 3 ? 2 * (A_PLANE_BYTES + kBBytes) : (A_PLANE_BYTES + kBBytes);
+    // k-blocks per pipeline stage.  The one-pass kinds issue only two MMAs per k-block, and the single issuing thread's
+    // barrier wait + commit per stage then costs as much as the tensor work it feeds (measured: tensor pipe 69 % busy).
+    // Four k-blocks per stage (8 MMAs per wait) took bf16 MAIN from 0.357 to 0.277 ms at C2; six per stage with two
+    // stages is slower again (3.29 vs 2.81 ms at N = 1M), and the fp32-grade kind (6 MMAs per k-block) gains nothing.
+    static constexpr int kKbPerStage = PASSES == 3 ? 1 : 4;
+    static constexpr int kStageBytes = kKbPerStage * kSubBytes;
+    static constexpr int kStages = PASSES == 3 ? (CG == 2 ? 6 : 4) : (CG == 2 ? 3 : 2);
 };
 
 enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
@@ -361,18 +368,22 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
                     const int item0 = tile * BLOCK_N + int(cta_rank) * (BLOCK_N / CG);     // this CTA's share of the item tile
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                    for (int kb0 = 0; kb0 < p.num_kb; kb0 += Cfg::kKbPerStage) {
+                        const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
                         mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag);
-                        const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes;
-                        if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * Cfg::kStageBytes));
-                        if (PASSES == 3) {
-                            load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
-                            load(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), m_tile * BLOCK_M, kb);
-                            load(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
-                            load(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes, &tmB1, full_bar(stage), item0, kb);
-                        } else {
-                            load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
-                            load(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
+                        if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * n_sub * Cfg::kSubBytes));
+                        for (int u = 0; u < n_sub; ++u) {
+                            const int kb = kb0 + u;
+                            const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes + uint32_t(u) * Cfg::kSubBytes;
+                            if (PASSES == 3) {
+                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                                load(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), m_tile * BLOCK_M, kb);
+                                load(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
+                                load(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes, &tmB1, full_bar(stage), item0, kb);
+                            } else {
+                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                                load(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
+                            }
                         }
                         if (!leader) mbar_arrive_leader(full_bar(stage));
                         if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -401,26 +412,29 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     mbar_wait(tempty_bar(buf), acc_phase ^ 1u, p.error_flag);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + uint32_t(buf) * BLOCK_N;
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                    for (int kb0 = 0; kb0 < p.num_kb; kb0 += Cfg::kKbPerStage) {
+                        const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
                         mbar_wait(full_bar(stage), phase, p.error_flag);
                         tcgen05_fence_after();
-                        const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes;
+                        for (int u = 0; u < n_sub; ++u) {
+                            const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes + uint32_t(u) * Cfg::kSubBytes;
 #pragma unroll
-                        for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-                            const uint32_t koff = uint32_t(ks) * UMMA_K * 2;          // bytes inside the 64 B row
-                            const uint32_t accum = (kb | ks) != 0 ? 1u : 0u;
-                            if (PASSES == 3) {
-                                const uint64_t a_h = make_smem_desc_sw64(sb + koff);
-                                const uint64_t a_l = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
-                                const uint64_t b_h = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + koff);
-                                const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
-                                mma(d_tmem, a_h, b_h, accum);
-                                mma(d_tmem, a_h, b_l, 1u);
-                                mma(d_tmem, a_l, b_h, 1u);
-                            } else {
-                                const uint64_t a = make_smem_desc_sw64(sb + koff);
-                                const uint64_t b = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
-                                mma(d_tmem, a, b, accum);
+                            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                                const uint32_t koff = uint32_t(ks) * UMMA_K * 2;          // bytes inside the 64 B row
+                                const uint32_t accum = (kb0 | u | ks) != 0 ? 1u : 0u;
+                                if (PASSES == 3) {
+                                    const uint64_t a_h = make_smem_desc_sw64(sb + koff);
+                                    const uint64_t a_l = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
+                                    const uint64_t b_h = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + koff);
+                                    const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
+                                    mma(d_tmem, a_h, b_h, accum);
+                                    mma(d_tmem, a_h, b_l, 1u);
+                                    mma(d_tmem, a_l, b_h, 1u);
+                                } else {
+                                    const uint64_t a = make_smem_desc_sw64(sb + koff);
+                                    const uint64_t b = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
+                                    mma(d_tmem, a, b, accum);
+                                }
                             }
                         }
                         commit(empty_bar(stage));                      // smem slot free (in both CTAs) once these MMAs retire
