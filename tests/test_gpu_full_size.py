@@ -1,0 +1,87 @@
+"""GPU, BASELINE.json's full sizes: properties that do not need a CPU pass over the whole problem
+(the oracle comparison at sizes it finishes in seconds lives in test_gpu_fused.py / test_gpu_kernels.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _enough_memory(gb):
+    return torch.cuda.is_available() and torch.cuda.get_device_properties(0).total_memory >= gb * 2**30
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from anncur_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+@pytest.mark.skipif(not _enough_memory(100), reason="needs a 100+ GB device")
+def test_c4_size_ten_million_items(eng):
+    """Config 4 size on one GPU: N = 10 000 000 items, k_i = 500, top-100.
+    (1) the fused result equals a plain fp32 torch matmul + topk over the same E (tie-tolerant set equality, 1e-4 scores);
+    (2) four item shards merged through the key exchange format equal the single-shard answer exactly;
+    (3) results are sorted best-first with unique indices."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, K, B, k = 10_000_000, 500, 130, 100
+    r = 32
+    W = torch.randn(K, r, device="cuda", generator=g)
+    E = torch.empty((K, N), device="cuda")
+    for a in range(0, N, 1_000_000):
+        Y = torch.randn(1_000_000, r, device="cuda", generator=g)
+        E[:, a:a + 1_000_000] = W @ Y.t() / r ** 0.5 + 0.05 * torch.randn(K, 1_000_000, device="cuda", generator=g)
+    Q = torch.randn(B, r, device="cuda", generator=g) @ W.t() / r ** 0.5 + 0.05 * torch.randn(B, K, device="cuda", generator=g)
+    packed = eng.PackedItems(E, "f32x3")
+    v, i = eng.score_topk(Q, packed, k)
+    assert bool((v[:, :-1] >= v[:, 1:]).all())
+    assert all(len(set(row.tolist())) == k for row in i.cpu())
+    # (1) dense fp32 reference on the device (torch matmul with TF32 off = fp32 FFMA/cuBLAS)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dense = Q @ E                                               # 130 x 10M fp32 = 5.2 GB
+    ref = torch.topk(dense, k, dim=1)
+    scale = dense.abs().amax(dim=1, keepdim=True)
+    got_scores = torch.gather(dense, 1, i)
+    assert float(((v - got_scores).abs() / scale).max()) <= 1e-4
+    kth = ref.values[:, -1:]
+    assert bool((got_scores >= kth - 1e-4 * scale).all())       # every returned item is a top-k item up to the tie band
+    same = (i.unsqueeze(2) == ref.indices.unsqueeze(1)).any(dim=2).float().mean()
+    assert float(same) > 0.999
+    del dense, ref, got_scores
+    # (2) item shards + key-form merge
+    P = 4
+    keys = []
+    for p in range(P):
+        lo, hi = p * N // P, (p + 1) * N // P
+        pv, pi = eng.score_topk(Q, eng.PackedItems(E[:, lo:hi], "f32x3"), k, idx_offset=lo)
+        keys.append(eng.topk_to_keys(pv, pi))
+    mv, mi = eng.merge_topk_keys(torch.stack(keys).contiguous(), k)
+    assert torch.equal(mi, i) and torch.allclose(mv, v, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not _enough_memory(100), reason="needs a 100+ GB device")
+def test_c5_size_reconstruction_error_is_additive_over_item_shards(eng):
+    """Config 5 size: 10 000 queries x 1 000 000 items, k_i = 200.  sum_j (Q E - A)^2 over all items equals the sum of
+    the same quantity over item shards (what a multi-GPU run all-reduces), and a planted exact-rank matrix gives ~0."""
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n, N, K = 10_000, 1_000_000, 200
+    Qm = torch.randn(n, K, device="cuda", generator=g)
+    E = torch.randn(K, N, device="cuda", generator=g) / K ** 0.5
+    A = torch.empty((n, N), device="cuda")                      # 40 GB
+    for a in range(0, N, 100_000):
+        A[:, a:a + 100_000] = Qm @ E[:, a:a + 100_000] + 0.01 * torch.randn(n, 100_000, device="cuda", generator=g)
+    err2, norm2 = eng.recon_error_rows(Qm, E, A)
+    parts_e = torch.zeros_like(err2)
+    parts_n = torch.zeros_like(norm2)
+    for a in range(0, N, 250_000):
+        e2, n2 = eng.recon_error_rows(Qm, E[:, a:a + 250_000], A[:, a:a + 250_000])
+        parts_e += e2
+        parts_n += n2
+    assert torch.allclose(parts_e, err2, rtol=1e-9) and torch.allclose(parts_n, norm2, rtol=1e-9)
+    rel = float(torch.sqrt(err2.sum()) / torch.sqrt(norm2.sum()))
+    assert abs(rel - 0.01 / (1.0 + 0.01 ** 2) ** 0.5) < 1e-3     # |noise| / |A| with unit-variance Q E
+    # rows whose A is exactly Q E reconstruct to fp32 rounding
+    A[:64] = Qm[:64] @ E
+    e2, n2 = eng.recon_error_rows(Qm[:64], E, A[:64])
+    assert float(torch.sqrt(e2.sum() / n2.sum())) < 1e-5
