@@ -35,6 +35,7 @@ PROTOTYPES = {
     "anncur_merge_topk_keys_workspace_bytes": (_sz, [_i]),
     "anncur_merge_topk_keys": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "anncur_rerank_overlap": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp, _i, C.POINTER(C.c_int), _i, _vp, _vp, _vp, _vp]),
+    "anncur_overlap_counts": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "anncur_recon_error_f32": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),
     "anncur_adaptive_round_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
     "anncur_adaptive_round": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),

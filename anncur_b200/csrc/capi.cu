@@ -230,6 +230,13 @@ int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n
                           out_rr_idx, out_rr_vals, out_common, cudaStream_t(stream));
 }
 
+int anncur_overlap_counts(const int64_t* a_idx, const int64_t* b_idx, int n_rows, int k, int32_t* out_common, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0, "overlap_counts: negative n_rows");
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(a_idx && b_idx && out_common, "overlap_counts: null pointer");
+    return overlap_counts(a_idx, b_idx, n_rows, k, out_common, cudaStream_t(stream));
+}
+
 int anncur_recon_error_f32(const float* Q, int ldq, const float* E, int64_t lde, const float* A, int64_t lda,
                            int n_rows, int64_t n_items, int k_dim, double* out_err2, double* out_norm2,
                            void* stream) {

@@ -36,6 +36,7 @@ int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out
 int rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,
                    int k_retr, const int64_t* exact_idx, int k_max, const int* k_list_host, int n_k,
                    int64_t* out_rr_idx, float* out_rr_vals, int32_t* out_common, cudaStream_t stream);
+int overlap_counts(const int64_t* a, const int64_t* b, int n_rows, int k, int32_t* out_common, cudaStream_t stream);
 
 // score_topk_umma.cu (tcgen05 / TMEM / TMA)
 size_t packed_items_bytes(int64_t n_items, int k_dim, int kind);

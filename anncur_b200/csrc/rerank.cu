@@ -103,4 +103,53 @@ int rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, 
     return ANNCUR_OK;
 }
 
+// K6 on its own: |set(a[row]) & set(b[row])| for two index lists per row (eval/eval_utils.py:139-150,
+// len(set(indices1).intersection(set(indices2)))).  One CTA per row: b is sorted in shared memory, duplicates inside a
+// row are counted once on either side (set semantics), every distinct a is looked up by binary search.
+__global__ void __launch_bounds__(RR_THREADS)
+overlap_counts_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int k, int n_pow2, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint64_t sb[];            // n_pow2 sorted b keys, then n_pow2 sorted a keys
+    uint64_t* sa = sb + n_pow2;
+    __shared__ int red[RR_THREADS / 32];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    // indices are mapped to unsigned keys that keep their order (offset by 2^63) so that -1 padding stays valid input
+    for (int t = tid; t < n_pow2; t += RR_THREADS) {
+        sb[t] = t < k ? uint64_t(b[int64_t(row) * k + t]) ^ 0x8000000000000000ull : 0ull;
+        sa[t] = t < k ? uint64_t(a[int64_t(row) * k + t]) ^ 0x8000000000000000ull : 0ull;
+    }
+    block_bitonic_sort_desc(sb, n_pow2);
+    block_bitonic_sort_desc(sa, n_pow2);                       // descending; real entries first (padding 0 is the minimum)
+    int c = 0;
+    for (int t = tid; t < k; t += RR_THREADS) {
+        const uint64_t key = sa[t];
+        if (t > 0 && sa[t - 1] == key) continue;               // duplicate inside a
+        int lo = 0, hi = k;                                    // first position in sb[0..k) with sb[pos] <= key (descending)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sb[mid] > key) lo = mid + 1; else hi = mid;
+        }
+        c += (lo < k && sb[lo] == key) ? 1 : 0;
+    }
+    c = warp_sum(c);
+    if ((tid & 31) == 0) red[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int w = 0; w < RR_THREADS / 32; ++w) s += red[w];
+        out[row] = s;
+    }
+}
+
+int overlap_counts(const int64_t* a, const int64_t* b, int n_rows, int k, int32_t* out_common, cudaStream_t stream) {
+    if (n_rows <= 0) return ANNCUR_OK;
+    if (k < 1 || k > 4096) { set_error("overlap_counts: k = %d outside [1, 4096]", k); return ANNCUR_E_INVALID; }
+    int n_pow2 = 2;
+    while (n_pow2 < k) n_pow2 <<= 1;
+    const size_t smem = sizeof(uint64_t) * 2 * size_t(n_pow2);
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(overlap_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    overlap_counts_kernel<<<n_rows, RR_THREADS, smem, stream>>>(a, b, k, n_pow2, out_common);
+    ANNCUR_LAUNCH_OK("overlap_counts_kernel");
+    return ANNCUR_OK;
+}
+
 }  // namespace anncur

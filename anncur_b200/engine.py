@@ -312,6 +312,23 @@ def rerank_overlap(exact, retr_idx, exact_idx, k_list):
     return rr_idx, rr_vals, common
 
 
+def overlap_counts(a_idx, b_idx):
+    """|set(a[row]) & set(b[row])| per row for two (n x k) int64 index lists (eval/eval_utils.py:139-150)."""
+    lib = _lib.load()
+    require_cuda()
+    a = torch.as_tensor(a_idx)
+    dev = a.device if a.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    a = a.to(device=dev, dtype=torch.int64).contiguous()
+    b = torch.as_tensor(b_idx).to(device=dev, dtype=torch.int64).contiguous()
+    assert a.dim() == 2 and a.shape == b.shape, (a.shape, b.shape)
+    n, k = a.shape
+    out = torch.zeros(n, dtype=torch.int32, device=dev)
+    if n > 0 and k > 0:
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_overlap_counts(_ptr(a), _ptr(b), n, k, _ptr(out), _stream()))
+    return out
+
+
 # ---- K7 -------------------------------------------------------------------------------------------
 def recon_error_rows(Q, E, A):
     """Per-row sum_j (Q.E - A)^2 and sum_j A^2 in fp64 without materialising Q.E."""

@@ -54,15 +54,11 @@ def compute_overlap(indices_list1, indices_list2):
     n = len(indices_list1)
     if n == 0 or len(indices_list2) == 0:
         return {m: ("mean 0.0", "std 0.0", "p50 0.0") for m in METRICS}
-    engine.require_cuda()
-    a = torch.as_tensor(np.asarray(indices_list1)).cuda()
-    b = torch.as_tensor(np.asarray(indices_list2)).cuda()
+    a = indices_list1 if torch.is_tensor(indices_list1) else torch.as_tensor(np.asarray(indices_list1))
+    b = indices_list2 if torch.is_tensor(indices_list2) else torch.as_tensor(np.asarray(indices_list2))
     assert a.shape == b.shape, f"Len of both indices is not same => {a.shape[-1]} != {b.shape[-1]}"
     k = a.shape[1]
-    # membership of each a[i, j] in row b[i]: sort b, binary search (unique indices per row assumed, as top-k lists are)
-    bs, _ = torch.sort(b, dim=1)
-    pos = torch.searchsorted(bs, a.contiguous()).clamp_(max=k - 1)
-    common = (torch.gather(bs, 1, pos) == a).sum(dim=1)
+    common = engine.overlap_counts(a, b)                                             # K6 kernel (set semantics)
     return _stats_strings(common.cpu().numpy(), k)
 
 

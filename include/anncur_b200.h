@@ -158,6 +158,11 @@ ANNCUR_API int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows
                           const int* k_list_host, int n_k, int64_t* out_rr_idx, float* out_rr_vals,
                           int32_t* out_common, void* stream);
 
+/* K6 on its own: out_common[row] = |set(a_idx[row, :]) & set(b_idx[row, :])| for two n_rows x k index lists
+ * (_compute_overlap_helper, eval/eval_utils.py:139-150).  k <= 4096. */
+ANNCUR_API int anncur_overlap_counts(const int64_t* a_idx, const int64_t* b_idx, int n_rows, int k,
+                          int32_t* out_common, void* stream);
+
 /* ---- K7: reconstruction error without materialising the approximation -------------------------
  * Replaces torch.norm((approx - A)[rows,:]) and torch.norm(A[rows,:])
  * (eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147): per row r of Q (n x k_dim) and

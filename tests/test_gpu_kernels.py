@@ -223,3 +223,14 @@ def test_merge_topk_keys_equals_pair_merge(eng):
     ov, oi = O.merge_topk(vals.numpy(), idx.numpy(), 100)
     mv, mi = eng.merge_topk_keys(keys, 100)
     assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mv.cpu().numpy(), ov)
+
+
+def test_overlap_counts_set_semantics(eng):
+    """eval/eval_utils.py:139-150: len(set(a) & set(b)) per row, duplicates and -1 padding included."""
+    rng = np.random.default_rng(9)
+    for (n, k, hi) in [(50, 1, 5), (200, 100, 300), (33, 1000, 5000), (7, 64, 40)]:       # last: many duplicates
+        a = rng.integers(-1, hi, size=(n, k))
+        b = rng.integers(-1, hi, size=(n, k))
+        got = eng.overlap_counts(torch.from_numpy(a), torch.from_numpy(b)).cpu().numpy()
+        want = np.array([len(set(a[r].tolist()) & set(b[r].tolist())) for r in range(n)])
+        assert np.array_equal(got, want)
