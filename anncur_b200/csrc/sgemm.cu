@@ -3,7 +3,8 @@
 //   Recon : never write C; accumulate per-row sum (C - T)^2 and sum T^2 against a target T
 //           (reconstruction error of eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147)
 // This is the exact-fp32 path (plain FFMA, k accumulated in order); the tensor-core path is in
-// score_topk_umma.cu.  128x128x16 CTA tile, 256 threads, 8x8 register tile, double-buffered smem.
+// score_topk_umma.cu.  128x128x16 CTA tile, 256 threads, 8x8 register tile (two 4-wide strips 64 apart in each
+// direction, so that the 128-bit shared-memory reads of a quarter warp are conflict-free), double-buffered smem.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,7 +32,10 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
     __shared__ double rowacc[2][BM];
 
     const int tid = threadIdx.x;
-    const int tx = tid % 16, ty = tid / 16;                 // 16 x 16 threads, each 8 x 8 outputs
+    const int tx = tid % 16, ty = tid / 16;                 // 16 x 16 threads, each 8 x 8 outputs:
+    // rows  ty*4 + {0..3} and 64 + ty*4 + {0..3},  columns  tx*4 + {0..3} and 64 + tx*4 + {0..3}
+    auto row_of = [&](int i) { return (i < 4 ? 0 : 64) + ty * 4 + (i & 3); };
+    auto col_of = [&](int j) { return (j < 4 ? 0 : 64) + tx * 4 + (j & 3); };
     const int64_t col0 = int64_t(blockIdx.x) * BN;
     const int row0 = blockIdx.y * BM;
 
@@ -48,10 +52,18 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
     float a_reg[8], b_reg[8];
     auto load_tiles = [&](int k0) {
         const int gr = row0 + a_r;
+        const float* ap = A + int64_t(gr) * lda + k0 + a_c;
+        if (gr < m && k0 + a_c + 7 < k && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+            float4 v0 = __ldg(reinterpret_cast<const float4*>(ap));
+            float4 v1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+            a_reg[0] = v0.x; a_reg[1] = v0.y; a_reg[2] = v0.z; a_reg[3] = v0.w;
+            a_reg[4] = v1.x; a_reg[5] = v1.y; a_reg[6] = v1.z; a_reg[7] = v1.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int gk = k0 + a_c + i;
-            a_reg[i] = (gr < m && gk < k) ? __ldg(A + int64_t(gr) * lda + gk) : 0.f;
+            for (int i = 0; i < 8; ++i) {
+                int gk = k0 + a_c + i;
+                a_reg[i] = (gr < m && gk < k) ? __ldg(A + int64_t(gr) * lda + gk) : 0.f;
+            }
         }
         const int gk = k0 + b_r;
         const int64_t gc = col0 + b_c;
@@ -84,12 +96,12 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
             float a[TM], b[TN];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
-                float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + i]);
+                float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][row_of(i)]);
                 a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
             }
 #pragma unroll
             for (int j = 0; j < TN; j += 4) {
-                float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
+                float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][col_of(j)]);
                 b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
             }
 #pragma unroll
@@ -104,17 +116,19 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
     if constexpr (sizeof(Epi) == sizeof(StoreEpilogue)) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            const int gr = row0 + ty * TM + i;
+            const int gr = row0 + row_of(i);
             if (gr >= m) continue;
-            const int64_t gc = col0 + tx * TN;
-            float* dst = epi.C + int64_t(gr) * epi.ldc + gc;
-            if (gc + TN - 1 < n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-            } else {
 #pragma unroll
-                for (int j = 0; j < TN; ++j)
-                    if (gc + j < n) dst[j] = acc[i][j];
+            for (int jh = 0; jh < TN; jh += 4) {
+                const int64_t gc = col0 + col_of(jh);
+                float* dst = epi.C + int64_t(gr) * epi.ldc + gc;
+                if (gc + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(acc[i][jh], acc[i][jh + 1], acc[i][jh + 2], acc[i][jh + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (gc + j < n) dst[j] = acc[i][jh + j];
+                }
             }
         }
     } else {
@@ -122,12 +136,12 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            const int gr = row0 + ty * TM + i;
+            const int gr = row0 + row_of(i);
             double e2 = 0.0, n2 = 0.0;
             if (gr < m) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
-                    const int64_t gc = col0 + tx * TN + j;
+                    const int64_t gc = col0 + col_of(j);
                     if (gc < n) {
                         float t = __ldg(epi.T + int64_t(gr) * epi.ldt + gc);
                         float d = acc[i][j] - t;
@@ -142,7 +156,7 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
                 e2 += __shfl_xor_sync(0xffffffffu, e2, o);
                 n2 += __shfl_xor_sync(0xffffffffu, n2, o);
             }
-            if (tx == 0) { rowacc[0][ty * TM + i] = e2; rowacc[1][ty * TM + i] = n2; }
+            if (tx == 0) { rowacc[0][row_of(i)] = e2; rowacc[1][row_of(i)] = n2; }
         }
         __syncthreads();
         if (tid < BM && row0 + tid < m) {
