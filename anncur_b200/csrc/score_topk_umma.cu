@@ -764,23 +764,28 @@ __global__ void fill_zero_scores_kernel(int n_queries, int k, int64_t n_items, i
 }
 
 // ---- SAMPLE -> per-row threshold -------------------------------------------------------------------
-// One warp per query row: j-th largest of the row's n_smax group maxima (MSD radix select on the
-// order-preserving 32-bit image of the floats), published as the exclusive bound of the MAIN pass.
-__global__ void __launch_bounds__(256)
+// One CTA per query row: j-th largest of the row's n_smax group maxima (MSD radix select on the order-preserving
+// 32-bit image of the floats, staged in shared memory when they fit), published as the exclusive bound of MAIN.
+constexpr int THR_THREADS = 128;
+constexpr int THR_SMEM_KEYS = 8192;
+
+__global__ void __launch_bounds__(THR_THREADS)
 sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_queries, int j, const float* __restrict__ row_delta,
                         uint32_t* __restrict__ thr_shared) {
-    __shared__ uint32_t hist_all[8][256];
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_queries) return;
-    const uint32_t lane = lane_id();
-    uint32_t* hist = hist_all[threadIdx.x >> 5];
+    __shared__ uint32_t keys_s[THR_SMEM_KEYS];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_red[2][THR_THREADS / 32];
+    __shared__ uint32_t s_prefix, s_mask, s_need, s_stop;
+    const int row = blockIdx.x, tid = threadIdx.x;
     const float* v = smax + int64_t(row) * n_smax;
-    uint32_t need = uint32_t(j);
-    bool have = n_smax >= j;
-    // group maxima of one row lie in a narrow band: start at the first byte in which largest and smallest differ
+    const bool staged = n_smax <= THR_SMEM_KEYS;
+    auto key_at = [&](int t) { return staged ? keys_s[t] : float_to_ordered(__ldcg(v + t)); };
+    // stage + min / max: group maxima of one row lie in a narrow band, the select starts at the first byte in which
+    // the largest and the smallest differ
     uint32_t kmax = 0u, kmin = 0xffffffffu;
-    for (int t = int(lane); t < n_smax; t += 32) {
+    for (int t = tid; t < n_smax; t += THR_THREADS) {
         const uint32_t key = float_to_ordered(__ldcg(v + t));
+        if (staged) keys_s[t] = key;
         kmax = max(kmax, key);
         kmin = min(kmin, key);
     }
@@ -789,50 +794,67 @@ sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_querie
         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
         kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     }
-    const int first_shift = (31 - __clz(int((kmax ^ kmin) | 1u))) & ~7;
-    uint32_t mask = first_shift >= 24 ? 0u : ~((1u << (first_shift + 8)) - 1u);
-    uint32_t prefix = kmax & mask;
-    for (int shift = first_shift; have && shift >= 0; shift -= 8) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
-        __syncwarp();
-        for (int t = int(lane); t < n_smax; t += 32) {
-            const uint32_t key = float_to_ordered(__ldcg(v + t));
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = kmax; s_red[1][tid >> 5] = kmin; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < THR_THREADS / 32; ++w) { kmax = max(kmax, s_red[0][w]); kmin = min(kmin, s_red[1][w]); }
+        const int first_shift = (31 - __clz(int((kmax ^ kmin) | 1u))) & ~7;
+        s_mask = first_shift >= 24 ? 0u : ~((1u << (first_shift + 8)) - 1u);
+        s_prefix = kmax & s_mask;
+        s_need = uint32_t(j);
+        s_stop = uint32_t(first_shift);                 // reused as the current shift
+    }
+    __syncthreads();
+    const bool have = n_smax >= j;
+    bool ok = have;
+    for (int shift = int(s_stop); ok && shift >= 0; shift -= 8) {
+        for (int t = tid; t < 256; t += THR_THREADS) hist[t] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, mask = s_mask;
+        for (int t = tid; t < n_smax; t += THR_THREADS) {
+            const uint32_t key = key_at(t);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
-        __syncwarp();
-        uint32_t c[8], lane_sum = 0;
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t need = s_need;
+            uint32_t c[8], lane_sum = 0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
-        uint32_t incl = lane_sum;                       // inclusive suffix sum towards the higher digits
+            for (int b = 0; b < 8; ++b) { c[b] = hist[tid * 8 + b]; lane_sum += c[b]; }
+            uint32_t incl = lane_sum;                   // inclusive suffix sum towards the higher digits
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t t = __shfl_down_sync(0xffffffffu, incl, off);
-            if (lane + off < 32) incl += t;
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_down_sync(0xffffffffu, incl, off);
+                if (tid + off < 32) incl += t;
+            }
+            uint32_t running = incl - lane_sum;
+            bool found = false;
+            uint32_t d = 0, new_need = 0;
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+                if (!found && running + c[b] >= need) { found = true; d = uint32_t(tid) * 8 + b; new_need = need - running; }
+                running += c[b];
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, found);
+            if (ballot != 0) {
+                const int src = 31 - __clz(int(ballot));
+                d = __shfl_sync(0xffffffffu, d, src);
+                new_need = __shfl_sync(0xffffffffu, new_need, src);
+            }
+            if (tid == 0) {
+                if (ballot == 0) s_need = 0xffffffffu;  // fewer than j values: no threshold
+                else { s_prefix = prefix | (d << shift); s_mask = mask | (0xffu << shift); s_need = new_need; }
+            }
         }
-        uint32_t running = incl - lane_sum;
-        bool found = false;
-        uint32_t d = 0, new_need = 0;
-#pragma unroll
-        for (int b = 7; b >= 0; --b) {
-            if (!found && running + c[b] >= need) { found = true; d = lane * 8 + b; new_need = need - running; }
-            running += c[b];
-        }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, found);
-        if (ballot == 0) { have = false; break; }
-        const int src = 31 - __clz(int(ballot));
-        d = __shfl_sync(0xffffffffu, d, src);
-        need = __shfl_sync(0xffffffffu, new_need, src);
-        prefix |= d << shift;
-        mask |= 0xffu << shift;
-        __syncwarp();
+        __syncthreads();
+        ok = s_need != 0xffffffffu;
     }
-    if (lane == 0) {
-        // prefix = ordered image of the j-th largest maximum; scores >= it are kept (exclusive bound = it - 1)
+    if (tid == 0) {
+        // s_prefix = ordered image of the j-th largest maximum; scores >= it are kept (exclusive bound = it - 1)
         const uint32_t lowest = float_to_ordered(-INFINITY);
         uint32_t bound = lowest;
-        if (have && prefix > lowest) {
-            const float t = ordered_to_float(prefix) - row_delta[row];      // see pack_queries_kernel
+        if (ok && s_prefix > lowest) {
+            const float t = ordered_to_float(s_prefix) - row_delta[row];      // see pack_queries_kernel
             bound = float_to_ordered(t);
             bound = bound > lowest ? bound - 1u : lowest;
         }
@@ -943,7 +965,9 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     const int cg = cta_group_for(pl.m_tiles);                 // work is scheduled over CTA pairs when cg == 2
     const int units = sms / cg > 0 ? sms / cg : 1;
     const int m_groups = pl.m_tiles > 0 ? (pl.m_tiles + cg - 1) / cg : 1;
-    // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row
+    // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row.  (Coarser strides
+    // were tried for large item sets: G = 64 makes SAMPLE 4x cheaper but leaves ~800 instead of ~460 survivors per
+    // row at k = 100, which costs more in the select than it saves -- measured slower at N = 1M for B = 64 and 4096.)
     for (int G : {16, 8, 4}) {
         const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-6);
         const int64_t s_items = (n_items + G - 1) / G;
@@ -1198,7 +1222,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         else rc = bf16 ? launch_fused<1, true, 8, 1>(a0, a0, s0, s0, sp, false, stream)
                        : launch_fused<1, false, 8, 1>(a0, a0, s0, s0, sp, false, stream);
         if (rc != ANNCUR_OK) return rc;
-        sample_threshold_kernel<<<qgrid, 256, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr);
+        sample_threshold_kernel<<<n_queries, THR_THREADS, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr);
         ANNCUR_LAUNCH_OK("sample_threshold_kernel");
     }
     // MAIN
