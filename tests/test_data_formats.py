@@ -103,3 +103,31 @@ def test_cur_method_on_split_files_matches_reference_results(tmp_path, gold, dum
         tk, kr, an = key.split("|")
         if int(an.split("anc_n_e=")[1]) in k_i_subset:
             assert sorted(res[tk][kr][an]) == sorted(m)             # same metric keys as the reference writes
+
+
+def test_cli_flags_mirror_the_reference_script():
+    from anncur_b200.run_fixed_split_eval import build_parser
+    flags = {a.dest for a in build_parser()._actions}
+    reference_flags = {"data_name", "eval_method", "res_dir", "test_data_file", "train_data_file", "n_seeds", "bi_model_file",
+                       "batch_size", "e2e_fname", "n_fixed_anc_ent", "mention_file", "entity_file", "mode", "misc", "use_wandb"}
+    assert reference_flags <= flags                                   # ..._w_fixed_train_test_splits.py:515-542
+    with pytest.raises(SystemExit):
+        from anncur_b200.run_fixed_split_eval import main
+        main(["--res_dir", "x", "--test_data_file", "t.pkl", "--eval_method", "bienc"])
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_writes_reference_layout(tmp_path, gold, dump):
+    from anncur_b200.run_fixed_split_eval import main
+    a = gold["splits"]["args"]
+    F.write_splits(dump, a["num_train_ment_vals"], a["num_splits"], a["seed"], a["dev_frac"], str(tmp_path / "splits"))
+    c = gold["cur_eval"]
+    f = main(["--data_name", "yugioh", "--eval_method", "cur", "--res_dir", str(tmp_path / "res"), "--misc", "t",
+              "--test_data_file", str(tmp_path / "splits" / c["test"]), "--train_data_file", str(tmp_path / "splits" / c["train"]),
+              "--n_seeds", "2", "--k_i", "50", "200", "--k_r", "100", "500"])
+    d = json.load(open(f))
+    assert sorted(d) == ["other_args", "seed=0", "seed=1"]
+    assert d["other_args"]["retriever_params"] == c["retrieval_params"] and d["other_args"]["eval_method"] == "cur"
+    want = c["eval_res_common_frac_mean_std"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"][0]
+    got = d["seed=0"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"]["exact_vs_reranked_approx_retvr~common_frac_mean"]
+    assert abs(got - want) <= 0.03
