@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libanncur_b200.so")
 
 ABI_VERSION = 1
-KIND_F32X3, KIND_BF16 = 0, 1
+KIND_F32X3, KIND_BF16, KIND_F32R = 0, 1, 2
 MAX_K, MAX_K_FUSED = 2048, 1024
 E_INVALID, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
 
@@ -25,6 +25,7 @@ PROTOTYPES = {
     "anncur_pack_items": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "anncur_score_topk_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "anncur_score_topk": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_score_topk_redo_rows": (_i, [_vp, _i, _i64, _i, _i, _i, C.POINTER(C.c_int), _vp]),
     "anncur_search_host_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "anncur_search_host": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_score_topk_f32_workspace_bytes": (_sz, [_i, _i64, _i, _i]),

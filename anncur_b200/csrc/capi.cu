@@ -107,6 +107,11 @@ int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed
                             out_idx, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+int anncur_score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind,
+                                int* redo_rows_host, void* stream) {
+    ANNCUR_REQUIRE(workspace && redo_rows_host, "score_topk_redo_rows: null pointer");
+    return score_topk_redo_rows(workspace, n_queries, n_items, k_dim, k, kind, redo_rows_host, cudaStream_t(stream));
+}
 
 // ---- host-buffer search: H2D of the query batch, fused score + top-k, D2H of the result ----------
 static size_t host_stage_q_bytes(int n_queries, int k_dim) { return align_up(sizeof(float) * size_t(n_queries) * size_t(k_dim > 0 ? k_dim : 1), 256); }

@@ -19,6 +19,12 @@ int merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, in
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
                       int64_t* out_idx, cudaStream_t stream);
 
+// refine_topk.cu
+int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
+                         int64_t idx_offset, const float* Q, int ldq, int k_dim, const float* ET, int ld,
+                         const float* row_inv_scale, float* out_vals, int64_t* out_idx, uint32_t* thr_shared,
+                         uint32_t* mtile_flags, int m_tiles, int64_t n_items, cudaStream_t stream);
+
 // sgemm.cu
 int sgemm_rowmajor(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int m,
                    int64_t n, int k, cudaStream_t stream);
@@ -46,6 +52,9 @@ size_t score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int
 int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
                      int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
                      int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+int score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind, int* redo_rows_host,
+                         cudaStream_t stream);
 
 // smallest j with P[Binomial(n, p) >= j] <= eps (rank used by the sampled thresholds)
 int binomial_tail_rank(int n, double p, double eps);

@@ -1,0 +1,298 @@
+// F32R, second half: exact fp32 re-scoring of the survivors of the one-pass filter, then the row top-k.
+//
+// The fused kernel (score_topk_umma.cu, kind F32R) leaves, per query row, the items whose score UPPER bound
+// UB_n = A_n + b_n reached the row's push threshold T (a lower bound of the k-th best fp32 score).  One warp per row:
+//   1. gather the row's candidates (keys ordered by UB) into shared memory;
+//   2. re-score the k candidates with the largest UB in fp32 from the item-major copy of E in the packed index
+//      (S_n = sum_i q_i e_in, the reference's torch.matmul arithmetic, eval/matrix_approx_zeshel.py:109-119);
+//      the smallest of these k scores, s_min, is a lower bound of the true k-th best score;
+//   3. re-score every other candidate whose UB reaches s_min (an item with UB < s_min cannot be in the top-k);
+//   4. top-k of the re-scored candidates by (S, lower index), sorted best-first (torch.topk, :121-126);
+//   5. certificate: every item that was NOT pushed has S <= UB <= T, so the result is the exact top-k if the k-th
+//      re-scored value is > T.  Rows that fail it, rows with fewer than min(k, N) candidates and rows with a list
+//      that filled up are flagged for the REDO pass (3-pass kind, streaming from -inf).
+// On the bench workloads a row has ~400 candidates, of which k + ~6 are re-scored (2 KB of E each, one coalesced
+// 512-byte request per warp load).
+#include "common.cuh"
+#include "kernels.h"
+#include "warp_select.cuh"
+
+namespace anncur {
+
+constexpr int kRefCap = 1024;          // candidates of one row held in shared memory
+constexpr int kRefWarps = 4;
+constexpr int kRefMaxLists = 1024;
+constexpr int kRefBatch = 4;           // candidates re-scored together (their loads are all in flight at once)
+
+struct RefineParams {
+    const uint64_t* cand;     // [row][n_lists][cap] RAW entries (common.cuh: raw_to_key); score word = UB in scaled units
+    const uint32_t* counts;   // [row][n_lists]; top bit = the list filled up
+    int n_lists, cap, n_rows, k, n_sort;
+    int64_t n_items, idx_offset;
+    const float* Q;           // [row][ldq] fp32 queries as the caller passed them
+    int ldq, k_dim;
+    const float* ET;          // [item][ld] fp32 item-major copy of E
+    int ld;
+    const float* row_inv_scale;   // UB (scaled units) * row_inv_scale[row] = UB in the units of S
+    float* out_vals;
+    int64_t* out_idx;
+    uint32_t* thr_shared;     // in: the row's push threshold (exclusive, ordered image); out: -inf = REDO this row, +inf = done
+    uint32_t* mtile_flags;    // [m_tiles] query-tile flags, then [1] number of flagged rows, then the flagged rows
+    int m_tiles;
+};
+
+// dot(q, ET[item]) for kRefBatch items at once; q is held in registers as U float4 per lane (k_dim <= 128 U)
+template <int U>
+__device__ __forceinline__ void rescore_batch(const float4 (&qv)[U], const float* __restrict__ ET, int ld, int ld4,
+                                              const uint32_t (&item)[kRefBatch], float (&s)[kRefBatch]) {
+    const int lane = int(lane_id());
+    float4 e[kRefBatch][U];
+#pragma unroll
+    for (int c = 0; c < kRefBatch; ++c) {
+        const float4* rowp = reinterpret_cast<const float4*>(ET + int64_t(item[c]) * ld);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = lane + 32 * u;
+            e[c][u] = j < ld4 ? __ldg(rowp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kRefBatch; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc = fmaf(qv[u].x, e[c][u].x, acc);
+            acc = fmaf(qv[u].y, e[c][u].y, acc);
+            acc = fmaf(qv[u].z, e[c][u].z, acc);
+            acc = fmaf(qv[u].w, e[c][u].w, acc);
+        }
+        s[c] = warp_sum(acc);
+    }
+}
+
+// any k_dim: q re-read from global (L1) per 128-float chunk
+__device__ __forceinline__ float rescore_long(const float* __restrict__ q, int k_dim, const float* __restrict__ ET, int ld,
+                                              int ld4, uint32_t item) {
+    const int lane = int(lane_id());
+    const float4* rowp = reinterpret_cast<const float4*>(ET + int64_t(item) * ld);
+    float acc = 0.f;
+    for (int j = lane; j < ld4; j += 32) {
+        const float4 e = __ldg(rowp + j);
+        const int i = 4 * j;
+        acc = fmaf(i + 0 < k_dim ? __ldg(q + i + 0) : 0.f, e.x, acc);
+        acc = fmaf(i + 1 < k_dim ? __ldg(q + i + 1) : 0.f, e.y, acc);
+        acc = fmaf(i + 2 < k_dim ? __ldg(q + i + 2) : 0.f, e.z, acc);
+        acc = fmaf(i + 3 < k_dim ? __ldg(q + i + 3) : 0.f, e.w, acc);
+    }
+    return warp_sum(acc);
+}
+
+template <int U>
+__global__ void __launch_bounds__(kRefWarps * 32)
+refine_topk_kernel(const RefineParams p) {
+    extern __shared__ __align__(16) uint64_t ref_smem[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t* keys = ref_smem + size_t(warp) * kRefCap;
+    uint32_t* words = reinterpret_cast<uint32_t*>(ref_smem + size_t(kRefWarps) * kRefCap);
+    uint32_t* hist = words + warp * 256;
+    uint16_t* work = reinterpret_cast<uint16_t*>(words + kRefWarps * 256) + warp * kRefCap;       // positions to re-score
+    uint32_t* offs = words + kRefWarps * 256 + kRefWarps * (kRefCap / 2) + warp * (p.n_lists + 1);
+    const uint32_t k = uint32_t(p.k);
+    const int ld4 = p.ld >> 2;
+    const uint32_t lowest = float_to_ordered(-INFINITY);
+
+    for (int row = blockIdx.x * kRefWarps + warp; row < p.n_rows; row += gridDim.x * kRefWarps) {
+        // ---- list lengths -> offsets; a marked list gives the row up ------------------------------------
+        bool marked = false;
+        for (int l = int(lane); l < p.n_lists; l += 32) {
+            const uint32_t c = __ldcg(p.counts + int64_t(row) * p.n_lists + l);
+            marked |= (c & 0x80000000u) != 0u;
+            offs[l + 1] = min(c & 0x7fffffffu, uint32_t(p.cap));
+        }
+        marked = __any_sync(0xffffffffu, marked);
+        __syncwarp();
+        uint32_t carry = 0;
+        for (int base = 0; base < p.n_lists; base += 32) {
+            const int l = base + int(lane);
+            const uint32_t v = l < p.n_lists ? offs[l + 1] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= uint32_t(off)) incl += t;
+            }
+            if (l < p.n_lists) offs[l + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) offs[0] = 0;
+        const uint32_t total = carry;
+        __syncwarp();
+        const int64_t need = p.n_items < int64_t(k) ? p.n_items : int64_t(k);
+        bool redo = marked || int64_t(total) < need || total > uint32_t(kRefCap);
+        const float inv_scale = p.row_inv_scale[row];
+        const float to_scaled = 1.0f / inv_scale;                          // power of two: exact
+        const uint32_t thr_ord = __ldcg(p.thr_shared + row);
+
+        if (!redo) {
+            // ---- gather (flat element -> (list, position) by binary search in the offsets) ---------------
+            for (uint32_t e0 = 0; e0 < total; e0 += 128) {
+                uint64_t reg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + uint32_t(u) * 32u + lane;
+                    reg[u] = 0ull;
+                    if (e < total) {
+                        int lo = 0, hi = p.n_lists;
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (offs[mid] <= e) lo = mid; else hi = mid;
+                        }
+                        reg[u] = raw_to_key(__ldcg(p.cand + (int64_t(row) * p.n_lists + lo) * p.cap + (e - offs[lo])));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + uint32_t(u) * 32u + lane;
+                    if (e < total) keys[e] = reg[u];
+                }
+            }
+            __syncwarp();
+            // ---- the query row, in registers -------------------------------------------------------------
+            const float* q = p.Q + int64_t(row) * p.ldq;
+            float4 qv[U > 0 ? U : 1];
+            if (U > 0) {
+#pragma unroll
+                for (int u = 0; u < (U > 0 ? U : 1); ++u) {
+                    const int i = 4 * (int(lane) + 32 * u);
+                    qv[u].x = i + 0 < p.k_dim ? __ldg(q + i + 0) : 0.f;
+                    qv[u].y = i + 1 < p.k_dim ? __ldg(q + i + 1) : 0.f;
+                    qv[u].z = i + 2 < p.k_dim ? __ldg(q + i + 2) : 0.f;
+                    qv[u].w = i + 3 < p.k_dim ? __ldg(q + i + 3) : 0.f;
+                }
+            }
+            // re-score the candidates at positions work[0 .. n_work): keys[pos] becomes (S, item); returns min S
+            auto rescore = [&](uint32_t n_work) {
+                float s_min = INFINITY;
+                for (uint32_t i0 = 0; i0 < n_work; i0 += kRefBatch) {
+                    uint32_t pos[kRefBatch], item[kRefBatch];
+                    float s[kRefBatch];
+#pragma unroll
+                    for (int c = 0; c < kRefBatch; ++c) {
+                        pos[c] = work[min(i0 + uint32_t(c), n_work - 1u)];
+                        item[c] = key_index(keys[pos[c]]);
+                    }
+                    if (U > 0) {
+                        rescore_batch<(U > 0 ? U : 1)>(qv, p.ET, p.ld, ld4, item, s);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kRefBatch; ++c) s[c] = rescore_long(q, p.k_dim, p.ET, p.ld, ld4, item[c]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < kRefBatch; ++c) {
+                        if (i0 + uint32_t(c) < n_work) {
+                            s_min = fminf(s_min, s[c]);
+                            if (lane == 0) keys[pos[c]] = make_key(s[c], item[c]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                return s_min;
+            };
+            // ---- phase A: the k candidates with the largest upper bound ------------------------------------
+            uint64_t prefix = 0ull, mask = 0ull;
+            if (total > k) warp_radix_kth(keys, total, k, hist, prefix, mask);
+            uint32_t n_work = 0;
+            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const bool win = t < total && (keys[t] & mask) >= prefix;
+                const uint32_t ballot = __ballot_sync(0xffffffffu, win);
+                if (win) work[n_work + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
+                hist[t0 >> 5] = ballot;                                    // who has been re-scored (hist is free here)
+                n_work += __popc(ballot);
+            }
+            __syncwarp();
+            const float s_min = rescore(n_work);
+            // ---- phase B: every other candidate whose upper bound reaches s_min; the rest is dropped --------
+            if (total > k) {
+                const float s_min_scaled = s_min * to_scaled;
+                uint32_t n_more = 0;
+                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    const bool done = (hist[t0 >> 5] >> lane) & 1u;
+                    const bool open = t < total && !done;
+                    const bool more = open && key_score(keys[t]) >= s_min_scaled;
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, more);
+                    if (more) work[n_more + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
+                    if (open && !more) keys[t] = 0ull;
+                    n_more += __popc(ballot);
+                }
+                __syncwarp();
+                if (n_more > 0) rescore(n_more);
+            }
+            // ---- top-k of the re-scored candidates ----------------------------------------------------------
+            uint32_t n_live = warp_compact_ge(keys, total, 0ull, 0ull);   // drops the zeroed entries
+            if (n_live > k) {
+                warp_radix_kth(keys, n_live, k, hist, prefix, mask);
+                n_live = warp_compact_ge(keys, n_live, prefix, mask);
+            }
+            for (uint32_t t = n_live + lane; t < uint32_t(p.n_sort); t += 32) keys[t] = 0ull;
+            __syncwarp();
+            warp_bitonic_sort_desc(keys, uint32_t(p.n_sort));
+            // ---- certificate: items that were never pushed have S <= UB <= T (all in scaled units) ---------
+            if (int64_t(total) < p.n_items && thr_ord > lowest) {
+                const float kth_scaled = key_score(keys[need - 1]) * to_scaled;
+                if (!(kth_scaled > ordered_to_float(thr_ord))) redo = true;
+            }
+            if (!redo) {
+                for (uint32_t t = lane; t < k; t += 32) {
+                    const uint64_t key = keys[t];
+                    const bool ok = key != 0ull;
+                    p.out_vals[int64_t(row) * k + t] = ok ? key_score(key) : ANNCUR_PAD_VAL;
+                    p.out_idx[int64_t(row) * k + t] = ok ? int64_t(key_index(key)) + p.idx_offset : int64_t(-1);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            p.thr_shared[row] = float_to_ordered(redo ? -INFINITY : INFINITY);
+            if (redo) {
+                atomicOr(p.mtile_flags + row / 128, 1u);
+                uint32_t* n_flagged = p.mtile_flags + p.m_tiles;
+                n_flagged[1 + atomicAdd(n_flagged, 1u)] = uint32_t(row);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
+                         int64_t idx_offset, const float* Q, int ldq, int k_dim, const float* ET, int ld,
+                         const float* row_inv_scale, float* out_vals, int64_t* out_idx, uint32_t* thr_shared,
+                         uint32_t* mtile_flags, int m_tiles, int64_t n_items, cudaStream_t stream) {
+    if (n_lists > kRefMaxLists) { set_error("refine_topk_keylists: %d lists per row > %d", n_lists, kRefMaxLists); return ANNCUR_E_UNSUPPORTED; }
+    if (k > kRefCap) { set_error("refine_topk_keylists: k = %d > %d", k, kRefCap); return ANNCUR_E_UNSUPPORTED; }
+    if (n_rows == 0) return ANNCUR_OK;
+    int n_sort = 2;
+    while (n_sort < k) n_sort <<= 1;
+    RefineParams p{cand, counts, n_lists, cap, n_rows, k, n_sort, n_items, idx_offset, Q, ldq, k_dim, ET, ld,
+                   row_inv_scale, out_vals, out_idx, thr_shared, mtile_flags, m_tiles};
+    const size_t smem = size_t(kRefWarps) * (kRefCap * sizeof(uint64_t) + 256 * sizeof(uint32_t) + kRefCap * sizeof(uint16_t) +
+                                             (size_t(n_lists) + 1) * sizeof(uint32_t));
+    int grid = (n_rows + kRefWarps - 1) / kRefWarps;
+    if (grid > 8 * sm_count()) grid = 8 * sm_count();
+    const int ld4 = ld >> 2;
+    auto launch = [&](auto kernel) {
+        ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kernel<<<grid, kRefWarps * 32, smem, stream>>>(p);
+        ANNCUR_LAUNCH_OK("refine_topk_kernel");
+        return ANNCUR_OK;
+    };
+    if (ld4 <= 32) return launch(refine_topk_kernel<1>);
+    if (ld4 <= 64) return launch(refine_topk_kernel<2>);
+    if (ld4 <= 128) return launch(refine_topk_kernel<4>);
+    return launch(refine_topk_kernel<0>);
+}
+
+}  // namespace anncur

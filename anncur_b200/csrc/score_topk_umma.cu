@@ -10,6 +10,16 @@
 //           h.h + h.l + l.h accumulate in one fp32 TMEM tile -- fp32-grade scores at 1/3 of the
 //           f16 tensor rate, and each operand still costs 4 bytes per element like plain fp32.
 //   BF16  : single bf16 pass.
+//   F32R  : fp32 results at the one-pass rate ("filter and refine").  MAIN is ONE f16 pass on the high halves, but
+//           the contraction carries one extra anchor slot: the item side holds ||e_n|| 2^-5, the query side
+//           +-1.05 ||q|| 2^-5, so the accumulator is A_n +- b_n with b_n = 1.05 2^-10 ||q|| ||e_n|| >= |S_n - A_n|
+//           (Cauchy-Schwarz over the per-element fp16 rounding errors; S_n = the fp32 score).  SAMPLE runs with
+//           the minus sign (lower bounds -> threshold T <= k-th best S), MAIN with the plus sign (upper bounds:
+//           every item that can be in the top-k is pushed), and refine_topk_keylists (refine_topk.cu) re-scores
+//           the ~k candidates whose upper bound reaches the k-th best fp32 score from an item-major fp32 copy of E
+//           kept in the packed index.  No step depends on a statistical error model: rows that end short, overflow
+//           a list or fail the final certificate (k-th refined score > push threshold) go to REDO, which is the
+//           3-pass kind on the same planes.
 //
 // Layout in HBM (built once per index by pack_items, per batch for Q by pack_queries):
 //   plane[kb][row][32]  16-bit elements, kb = k / 32; a TMA box {32, rows, 1} is one contiguous
@@ -100,6 +110,9 @@ struct FusedParams {
     float* smax;             // MODE_SAMPLE: [n_queries][n_smax] group maxima
     int n_smax;
     int close_compact;       // MODE_MAIN: cut lists back to k at the end of a work item (streaming mode: tightens the shared bound)
+    int a_last_kb;           // k-block coordinate of the query high plane used for the LAST k-block (F32R: the +b / -b / 0 variants)
+    int filter;              // MODE_MAIN, F32R: scores are upper bounds -> lists are never cut back; a list that fills up is
+                             // marked (top bit of its count) and the row goes to REDO
     int* error_flag;
 };
 
@@ -374,14 +387,15 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                         if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * n_sub * Cfg::kSubBytes));
                         for (int u = 0; u < n_sub; ++u) {
                             const int kb = kb0 + u;
+                            const int akb = kb == p.num_kb - 1 ? p.a_last_kb : kb;
                             const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes + uint32_t(u) * Cfg::kSubBytes;
                             if (PASSES == 3) {
-                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, akb);
                                 load(sb + A_PLANE_BYTES, &tmA1, full_bar(stage), m_tile * BLOCK_M, kb);
                                 load(sb + 2 * A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
                                 load(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes, &tmB1, full_bar(stage), item0, kb);
                             } else {
-                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, kb);
+                                load(sb, &tmA0, full_bar(stage), m_tile * BLOCK_M, akb);
                                 load(sb + A_PLANE_BYTES, &tmB0, full_bar(stage), item0, kb);
                             }
                         }
@@ -465,7 +479,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             const int row_c = row_ok ? row : 0;
             uint64_t* list = p.cand + (int64_t(row_c) * n_lists + chunk * EPI_HALVES + half) * int64_t(CAP);
             float* smax_row = p.smax + int64_t(row_c) * p.n_smax;
-            uint32_t cnt = 0;
+            uint32_t cnt = 0, overflow = 0;
             float thr_own = -INFINITY;
             float thr = INFINITY;
 
@@ -518,6 +532,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             };
             // make room: a 32-column group can add at most 32 survivors to a list
             auto make_room = [&]() {
+                if (p.filter) {                                  // upper-bound scores cannot be cut back to k: give the row up
+                    if (cnt > CAP - 32u) { overflow = 0x80000000u; thr = INFINITY; }
+                    return;
+                }
                 uint32_t full_mask = __ballot_sync(0xffffffffu, cnt > CAP - 32u);
                 while (full_mask) {
                     const int src = __ffs(int(full_mask)) - 1;
@@ -541,7 +559,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                 // in streaming mode (other chunks of the row tighten it as they compact)
                 if (!sample && (tile == t0 || p.close_compact != 0)) {
                     thr = INFINITY;
-                    if (row_ok) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
+                    if (row_ok && overflow == 0u) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
                 }
                 mbar_wait(tfull_bar(buf), acc_phase, p.error_flag);
                 tcgen05_fence_after();
@@ -585,7 +603,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     atomicMax(p.thr_shared + row, float_to_ordered(key_score(kth)) - 1u);
                 }
             }
-            if (row_ok) p.counts[int64_t(row) * n_lists + chunk * EPI_HALVES + half] = cnt;
+            if (row_ok) p.counts[int64_t(row) * n_lists + chunk * EPI_HALVES + half] = cnt | overflow;
         }
     }
 
@@ -682,18 +700,23 @@ pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int
 }
 
 // Q (B x k_dim, k contiguous) -> plane[kb][b][32], one warp per query row, per-row power-of-two scale.
-template <bool BF16>
+// F32R: slot k_dim of the last k-block of the high plane holds +1.05 ||q'|| 2^-5 (rounded up); k-blocks num_kb and
+// num_kb + 1 are copies of that last k-block with the slot set to -1.05 ||q'|| 2^-5 and to 0 (see FusedParams::a_last_kb).
+template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int k_dim, int num_kb,
                     const float* __restrict__ e_scale, uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l,
                     float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared,
                     uint32_t* __restrict__ mtile_flags, const float* __restrict__ e_rowmax, float* __restrict__ row_delta) {
+    constexpr bool BF16 = KIND == ANNCUR_KIND_BF16;
+    constexpr bool X3 = KIND == ANNCUR_KIND_F32X3;
+    constexpr bool R = KIND == ANNCUR_KIND_F32R;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_queries) return;
     const uint32_t lane = lane_id();
     const float* q = Q + int64_t(row) * ldq;
     float scale = 1.f;
-    float bound = 0.f;
+    float bound = 0.f, norm2 = 0.f;
     constexpr int RC = 16;                       // rows of up to 512 anchors are read once and kept in registers
     if (num_kb <= RC) {
         float xr[RC];
@@ -714,7 +737,8 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
                 const int kidx = u * 32 + int(lane);
                 const float x = xr[u] * scale;
                 split_store<BF16>(x, plane_h, plane_l, (int64_t(u) * n_queries + row) * 32 + lane);
-                if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+                if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+                if (R) norm2 = fmaf(x, x, norm2);
             }
         }
     } else {
@@ -730,10 +754,11 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
             int kidx = kb * 32 + int(lane);
             float x = kidx < k_dim ? q[kidx] * scale : 0.f;
             split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
-            if (!BF16 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+            if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
+            if (R) norm2 = fmaf(x, x, norm2);
         }
     }
-    if (!BF16) {
+    if (X3) {
         // SAMPLE scores use the high fp16 halves only.  Each product q_i e_i is then off by q_i e_i (eps_q + eps_e)
         // with rounding errors |eps| <= 2^-12 (std 2^-12 / sqrt 3), so a sampled score is off by a sum of K such
         // terms: std <= 0.82 * 2^-12 * sqrt(sum_i q_i^2 max_n e_in^2) (scaled units of the accumulator).  The
@@ -744,11 +769,62 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     } else if (lane == 0) {
         row_delta[row] = 0.f;
     }
+    if (R) {
+        // Error bound of the one-pass score A = sum_i h(q'_i) h(e'_i) against S = sum_i q'_i e'_i (scaled operands):
+        // |x - h(x)| <= 2^-11 |x| + 2^-25 (fp16 rounding, subnormals included), so by Cauchy-Schwarz
+        //   |S - A| <= (2^-10 + 2^-22) sqrt(|q'|^2 + K 2^-28) sqrt(|e'_n|^2 + K 2^-28).
+        // The slot product is 1.05 x that (rounded up on both sides): the 5 % cover the fp32 accumulation order of
+        // the tensor pipe and of the re-scoring kernel (each < 2^-17 sum_i |q'_i e'_i|) and the rounding of the norms.
+        norm2 = warp_sum(norm2);
+        const float slot = sqrtf(norm2 + float(k_dim) * 0x1p-28f) * (1.05f * 1.001f * 0x1p-5f);
+        const uint16_t slot_p = __half_as_ushort(__float2half_ru(slot));
+        const int kb_s = num_kb - 1, l_s = k_dim & 31;                       // the slot lives at anchor index k_dim
+        const int kidx = kb_s * 32 + int(lane);
+        const float x = kidx < k_dim ? q[kidx] * scale : 0.f;
+        const uint16_t h = __half_as_ushort(__float2half_rn(x));
+        const bool is_slot = int(lane) == l_s;
+        plane_h[(int64_t(kb_s) * n_queries + row) * 32 + lane] = is_slot ? slot_p : h;                       // +b: upper bounds
+        plane_h[(int64_t(num_kb) * n_queries + row) * 32 + lane] = is_slot ? uint16_t(slot_p | 0x8000u) : h; // -b: lower bounds
+        plane_h[(int64_t(num_kb + 1) * n_queries + row) * 32 + lane] = h;                                    //  0: plain scores
+    }
     if (lane == 0) {
         row_inv_scale[row] = 1.f / (scale * e_scale[0]);
         thr_shared[row] = float_to_ordered(-INFINITY);
         if ((row % BLOCK_M) == 0) mtile_flags[row / BLOCK_M] = 0u;
         if (row == 0) mtile_flags[(n_queries + BLOCK_M - 1) / BLOCK_M] = 0u;      // number of flagged rows
+    }
+}
+
+// F32R: slot k_dim of every item = ||e'_n|| 2^-5 rounded up (see pack_queries_kernel), one thread per item
+__global__ void __launch_bounds__(256)
+item_bound_slot_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int k_dim, const float* __restrict__ scale_p,
+                       uint16_t* __restrict__ plane_h) {
+    const float scale = scale_p[0];
+    for (int64_t n = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; n < n_items; n += int64_t(gridDim.x) * blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < k_dim; ++i) { const float x = E[int64_t(i) * lde + n] * scale; s = fmaf(x, x, s); }
+        const float ne = sqrtf(s + float(k_dim) * 0x1p-28f) * (1.001f * 0x1p-5f);
+        plane_h[(int64_t(k_dim >> 5) * n_items + n) * 32 + (k_dim & 31)] = __half_as_ushort(__float2half_ru(ne));
+    }
+}
+
+// F32R: item-major fp32 copy ET[n][ld] of E (k_dim x N), values untouched; 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+transpose_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int k_dim, int ld, float* __restrict__ ET) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n0 = int64_t(blockIdx.x) * 32;
+    const int k0 = blockIdx.y * 32;
+    for (int j = ty; j < 32; j += 8) {
+        const int kk = k0 + j;
+        const int64_t n = n0 + tx;
+        tile[j][tx] = (kk < k_dim && n < n_items) ? E[int64_t(kk) * lde + n] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t n = n0 + j;
+        const int kk = k0 + tx;
+        if (n < n_items && kk < ld) ET[n * ld + kk] = tile[tx][j];
     }
 }
 
@@ -897,9 +973,29 @@ static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int 
     return ANNCUR_OK;
 }
 
-static int num_kb_for(int k_dim) { return (k_dim + BLOCK_K - 1) / BLOCK_K; }
-static int planes_for(int kind) { return kind == ANNCUR_KIND_F32X3 ? 2 : 1; }
-static size_t plane_bytes(int64_t rows, int k_dim) { return align_up(size_t(num_kb_for(k_dim)) * size_t(rows) * BLOCK_K * 2, 256); }
+// F32R carries one extra anchor slot (index k_dim) for the error-bound term
+static int num_kb_for(int k_dim, int kind) { return (k_dim + (kind == ANNCUR_KIND_F32R ? 1 : 0) + BLOCK_K - 1) / BLOCK_K; }
+static int planes_for(int kind) { return kind == ANNCUR_KIND_BF16 ? 1 : 2; }
+static size_t plane_bytes(int64_t rows, int num_kb) { return align_up(size_t(num_kb) * size_t(rows) * BLOCK_K * 2, 256); }
+// query planes: F32R keeps two more copies of the last k-block of the high plane (bound slot = -b and 0)
+static int q_plane_kb(int num_kb, int kind) { return num_kb + (kind == ANNCUR_KIND_F32R ? 2 : 0); }
+static int et_ld(int k_dim) { return (k_dim + 3) & ~3; }                 // row stride (floats) of the item-major fp32 copy
+static bool valid_kind(int kind) { return kind == ANNCUR_KIND_F32X3 || kind == ANNCUR_KIND_BF16 || kind == ANNCUR_KIND_F32R; }
+
+struct PackedLayout {               // byte offsets inside a packed item index
+    int num_kb;
+    size_t plane, off_scratch, off_rowmax, off_et, total;
+};
+static PackedLayout packed_layout(int64_t n_items, int k_dim, int kind) {
+    PackedLayout L{};
+    L.num_kb = num_kb_for(k_dim, kind);
+    L.plane = plane_bytes(n_items, L.num_kb);
+    L.off_scratch = size_t(planes_for(kind)) * L.plane;
+    L.off_rowmax = L.off_scratch + 256;
+    L.off_et = L.off_rowmax + align_up(sizeof(float) * size_t(L.num_kb) * BLOCK_K, 256);
+    L.total = L.off_et + (kind == ANNCUR_KIND_F32R ? align_up(sizeof(float) * size_t(n_items) * et_ld(k_dim), 256) : 0);
+    return L;
+}
 
 static uint32_t pow2_at_least(uint32_t want) {
     uint32_t cap = 256;
@@ -959,7 +1055,7 @@ struct FusedPlan {
 static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
     FusedPlan pl{};
     const int sms = sm_count();
-    pl.num_kb = num_kb_for(k_dim);
+    pl.num_kb = num_kb_for(k_dim, kind);
     pl.m_tiles = (n_queries + BLOCK_M - 1) / BLOCK_M;
     pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
     const int cg = cta_group_for(pl.m_tiles);                 // work is scheduled over CTA pairs when cg == 2
@@ -994,7 +1090,7 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     pl.cap = pow2_at_least(want);
     if (pl.cap > 2048u) pl.cap = 2048u;
     size_t off = 0;
-    pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, k_dim);
+    pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, q_plane_kb(pl.num_kb, kind));
     pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
@@ -1009,14 +1105,14 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
 }
 
 size_t packed_items_bytes(int64_t n_items, int k_dim, int kind) {
-    if (n_items <= 0 || k_dim <= 0) return 256;
-    // planes | 256 B max-abs scratch | per-anchor-dimension max |E| (num_kb * 32 floats)
-    return size_t(planes_for(kind)) * plane_bytes(n_items, k_dim) + 256 + align_up(sizeof(float) * size_t(num_kb_for(k_dim)) * BLOCK_K, 256);
+    if (n_items <= 0 || k_dim <= 0 || !valid_kind(kind)) return 256;
+    // planes | 256 B max-abs scratch | per-anchor-dimension max |E| (num_kb * 32 floats) | F32R: E^T (N x et_ld fp32)
+    return packed_layout(n_items, k_dim, kind).total;
 }
 
 int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind, void* packed, float* e_scale_out,
                cudaStream_t stream) {
-    if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_BF16) { set_error("pack_items: unknown kind %d", kind); return ANNCUR_E_INVALID; }
+    if (!valid_kind(kind)) { set_error("pack_items: unknown kind %d", kind); return ANNCUR_E_INVALID; }
     const bool bf16 = kind == ANNCUR_KIND_BF16;
     if (n_items <= 0 || k_dim <= 0) {
         finish_scale_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(packed), e_scale_out, true);
@@ -1024,10 +1120,12 @@ int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind
         return ANNCUR_OK;
     }
     if (n_items >= (int64_t(1) << 31) - BLOCK_N) { set_error("pack_items: n_items %lld too large for one shard", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
-    const size_t pb = plane_bytes(n_items, k_dim);
-    uint16_t* plane_h = reinterpret_cast<uint16_t*>(packed);
-    uint16_t* plane_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(packed) + pb);
-    uint32_t* maxabs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(packed) + size_t(planes_for(kind)) * pb);
+    if (kind == ANNCUR_KIND_F32R && k_dim > ANNCUR_MAX_K_DIM_F32R) { set_error("pack_items: k_dim %d > %d for kind F32R", k_dim, ANNCUR_MAX_K_DIM_F32R); return ANNCUR_E_UNSUPPORTED; }
+    const PackedLayout L = packed_layout(n_items, k_dim, kind);
+    char* base = reinterpret_cast<char*>(packed);
+    uint16_t* plane_h = reinterpret_cast<uint16_t*>(base);
+    uint16_t* plane_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(base + L.plane);
+    uint32_t* maxabs = reinterpret_cast<uint32_t*>(base + L.off_scratch);
     ANNCUR_CUDA_OK(cudaMemsetAsync(maxabs, 0, 4, stream));
     if (!bf16) {
         absmax_kernel<<<sm_count() * 8, 256, 0, stream>>>(E, lde, k_dim, n_items, maxabs);
@@ -1035,19 +1133,43 @@ int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind
     }
     finish_scale_kernel<<<1, 1, 0, stream>>>(maxabs, e_scale_out, bf16);
     ANNCUR_LAUNCH_OK("finish_scale_kernel");
-    float* rowmax = reinterpret_cast<float*>(reinterpret_cast<char*>(maxabs) + 256);
-    row_absmax_kernel<<<num_kb_for(k_dim) * BLOCK_K, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, rowmax);
+    float* rowmax = reinterpret_cast<float*>(base + L.off_rowmax);
+    row_absmax_kernel<<<L.num_kb * BLOCK_K, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, rowmax);
     ANNCUR_LAUNCH_OK("row_absmax_kernel");
-    dim3 grid(unsigned((n_items + 63) / 64), unsigned(num_kb_for(k_dim)));
+    dim3 grid(unsigned((n_items + 63) / 64), unsigned(L.num_kb));
     if (bf16) pack_items_kernel<true><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
     else pack_items_kernel<false><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
     ANNCUR_LAUNCH_OK("pack_items_kernel");
+    if (kind == ANNCUR_KIND_F32R) {
+        const int64_t blocks = (n_items + 255) / 256;
+        item_bound_slot_kernel<<<unsigned(blocks < 16 * sm_count() ? blocks : 16 * sm_count()), 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h);
+        ANNCUR_LAUNCH_OK("item_bound_slot_kernel");
+        const int ld = et_ld(k_dim);
+        dim3 tgrid(unsigned((n_items + 31) / 32), unsigned((ld + 31) / 32));
+        transpose_items_kernel<<<tgrid, 256, 0, stream>>>(E, lde, n_items, k_dim, ld, reinterpret_cast<float*>(base + L.off_et));
+        ANNCUR_LAUNCH_OK("transpose_items_kernel");
+    }
     return ANNCUR_OK;
 }
 
 size_t score_topk_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int kind) {
     if (n_queries <= 0 || n_items <= 0 || k_dim <= 0 || k <= 0) return 256;
     return make_plan(n_queries, n_items, k_dim, k, kind).total;
+}
+
+// rows of the last call on `workspace` that the sampled path had to hand to the REDO pass (blocks on `stream`)
+int score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind, int* redo_rows_host,
+                         cudaStream_t stream) {
+    *redo_rows_host = 0;
+    if (n_queries <= 0 || n_items <= 0 || k_dim <= 0 || k <= 0 || !valid_kind(kind)) return ANNCUR_OK;
+    const FusedPlan pl = make_plan(n_queries, n_items, k_dim, k, kind);
+    if (pl.sample_stride == 0) return ANNCUR_OK;                 // unsampled calls stream from -inf, there is no REDO
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(workspace) + pl.off_flags);
+    uint32_t n = 0;
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(&n, flags + pl.m_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    ANNCUR_CUDA_OK(cudaStreamSynchronize(stream));
+    *redo_rows_host = int(n);
+    return ANNCUR_OK;
 }
 
 // ---- optional event timing of the fused kernel (anncur_profile_*) ---------------------------------
@@ -1148,7 +1270,7 @@ static int cta_group_for(int m_tiles) {
 int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
                      int64_t n_items, int k_dim, int kind, int k, int64_t idx_offset, float* out_vals,
                      int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_BF16) { set_error("score_topk: unknown kind %d", kind); return ANNCUR_E_INVALID; }
+    if (!valid_kind(kind)) { set_error("score_topk: unknown kind %d", kind); return ANNCUR_E_INVALID; }
     if (k < 1 || k > ANNCUR_MAX_K_FUSED) { set_error("score_topk: k = %d outside [1, %d]", k, ANNCUR_MAX_K_FUSED); return ANNCUR_E_INVALID; }
     if (n_queries <= 0) return ANNCUR_OK;
     if (n_items <= 0 || k_dim <= 0) {
@@ -1165,9 +1287,11 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         return ANNCUR_E_INVALID;
     }
     const bool bf16 = kind == ANNCUR_KIND_BF16;
+    const bool refine = kind == ANNCUR_KIND_F32R;
     const bool sampled = pl.sample_stride != 0;
     char* ws = reinterpret_cast<char*>(workspace);
-    const size_t qpb = plane_bytes(n_queries, k_dim);
+    const int q_kb = q_plane_kb(pl.num_kb, kind);
+    const size_t qpb = plane_bytes(n_queries, q_kb);
     uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
     uint16_t* q_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
     float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
@@ -1181,42 +1305,49 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     int* err = reinterpret_cast<int*>(ws + pl.off_err);
 
     const int qgrid = (n_queries + 7) / 8;
-    const size_t epb = plane_bytes(n_items, k_dim);
+    const PackedLayout L = packed_layout(n_items, k_dim, kind);
     const char* items = reinterpret_cast<const char*>(packed_items);
-    const float* e_rowmax = reinterpret_cast<const float*>(items + size_t(planes_for(kind)) * epb + 256);
-    if (bf16) pack_queries_kernel<true><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
-    else pack_queries_kernel<false><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    const float* e_rowmax = reinterpret_cast<const float*>(items + L.off_rowmax);
+    if (bf16) pack_queries_kernel<ANNCUR_KIND_BF16><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else if (refine) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
     ANNCUR_LAUNCH_OK("pack_queries_kernel");
 
     const int cg = cta_group_for(pl.m_tiles);
     const int b_box = BLOCK_N / cg;                       // a CTA of a pair stages half of each item tile
     CUtensorMap a0, a1, b0, b1;
     int rc;
-    if ((rc = make_plane_map(&a0, q_h, n_queries, pl.num_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&a0, q_h, n_queries, q_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
     if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, b_box, bf16)) != ANNCUR_OK) return rc;
     if (bf16) { a1 = a0; b1 = b0; }
     else {
-        if ((rc = make_plane_map(&a1, q_l, n_queries, pl.num_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
-        if ((rc = make_plane_map(&b1, items + epb, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&a1, q_l, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&b1, items + L.plane, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
     }
-    auto launch = [&](const CUtensorMap& mb0, const CUtensorMap& mb1, const FusedParams& fp, bool timed) {
+    // the full-precision launch: 3 passes (fp32-grade kinds) or the single bf16 pass
+    auto launch_full = [&](const FusedParams& fp, bool timed) {
         if (cg == 2)
-            return bf16 ? dispatch_cap<1, true, 2>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream)
-                        : dispatch_cap<3, false, 2>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream);
-        return bf16 ? dispatch_cap<1, true, 1>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream)
-                    : dispatch_cap<3, false, 1>(pl.cap, a0, a1, mb0, mb1, fp, timed, stream);
+            return bf16 ? dispatch_cap<1, true, 2>(pl.cap, a0, a1, b0, b1, fp, timed, stream)
+                        : dispatch_cap<3, false, 2>(pl.cap, a0, a1, b0, b1, fp, timed, stream);
+        return bf16 ? dispatch_cap<1, true, 1>(pl.cap, a0, a1, b0, b1, fp, timed, stream)
+                    : dispatch_cap<3, false, 1>(pl.cap, a0, a1, b0, b1, fp, timed, stream);
     };
     FusedParams fp{};
     fp.n_queries = n_queries; fp.num_kb = pl.num_kb; fp.k = k; fp.m_tiles = pl.m_tiles;
     fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err; fp.smax = smax; fp.n_smax = pl.n_smax;
+    // query high-plane variant of the last k-block (F32R only): +b at num_kb - 1, -b at num_kb, plain scores at num_kb + 1
+    const int akb_upper = pl.num_kb - 1, akb_lower = refine ? pl.num_kb : pl.num_kb - 1, akb_plain = refine ? pl.num_kb + 1 : pl.num_kb - 1;
+    fp.a_last_kb = akb_plain;
 
     if (sampled) {
         // SAMPLE: every G-th item through a strided view of the same planes, ONE tensor pass on the high halves
-        // (the threshold is lowered by the row's error bound) -> 32-column group maxima -> thresholds
+        // -> 32-column group maxima -> thresholds.  F32X3: plain one-pass scores, the threshold is lowered by the row's
+        // statistical error bound; F32R: lower bounds A - b, the threshold needs no margin.
         CUtensorMap s0;
         if ((rc = make_plane_map(&s0, items, n_items, pl.num_kb, b_box, bf16, pl.sample_stride)) != ANNCUR_OK) return rc;
         FusedParams sp = fp;
         sp.mode = MODE_SAMPLE; sp.n_items = pl.s_items; sp.n_tiles = pl.s_tiles; sp.n_chunks = pl.s_chunks;
+        sp.a_last_kb = akb_lower;
         if (cg == 2) rc = bf16 ? launch_fused<1, true, 8, 2>(a0, a0, s0, s0, sp, false, stream)
                                : launch_fused<1, false, 8, 2>(a0, a0, s0, s0, sp, false, stream);
         else rc = bf16 ? launch_fused<1, true, 8, 1>(a0, a0, s0, s0, sp, false, stream)
@@ -1228,13 +1359,27 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     // MAIN
     fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
     fp.close_compact = sampled ? 0 : 1;
-    if ((rc = launch(b0, b1, fp, true)) != ANNCUR_OK) return rc;
-    rc = select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
-                              out_idx, sampled ? 1 : 0, thr, flags, pl.m_tiles, n_items, big_rows, stream);
-    if (rc != ANNCUR_OK || !sampled) return rc;
-    // REDO: rows that came up short restart from -inf in streaming mode; unflagged query tiles are skipped
+    if (refine && sampled) {
+        // one f16 pass of upper bounds, then the exact re-scoring of the candidates (refine_topk.cu)
+        fp.a_last_kb = akb_upper; fp.filter = 1;
+        rc = cg == 2 ? dispatch_cap<1, false, 2>(pl.cap, a0, a0, b0, b0, fp, true, stream)
+                     : dispatch_cap<1, false, 1>(pl.cap, a0, a0, b0, b0, fp, true, stream);
+        if (rc != ANNCUR_OK) return rc;
+        rc = refine_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, Q, ldq, k_dim,
+                                  reinterpret_cast<const float*>(items + L.off_et), et_ld(k_dim), inv_scale, out_vals, out_idx,
+                                  thr, flags, pl.m_tiles, n_items, stream);
+        if (rc != ANNCUR_OK) return rc;
+        fp.a_last_kb = akb_plain; fp.filter = 0;
+    } else {
+        if ((rc = launch_full(fp, true)) != ANNCUR_OK) return rc;
+        rc = select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
+                                  out_idx, sampled ? 1 : 0, thr, flags, pl.m_tiles, n_items, big_rows, stream);
+        if (rc != ANNCUR_OK || !sampled) return rc;
+    }
+    // REDO: rows that came up short (F32R: or filled a list, or failed the certificate) restart from -inf in streaming
+    // mode with the full-precision launch; unflagged query tiles are skipped
     fp.mtile_flags = flags; fp.close_compact = 1;
-    if ((rc = launch(b0, b1, fp, false)) != ANNCUR_OK) return rc;
+    if ((rc = launch_full(fp, false)) != ANNCUR_OK) return rc;
     return select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
                                 out_idx, 2, thr, flags, pl.m_tiles, n_items, big_rows, stream);
 }

@@ -10,6 +10,7 @@
 // shared memory they are sorted there directly and the radix passes are skipped.
 #include "common.cuh"
 #include "kernels.h"
+#include "warp_select.cuh"
 
 namespace anncur {
 
@@ -361,87 +362,13 @@ select_lists_warp_kernel(KeyLists src, SelectOut o, int n_rows, uint32_t* __rest
         __syncwarp();
         uint32_t n_win = total;
         if (total > uint32_t(o.k)) {
-            // MSD radix select of the k-th largest key.  The candidates all passed the same threshold, so their
-            // leading bytes coincide: start at the first byte in which the row's largest and smallest key differ.
-            uint64_t kmax = 0ull, kmin = ~0ull;
-            for (uint32_t t = lane; t < total; t += 32) {
-                const uint64_t key = keys[t];
-                kmax = key > kmax ? key : kmax;
-                kmin = key < kmin ? key : kmin;
-            }
-            kmin = warp_min_u64(kmin);
-            kmax = ~warp_min_u64(~kmax);
-            const int top_bit = 63 - __clzll((long long)((kmax ^ kmin) | 1ull));
-            const int first_shift = top_bit & ~7;
-            uint64_t mask = first_shift >= 56 ? 0ull : ~((1ull << (first_shift + 8)) - 1ull);
-            uint64_t prefix = kmax & mask;
-            uint32_t need = uint32_t(o.k);
-            for (int shift = first_shift; shift >= 0; shift -= 8) {
-#pragma unroll
-                for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
-                __syncwarp();
-                for (uint32_t t = lane; t < total; t += 32) {
-                    const uint64_t key = keys[t];
-                    if ((key & mask) == prefix) atomicAdd(&hist[uint32_t(key >> shift) & 255u], 1u);
-                }
-                __syncwarp();
-                uint32_t c[8], lane_sum = 0;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
-                uint32_t suf = lane_sum;                 // inclusive suffix sum towards the higher digits
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    uint32_t t = __shfl_down_sync(0xffffffffu, suf, off);
-                    if (lane + off < 32) suf += t;
-                }
-                uint32_t running = suf - lane_sum;
-                bool found = false;
-                uint32_t d = 0, new_need = 0, bucket = 0;
-#pragma unroll
-                for (int b = 7; b >= 0; --b) {
-                    if (!found && running + c[b] >= need) { found = true; d = lane * 8 + b; new_need = need - running; bucket = c[b]; }
-                    running += c[b];
-                }
-                const uint32_t ballot = __ballot_sync(0xffffffffu, found);
-                __syncwarp();
-                if (ballot == 0) break;
-                const int srcl = 31 - __clz(int(ballot));
-                d = __shfl_sync(0xffffffffu, d, srcl);
-                need = __shfl_sync(0xffffffffu, new_need, srcl);
-                bucket = __shfl_sync(0xffffffffu, bucket, srcl);
-                prefix |= uint64_t(d) << shift;
-                mask |= 0xffull << shift;
-                if (bucket == need) break;               // digit bucket taken whole
-            }
-            // in-place stable compaction of the winners (write index never passes the read index)
-            uint32_t running = 0;
-            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                const uint64_t key = t < total ? keys[t] : 0ull;
-                const bool keep = key != 0ull && (key & mask) >= prefix;
-                const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-                __syncwarp();
-                if (keep) keys[running + __popc(ballot & ((1u << lane) - 1u))] = key;
-                running += __popc(ballot);
-                __syncwarp();
-            }
-            n_win = running;
+            uint64_t prefix, mask;
+            warp_radix_kth(keys, total, uint32_t(o.k), hist, prefix, mask);
+            n_win = warp_compact_ge(keys, total, prefix, mask);
         }
         for (uint32_t t = n_win + lane; t < n_sort; t += 32) keys[t] = 0ull;
         __syncwarp();
-        // bitonic sort, descending, of n_sort keys by one warp
-        for (uint32_t size = 2; size <= n_sort; size <<= 1) {
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t t = lane; t < (n_sort >> 1); t += 32) {
-                    const uint32_t lo = 2 * t - (t & (stride - 1));
-                    const uint32_t hi = lo + stride;
-                    const bool desc = (lo & size) == 0;
-                    const uint64_t a = keys[lo], b = keys[hi];
-                    if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
-                }
-                __syncwarp();
-            }
-        }
+        warp_bitonic_sort_desc(keys, n_sort);
         const float scale = o.row_scale ? o.row_scale[row] : 1.0f;
         for (int t = int(lane); t < o.k; t += 32) {
             const uint64_t key = keys[t];

@@ -6,9 +6,9 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import KIND_BF16, KIND_F32X3, MAX_K, MAX_K_FUSED  # noqa: F401
+from ._lib import KIND_BF16, KIND_F32R, KIND_F32X3, MAX_K, MAX_K_FUSED  # noqa: F401
 
-KINDS = {"f32x3": KIND_F32X3, "bf16": KIND_BF16}
+KINDS = {"f32r": KIND_F32R, "f32x3": KIND_F32X3, "bf16": KIND_BF16}
 
 
 def require_cuda():
@@ -187,6 +187,19 @@ def score_topk(Q, packed, k, idx_offset=0, out=None):
                                              packed.k_dim, packed.kind, int(k), int(idx_offset), _ptr(vals), _ptr(idx),
                                              _ptr(ws), ws.numel(), _stream()))
     return vals, idx
+
+
+def last_redo_rows(n_queries, packed, k):
+    """Rows of the last score_topk(Q[n_queries x k_dim], packed, k) call on this device that the fallback pass had to
+    recompute (anncur_score_topk_redo_rows) -- 0 when the fast path served every row.  Synchronises the stream."""
+    lib = _lib.load()
+    nbytes = lib.anncur_score_topk_workspace_bytes(n_queries, packed.n_items, packed.k_dim, k, packed.kind)
+    ws = WORKSPACE.get("score_topk", nbytes, packed.device)
+    n = C.c_int(0)
+    with torch.cuda.device(packed.device):
+        _lib.check(lib.anncur_score_topk_redo_rows(_ptr(ws), int(n_queries), packed.n_items, packed.k_dim, int(k), packed.kind,
+                                                   C.byref(n), _stream()))
+    return n.value
 
 
 def search_host(Q_host, packed, k, out_vals_host, out_idx_host, idx_offset=0, ws_key="search_host"):

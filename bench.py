@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="f32x3", choices=["f32x3", "bf16"])
+    ap.add_argument("--precision", default="f32r", choices=["f32r", "f32x3", "bf16"])
     ap.add_argument("--shard", default=None, choices=["queries", "items"])
     ap.add_argument("--no-extra", action="store_true", help="skip the bf16 / recall side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -412,8 +412,11 @@ def main():
     n_local = hi - lo
     fused_ms_avg = fused_ms / max(fused_n, 1)
     flops = 2.0 * B * k_i * n_local
+    # bytes of E the MAIN kernel streams per launch: both fp16 planes (f32x3), or one 16-bit plane (bf16; f32r streams
+    # only the high plane -- the fp32 copy is touched for the ~k re-scored candidates of a row, by the refine kernel)
     e_bytes = (4 if args.precision == "f32x3" else 2) * k_i * n_local
     alg_bytes = e_bytes + 4 * B * k_i + 12 * B * k
+    passes = 3 if args.precision == "f32x3" else 1
     tf = flops / (fused_ms_avg * 1e-3) / 1e12 if fused_n else None
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of the MAIN kernel, one `ncu --set full` capture per (workload, kind)
@@ -425,11 +428,12 @@ def main():
         "traffic": NCU_TRAFFIC.get((args.workload, args.precision)) if world == 1 else None, "peak_source": peak_src,
         "launch_ms": fused_ms_avg, "launches_timed": fused_n, "share_of_step": fused_ms / ms_total if ms_total else None,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-        "tensor_passes": 3 if args.precision == "f32x3" else 1,
-        "tensor_pipe_tflops": (tf * (3 if args.precision == "f32x3" else 1)) if tf else None,
-        "tensor_pipe_frac": (tf * (3 if args.precision == "f32x3" else 1) / peak_tf) if tf else None,
-        "note": "achieved/frac count the algorithmic flops 2*B*k_i*N once; the fp32-grade kind issues 3 f16 tensor passes per "
-                "product (h.h + h.l + l.h), so the tensor pipe itself runs at tensor_pipe_tflops (frac of the same measured peak)",
+        "tensor_passes": passes,
+        "tensor_pipe_tflops": (tf * passes) if tf else None,
+        "tensor_pipe_frac": (tf * passes / peak_tf) if tf else None,
+        "note": "achieved/frac count the algorithmic flops 2*B*k_i*N once; kind f32x3 issues 3 f16 tensor passes per product "
+                "(h.h + h.l + l.h), so its tensor pipe runs at tensor_pipe_tflops; kind f32r issues one pass (upper bounds of "
+                "the scores) and re-scores ~k candidates per row in fp32 in a separate kernel (not part of launch_ms)",
         "hbm_gbs_achieved": alg_bytes / (fused_ms_avg * 1e-3) / 1e9 if fused_n else None,
         "hbm_gbs_peak": peaks.get("hbm_gbs"),
     }
@@ -438,34 +442,40 @@ def main():
         "metric": "queries/sec (ANNCUR score+top-100)", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak" if shard == "queries" else "strong", "vs_baseline": None,
-        "dtype": "f32 (2xfp16 split operands, 3 tcgen05 passes, fp32 accumulate)" if args.precision == "f32x3" else "bf16",
+        "dtype": {"f32x3": "f32 (2xfp16 split operands, 3 tcgen05 passes, fp32 accumulate)", "bf16": "bf16",
+                  "f32r": "f32 (one f16 tcgen05 pass of rigorous score upper bounds, fp32 FFMA re-scoring of the candidates)"}[args.precision],
         "data": "synthetic", "config": workload_config(args, world, shard),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "anncur_search_host (C ABI, pinned host buffers)" if index is None else "ShardedIndex.search + pinned copies"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
         "index_build_s": {"pinv": wl["build_s"]["pinv"], "U@R": wl["build_s"]["gemm"], "pack": t_pack},
     }
+    if index is None:
+        # rows of the last device-resident batch that needed the fallback pass (0 = the fast path served the whole batch)
+        engine.score_topk(batches[0], packed, k, idx_offset=lo, out=(out_v, out_i))
+        line["redo_rows_last_batch"] = engine.last_redo_rows(B, packed, k)
 
     # ---- side measurements (rank 0, single GPU): other precision + recall, CPU baseline -----------------
     if world == 1 and not args.no_extra:
-        other = "bf16" if args.precision == "f32x3" else "f32x3"
-        packed_o = engine.PackedItems(wl["E"], other)
-        for j in range(3):
-            engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
-        torch.cuda.synchronize()
-        n_o = max(10, args.steps // 4)
-        ev0.record()
-        for j in range(n_o):
-            engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
-        ev1.record()
-        torch.cuda.synchronize()
-        qps_o = B * n_o / (ev0.elapsed_time(ev1) * 1e-3)
+        line["other_precision"] = []
         v_a, i_a = engine.score_topk(batches[0], packed, k)
-        v_b, i_b = engine.score_topk(batches[0], packed_o, k)
-        inter = (i_a.unsqueeze(2) == i_b.unsqueeze(1)).any(dim=2).float().sum(dim=1) / k
-        line["other_precision"] = {"precision": other, "value": qps_o, "unit": "queries/s",
-                                   "recall_at_k_vs_" + args.precision: float(inter.mean().item())}
-        del packed_o
+        for other in [p for p in ("f32r", "f32x3", "bf16") if p != args.precision]:
+            packed_o = engine.PackedItems(wl["E"], other)
+            for j in range(3):
+                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
+            torch.cuda.synchronize()
+            n_o = max(10, args.steps // 4)
+            ev0.record()
+            for j in range(n_o):
+                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
+            ev1.record()
+            torch.cuda.synchronize()
+            qps_o = B * n_o / (ev0.elapsed_time(ev1) * 1e-3)
+            v_b, i_b = engine.score_topk(batches[0], packed_o, k)
+            inter = (i_a.unsqueeze(2) == i_b.unsqueeze(1)).any(dim=2).float().sum(dim=1) / k
+            line["other_precision"].append({"precision": other, "value": qps_o, "unit": "queries/s",
+                                            "recall_at_k_vs_" + args.precision: float(inter.mean().item())})
+            del packed_o
     if world == 1 and rank == 0 and not args.no_cpu:
         rows = cpu_sample_rows(N, B)
         E_host = wl["E"].cpu()

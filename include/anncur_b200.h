@@ -50,6 +50,11 @@ extern "C" {
 /* precision of the fused score + top-k tensor-core path */
 #define ANNCUR_KIND_F32X3 0  /* fp32-grade: operands split into two fp16 terms, 3 tcgen05 passes */
 #define ANNCUR_KIND_BF16  1  /* single bf16 pass (reported separately as recall@k)             */
+#define ANNCUR_KIND_F32R  2  /* fp32 results at the one-pass rate: ONE f16 tcgen05 pass computes a rigorous upper bound of
+                                every score (per-item error bound folded into the contraction), the ~k items whose bound
+                                reaches the k-th best score are re-scored in plain fp32 (FFMA) from an item-major fp32 copy
+                                of E kept in the packed index (8 instead of 4 bytes per element of E) */
+#define ANNCUR_MAX_K_DIM_F32R 8192  /* largest k_dim of kind F32R                                */
 
 #define ANNCUR_MAX_K        2048  /* largest k of any top-k entry point                         */
 #define ANNCUR_MAX_K_FUSED  1024  /* largest k of the fused tensor-core path                    */
@@ -99,6 +104,13 @@ ANNCUR_API int anncur_score_topk(const float* Q, int ldq, int n_queries, const v
                       const float* e_scale, int64_t n_items, int k_dim, int kind, int k,
                       int64_t idx_offset, float* out_vals, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Introspection: how many query rows of the LAST anncur_score_topk call that used `workspace` (same shape arguments)
+ * were recomputed by the fallback pass (sampled threshold missed; kind F32R: a candidate list filled up or the exactness
+ * certificate failed).  Results are correct either way -- this is the number that tells whether the fast path served
+ * the call.  Blocks until `stream` is idle. */
+ANNCUR_API int anncur_score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind,
+                                int* redo_rows_host, void* stream);
 
 /* Host-buffer form of the same call -- what a CPU-resident caller such as the reference's eval
  * scripts (CPU torch tensors, eval/run_retrieval_eval_wrt_exact_crossenc_w_fixed_train_test_splits.py

@@ -52,6 +52,111 @@ def test_fused_f32x3_matches_oracle(eng, B, K, N, k):
     _check(eng, _rand((B, K), B + K), _rand((K, N), N + k), k)
 
 
+# ---- kind "f32r": one f16 filter pass of upper bounds + exact fp32 re-scoring of the candidates ----------------------
+# Its values are plain fp32 dot products, so the tolerance is 1e-5 (of the row's max |score|) instead of 1e-4.
+@pytest.mark.parametrize("B,K,N,k", [
+    (128, 32, 256, 10),         # no SAMPLE pass at this size: 3-pass streaming on the F32R planes (extra k-block: K % 32 == 0)
+    (1, 50, 10000, 100),
+    (7, 500, 3000, 100),
+    (130, 64, 60000, 64),       # K % 32 == 0 -> the bound slot opens a new k-block; re-score with 1 float4 per lane
+    (300, 200, 50000, 1),       # k = 1; 2 float4 per lane
+    (64, 500, 50000, 100),      # the bench shape; 4 float4 per lane
+    (257, 512, 70000, 100),     # K = 512 -> 17 k-blocks
+    (40, 700, 40000, 50),       # K > 512: query planes not register-cached, re-score through the long path
+    (33, 40, 90000, 129),
+    (20, 128, 60000, 500),
+    (12, 64, 120000, 1000),     # k_r = 1000, the reference's largest retrieval size
+])
+def test_fused_f32r_matches_oracle(eng, B, K, N, k):
+    _check(eng, _rand((B, K), B + K), _rand((K, N), N + k), k, kind="f32r", rel=1e-5)
+
+
+def test_fused_f32r_scale_extremes_and_offsets(eng):
+    for qs, es in [(15.0, 15.0), (1e-6, 1e-3), (3e4, 2e3)]:
+        _check(eng, _rand((40, 100), 3, qs), _rand((100, 40000), 4, es), 50, kind="f32r", rel=1e-5)
+    Q = _rand((64, 100), 5)
+    Q *= torch.logspace(-6, 6, 64).unsqueeze(1)
+    _check(eng, Q, _rand((100, 40000), 6), 50, kind="f32r", rel=1e-5, offset=2**40)
+    # items of wildly different norms: the per-item bound b_n differs by orders of magnitude inside one tile
+    E = _rand((100, 40000), 7) * torch.logspace(-4, 2, 40000).unsqueeze(0)[:, torch.randperm(40000, generator=torch.Generator().manual_seed(0))]
+    _check(eng, _rand((50, 100), 8), E, 100, kind="f32r", rel=1e-5)
+
+
+def test_fused_f32r_fast_path_serves_generic_inputs(eng):
+    """Generic inputs must not lean on the fallback: no row of a random / low-rank batch goes to REDO, while the
+    adversarial batch (all-equal scores) is entirely recomputed there."""
+    K, N, B, k = 500, 100000, 512, 100
+    Q, E = _rand((B, K), 41), _rand((K, N), 42)
+    packed = eng.PackedItems(E.cuda(), "f32r")
+    eng.score_topk(Q.cuda(), packed, k)
+    assert eng.last_redo_rows(B, packed, k) == 0
+    A = torch.from_numpy(O.synthetic_scores(600, 60000, rank=64, noise=0.05, seed=1))
+    rows_i, cols_i = O.sample_anchors(600, 60000, 100, 200, 1)
+    f = O.cur_build(A[rows_i, :], A[:, cols_i], rows_i, cols_i, "rows", check=False)
+    packed = eng.PackedItems(f.latent_cols.cuda(), "f32r")
+    eng.score_topk(A[:, cols_i].contiguous().cuda(), packed, k)
+    assert eng.last_redo_rows(600, packed, k) == 0
+    packed = eng.PackedItems(torch.ones(32, 60000).cuda(), "f32r")
+    eng.score_topk(torch.ones(130, 32).cuda(), packed, 10)
+    assert eng.last_redo_rows(130, packed, 10) == 130
+
+
+def test_fused_f32r_exact_on_integer_data_with_ties(eng):
+    """Small-integer operands: every fp32 dot product is exact, so the answer must equal the exact top-k with ties
+    broken towards the lower index -- bit for bit, values and indices."""
+    rng = np.random.default_rng(3)
+    B, K, N, k = 200, 96, 70000, 100
+    Q = torch.from_numpy(rng.integers(-3, 4, (B, K)).astype(np.float32))
+    E = torch.from_numpy(rng.integers(-3, 4, (K, N)).astype(np.float32))
+    v, i = eng.score_topk(Q.cuda(), eng.PackedItems(E.cuda(), "f32r"), k)
+    S = (Q.double() @ E.double()).numpy()
+    order = np.lexsort((np.broadcast_to(np.arange(N), S.shape), -S), axis=1)[:, :k]
+    assert (i.cpu().numpy() == order).all()
+    assert (v.cpu().numpy() == np.take_along_axis(S, order, 1).astype(np.float32)).all()
+
+
+def test_fused_f32r_adversarial_inputs_fall_back(eng):
+    """Inputs built to defeat the filter: ascending scores and all-equal scores (every item passes the threshold ->
+    lists fill up -> REDO), a planted sample miss (rows end short -> REDO), and thousands of exact ties at the top."""
+    K, N = 32, 60000
+    E = torch.zeros(K, N)
+    E[0] = torch.arange(N, dtype=torch.float32) / N
+    Q = torch.zeros(70, K)
+    Q[:, 0] = torch.linspace(0.5, 2.0, 70)
+    v, i = _check(eng, Q, E, 100, kind="f32r", rel=1e-5)
+    assert (i == np.arange(N - 1, N - 101, -1)[None, :]).all()
+    packed = eng.PackedItems(torch.ones(K, N).cuda(), "f32r")
+    v, i = eng.score_topk(torch.ones(3, K).cuda(), packed, 10)
+    assert (i.cpu().numpy() == np.arange(10)[None, :]).all() and np.allclose(v.cpu().numpy(), K)
+    E = _rand((K, N), 7)
+    E[0, ::16] += 50.0
+    Q = _rand((300, K), 8)
+    Q[:, 0] = 0.0
+    Q[[5, 131, 299], 0] = 1.0
+    _check(eng, Q, E, 100, kind="f32r", rel=1e-5)
+    Q, E = _rand((150, 64), 11), _rand((64, 80000), 12)
+    E[:, 1000:9000] = E[:, 999:1000]
+    _check(eng, Q, E, 100, kind="f32r", rel=1e-5)
+
+
+def test_fused_f32r_search_host_and_c2_sample(eng):
+    """Host-buffer entry point == device entry point for kind f32r; C2-sized call checked on a row sample."""
+    K, N, B, k = 500, 100000, 4096, 100
+    Q, E = _rand((B, K), 21), _rand((K, N), 22)
+    packed = eng.PackedItems(E.cuda(), "f32r")
+    v, i = eng.score_topk(Q.cuda(), packed, k)
+    rows = np.random.default_rng(0).choice(B, 96, replace=False)
+    dense = (Q[rows].double() @ E.double()).numpy()
+    ref = torch.topk(torch.from_numpy(dense), k, dim=1)
+    assert_topk_sets_match(i[rows].cpu().numpy(), ref.indices.numpy(), full_scores=dense, rel=1e-5)
+    assert_scores_close(v[rows].cpu().numpy(), ref.values.numpy(), rel=1e-5)
+    vh = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    ih = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    eng.search_host(Q.pin_memory(), packed, k, vh, ih)
+    torch.cuda.synchronize()
+    assert torch.equal(ih, i.cpu()) and torch.equal(vh, v.cpu())
+
+
 def test_fused_k_larger_than_items_pads(eng):
     _check(eng, _rand((5, 16), 1), _rand((16, 40), 2), 64)
 
@@ -200,11 +305,12 @@ from anncur_b200 import engine as eng
 from oracle import cur_oracle as O
 from tests.parity import assert_scores_close, assert_topk_sets_match
 rng = np.random.default_rng(5)
-for (B, K, N, k, kind) in [(700, 96, 90000, 100, "f32x3"), (129, 500, 3000, 10, "f32x3"), (513, 64, 70000, 40, "bf16")]:
+for (B, K, N, k, kind) in [(700, 96, 90000, 100, "f32x3"), (129, 500, 3000, 10, "f32x3"), (513, 64, 70000, 40, "bf16"),
+                           (700, 96, 90000, 100, "f32r"), (100, 500, 60000, 10, "f32r")]:
     Q = torch.from_numpy(rng.standard_normal((B, K), dtype=np.float32)); E = torch.from_numpy(rng.standard_normal((K, N), dtype=np.float32))
     v, i = eng.score_topk(Q.cuda(), eng.PackedItems(E.cuda(), kind), k)
     dense = (Q.double() @ E.double()).numpy(); ref = O.score_topk(Q, E, k)
-    if kind == "f32x3":
+    if kind != "bf16":
         assert_topk_sets_match(i.cpu().numpy(), ref.indices.numpy(), full_scores=dense)
         assert_scores_close(v.cpu().numpy(), np.take_along_axis(dense, i.cpu().numpy(), 1))
     else:
