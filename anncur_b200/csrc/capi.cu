@@ -140,7 +140,9 @@ int anncur_search_host(const float* Q_host, int ldq, int n_queries, const void* 
     float* v_dev = reinterpret_cast<float*>(ws);                      ws += host_stage_v_bytes(n_queries, k);
     int64_t* i_dev = reinterpret_cast<int64_t*>(ws);                  ws += host_stage_i_bytes(n_queries, k);
     const size_t inner = workspace_bytes - size_t(ws - reinterpret_cast<char*>(workspace));
-    if (k_dim > 0)
+    if (k_dim > 0 && ldq == k_dim)
+        ANNCUR_CUDA_OK(cudaMemcpyAsync(q_dev, Q_host, sizeof(float) * size_t(k_dim) * size_t(n_queries), cudaMemcpyHostToDevice, s));
+    else if (k_dim > 0)
         ANNCUR_CUDA_OK(cudaMemcpy2DAsync(q_dev, sizeof(float) * size_t(k_dim), Q_host, sizeof(float) * size_t(ldq),
                                          sizeof(float) * size_t(k_dim), size_t(n_queries), cudaMemcpyHostToDevice, s));
     int rc = anncur_score_topk(q_dev, k_dim, n_queries, packed_items, e_scale, n_items, k_dim, kind, k, idx_offset, v_dev,

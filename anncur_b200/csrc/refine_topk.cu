@@ -20,7 +20,6 @@
 namespace anncur {
 
 constexpr int kRefCap = 1024;          // candidates of one row held in shared memory
-constexpr int kRefWarps = 4;
 constexpr int kRefMaxLists = 1024;
 constexpr int kRefBatch = 4;           // candidates re-scored together (their loads are all in flight at once)
 
@@ -41,11 +40,17 @@ struct RefineParams {
     int m_tiles;
 };
 
-// dot(q, ET[item]) for kRefBatch items at once; q is held in registers as U float4 per lane (k_dim <= 128 U)
+// dot(q, ET[item]) for kRefBatch = 4 items at once; q is held in registers as U float4 per lane (k_dim <= 128 U).
+// All 4 x U loads of a lane are issued before the first use.  Returns, in every lane, the score of item[lane >> 3]
+// (the four partial sums are reduced together: 6 shuffles instead of 20).
 template <int U>
-__device__ __forceinline__ void rescore_batch(const float4 (&qv)[U], const float* __restrict__ ET, int ld, int ld4,
-                                              const uint32_t (&item)[kRefBatch], float (&s)[kRefBatch]) {
+__device__ __forceinline__ float rescore_batch(const float4 (&qv)[U], const float* __restrict__ ET, int ld, int ld4,
+                                               const uint32_t (&item)[kRefBatch]) {
+    static_assert(kRefBatch == 4, "the reduction below is written for 4 candidates");
     const int lane = int(lane_id());
+    // The loads are volatile asm and are followed by one (empty) volatile asm per loaded vector, so that neither
+    // compiler stage can sink a load down to its first use: all 4 x U requests are in flight before the first FMA
+    // (without this the compiler interleaved load / use and every load paid its full latency: 134 -> 313 us at C2).
     float4 e[kRefBatch][U];
 #pragma unroll
     for (int c = 0; c < kRefBatch; ++c) {
@@ -53,9 +58,19 @@ __device__ __forceinline__ void rescore_batch(const float4 (&qv)[U], const float
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int j = lane + 32 * u;
-            e[c][u] = j < ld4 ? __ldg(rowp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* ptr = rowp + (j < ld4 ? j : 0);                  // out-of-range lanes re-read element 0; their q is 0
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(e[c][u].x), "=f"(e[c][u].y), "=f"(e[c][u].z), "=f"(e[c][u].w) : "l"(ptr));
         }
     }
+#pragma unroll
+    for (int c = 0; c < kRefBatch; ++c) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            asm volatile("" : "+f"(e[c][u].x), "+f"(e[c][u].y), "+f"(e[c][u].z), "+f"(e[c][u].w));
+        }
+    }
+    float s[kRefBatch];
 #pragma unroll
     for (int c = 0; c < kRefBatch; ++c) {
         float acc = 0.f;
@@ -66,8 +81,16 @@ __device__ __forceinline__ void rescore_batch(const float4 (&qv)[U], const float
             acc = fmaf(qv[u].z, e[c][u].z, acc);
             acc = fmaf(qv[u].w, e[c][u].w, acc);
         }
-        s[c] = warp_sum(acc);
+        s[c] = acc;
     }
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+    float a = (hi16 ? s[2] : s[0]) + __shfl_xor_sync(0xffffffffu, hi16 ? s[0] : s[2], 16);
+    float b = (hi16 ? s[3] : s[1]) + __shfl_xor_sync(0xffffffffu, hi16 ? s[1] : s[3], 16);
+    float v = (hi8 ? b : a) + __shfl_xor_sync(0xffffffffu, hi8 ? a : b, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
 // any k_dim: q re-read from global (L1) per 128-float chunk
@@ -87,56 +110,64 @@ __device__ __forceinline__ float rescore_long(const float* __restrict__ q, int k
     return warp_sum(acc);
 }
 
-template <int U>
-__global__ void __launch_bounds__(kRefWarps * 32)
+// One CTA of W warps per row.  W = 1 for large batches (every row is one warp's private chain, ~16 rows in flight per
+// SM); W = 4 for small batches, where the kernel time IS the per-row latency: the gather and the two re-scoring phases are
+// split over the warps (the selects stay on warp 0).
+// Register budget 128: with less, ptxas sinks the 16 loads of a re-scoring batch down to their uses.
+template <int W> __device__ __forceinline__ void cta_sync() { if (W > 1) __syncthreads(); else __syncwarp(); }
+
+template <int U, int W>
+__global__ void __launch_bounds__(W * 32, W == 1 ? 16 : 4)
 refine_topk_kernel(const RefineParams p) {
     extern __shared__ __align__(16) uint64_t ref_smem[];
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    uint64_t* keys = ref_smem + size_t(warp) * kRefCap;
-    uint32_t* words = reinterpret_cast<uint32_t*>(ref_smem + size_t(kRefWarps) * kRefCap);
-    uint32_t* hist = words + warp * 256;
-    uint16_t* work = reinterpret_cast<uint16_t*>(words + kRefWarps * 256) + warp * kRefCap;       // positions to re-score
-    uint32_t* offs = words + kRefWarps * 256 + kRefWarps * (kRefCap / 2) + warp * (p.n_lists + 1);
+    uint64_t* keys = ref_smem;                                            // [kRefCap]
+    uint64_t* sh64 = ref_smem + kRefCap;                                  // [2]: prefix, mask of the phase-A select
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sh64 + 2);               // [256]
+    float* sh_min = reinterpret_cast<float*>(hist + 256);                 // [W]
+    uint32_t* sh_total = reinterpret_cast<uint32_t*>(sh_min + W);         // [2]: total, marked
+    uint32_t* offs = sh_total + 2;                                        // [n_lists + 1]
     const uint32_t k = uint32_t(p.k);
     const int ld4 = p.ld >> 2;
     const uint32_t lowest = float_to_ordered(-INFINITY);
 
-    for (int row = blockIdx.x * kRefWarps + warp; row < p.n_rows; row += gridDim.x * kRefWarps) {
-        // ---- list lengths -> offsets; a marked list gives the row up ------------------------------------
-        bool marked = false;
-        for (int l = int(lane); l < p.n_lists; l += 32) {
-            const uint32_t c = __ldcg(p.counts + int64_t(row) * p.n_lists + l);
-            marked |= (c & 0x80000000u) != 0u;
-            offs[l + 1] = min(c & 0x7fffffffu, uint32_t(p.cap));
-        }
-        marked = __any_sync(0xffffffffu, marked);
-        __syncwarp();
-        uint32_t carry = 0;
-        for (int base = 0; base < p.n_lists; base += 32) {
-            const int l = base + int(lane);
-            const uint32_t v = l < p.n_lists ? offs[l + 1] : 0u;
-            uint32_t incl = v;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= uint32_t(off)) incl += t;
+    for (int row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        // ---- list lengths -> offsets; a marked list gives the row up (warp 0) ----------------------------
+        if (warp == 0) {
+            bool marked = false;
+            for (int l = int(lane); l < p.n_lists; l += 32) {
+                const uint32_t c = __ldcg(p.counts + int64_t(row) * p.n_lists + l);
+                marked |= (c & 0x80000000u) != 0u;
+                offs[l + 1] = min(c & 0x7fffffffu, uint32_t(p.cap));
             }
-            if (l < p.n_lists) offs[l + 1] = carry + incl;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            marked = __any_sync(0xffffffffu, marked);
+            __syncwarp();
+            uint32_t carry = 0;
+            for (int base = 0; base < p.n_lists; base += 32) {
+                const int l = base + int(lane);
+                const uint32_t v = l < p.n_lists ? offs[l + 1] : 0u;
+                uint32_t incl = v;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= uint32_t(off)) incl += t;
+                }
+                if (l < p.n_lists) offs[l + 1] = carry + incl;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) { offs[0] = 0; sh_total[0] = carry; sh_total[1] = marked ? 1u : 0u; }
         }
-        if (lane == 0) offs[0] = 0;
-        const uint32_t total = carry;
-        __syncwarp();
+        cta_sync<W>();
+        const uint32_t total = sh_total[0];
         const int64_t need = p.n_items < int64_t(k) ? p.n_items : int64_t(k);
-        bool redo = marked || int64_t(total) < need || total > uint32_t(kRefCap);
-        const float inv_scale = p.row_inv_scale[row];
-        const float to_scaled = 1.0f / inv_scale;                          // power of two: exact
+        bool redo = sh_total[1] != 0u || int64_t(total) < need || total > uint32_t(kRefCap);
+        const float to_scaled = 1.0f / p.row_inv_scale[row];               // power of two: exact
         const uint32_t thr_ord = __ldcg(p.thr_shared + row);
 
         if (!redo) {
             // ---- gather (flat element -> (list, position) by binary search in the offsets) ---------------
-            for (uint32_t e0 = 0; e0 < total; e0 += 128) {
+            for (uint32_t e0 = uint32_t(warp) * 128u; e0 < total; e0 += 128u * W) {
                 uint64_t reg[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -157,8 +188,7 @@ refine_topk_kernel(const RefineParams p) {
                     if (e < total) keys[e] = reg[u];
                 }
             }
-            __syncwarp();
-            // ---- the query row, in registers -------------------------------------------------------------
+            // ---- the query row, in registers (zero beyond k_dim: those lanes re-read element 0 of the item) ---
             const float* q = p.Q + int64_t(row) * p.ldq;
             float4 qv[U > 0 ? U : 1];
             if (U > 0) {
@@ -171,91 +201,109 @@ refine_topk_kernel(const RefineParams p) {
                     qv[u].w = i + 3 < p.k_dim ? __ldg(q + i + 3) : 0.f;
                 }
             }
-            // re-score the candidates at positions work[0 .. n_work): keys[pos] becomes (S, item); returns min S
-            auto rescore = [&](uint32_t n_work) {
-                float s_min = INFINITY;
-                for (uint32_t i0 = 0; i0 < n_work; i0 += kRefBatch) {
+            cta_sync<W>();
+            // re-score the candidates of keys[t0 .. t0 + 32) named by `ballot` (same value in all lanes), four at a time:
+            // keys[pos] becomes (S, item); s_min collects this lane's share of the minimum
+            float s_min = INFINITY;
+            auto rescore = [&](uint32_t t0, uint32_t ballot) {
+                while (ballot) {
                     uint32_t pos[kRefBatch], item[kRefBatch];
-                    float s[kRefBatch];
+                    int n = 0;
 #pragma unroll
                     for (int c = 0; c < kRefBatch; ++c) {
-                        pos[c] = work[min(i0 + uint32_t(c), n_work - 1u)];
+                        if (ballot) { pos[c] = t0 + uint32_t(__ffs(int(ballot)) - 1); ballot &= ballot - 1u; n = c + 1; }
+                        else pos[c] = pos[0];
                         item[c] = key_index(keys[pos[c]]);
                     }
+                    const int c_own = int(lane >> 3);
+                    float s_own;
                     if (U > 0) {
-                        rescore_batch<(U > 0 ? U : 1)>(qv, p.ET, p.ld, ld4, item, s);
+                        s_own = rescore_batch<(U > 0 ? U : 1)>(qv, p.ET, p.ld, ld4, item);
                     } else {
+                        float s4[kRefBatch];
 #pragma unroll
-                        for (int c = 0; c < kRefBatch; ++c) s[c] = rescore_long(q, p.k_dim, p.ET, p.ld, ld4, item[c]);
+                        for (int c = 0; c < kRefBatch; ++c) s4[c] = rescore_long(q, p.k_dim, p.ET, p.ld, ld4, item[c]);
+                        s_own = c_own == 0 ? s4[0] : c_own == 1 ? s4[1] : c_own == 2 ? s4[2] : s4[3];
                     }
+                    const uint32_t pos_own = c_own == 0 ? pos[0] : c_own == 1 ? pos[1] : c_own == 2 ? pos[2] : pos[3];
+                    const uint32_t item_own = c_own == 0 ? item[0] : c_own == 1 ? item[1] : c_own == 2 ? item[2] : item[3];
                     __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < kRefBatch; ++c) {
-                        if (i0 + uint32_t(c) < n_work) {
-                            s_min = fminf(s_min, s[c]);
-                            if (lane == 0) keys[pos[c]] = make_key(s[c], item[c]);
-                        }
+                    if (c_own < n) {
+                        s_min = fminf(s_min, s_own);
+                        if ((lane & 7u) == 0u) keys[pos_own] = make_key(s_own, item_own);
                     }
                     __syncwarp();
                 }
-                return s_min;
             };
             // ---- phase A: the k candidates with the largest upper bound ------------------------------------
-            uint64_t prefix = 0ull, mask = 0ull;
-            if (total > k) warp_radix_kth(keys, total, k, hist, prefix, mask);
-            uint32_t n_work = 0;
-            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                const bool win = t < total && (keys[t] & mask) >= prefix;
-                const uint32_t ballot = __ballot_sync(0xffffffffu, win);
-                if (win) work[n_work + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
-                hist[t0 >> 5] = ballot;                                    // who has been re-scored (hist is free here)
-                n_work += __popc(ballot);
+            if (warp == 0) {
+                uint64_t prefix = 0ull, mask = 0ull;
+                if (total > k) warp_radix_kth(keys, total, k, hist, prefix, mask);
+                if (lane == 0) { sh64[0] = prefix; sh64[1] = mask; }
             }
-            __syncwarp();
-            const float s_min = rescore(n_work);
+            cta_sync<W>();
+            {
+                // (an L2 prefetch of the next chunk's winners was tried here: no gain -- the row's time goes to issue latency
+                // of the many small steps at 16 warps per SM, not to waiting for DRAM)
+                const uint64_t prefix = sh64[0], mask = sh64[1];
+                for (uint32_t t0 = uint32_t(warp) * 32u; t0 < total; t0 += 32u * W) {
+                    const uint32_t t = t0 + lane;
+                    const bool win = t < total && (keys[t] & mask) >= prefix;
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, win);
+                    if (lane == 0) hist[t0 >> 5] = ballot;                 // who has been re-scored (hist is free here)
+                    rescore(t0, ballot);
+                }
+            }
+            s_min = -warp_max_f(-s_min);
+            if (W > 1) {
+                if (lane == 0) sh_min[warp] = s_min;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < W; ++w) s_min = fminf(s_min, sh_min[w]);
+            }
             // ---- phase B: every other candidate whose upper bound reaches s_min; the rest is dropped --------
             if (total > k) {
                 const float s_min_scaled = s_min * to_scaled;
-                uint32_t n_more = 0;
-                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                __syncwarp();
+                for (uint32_t t0 = uint32_t(warp) * 32u; t0 < total; t0 += 32u * W) {
                     const uint32_t t = t0 + lane;
                     const bool done = (hist[t0 >> 5] >> lane) & 1u;
                     const bool open = t < total && !done;
                     const bool more = open && key_score(keys[t]) >= s_min_scaled;
-                    const uint32_t ballot = __ballot_sync(0xffffffffu, more);
-                    if (more) work[n_more + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
                     if (open && !more) keys[t] = 0ull;
-                    n_more += __popc(ballot);
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, more);
+                    __syncwarp();
+                    rescore(t0, ballot);
                 }
+            }
+            cta_sync<W>();
+            // ---- top-k of the re-scored candidates (warp 0) --------------------------------------------------
+            if (warp == 0) {
+                uint64_t prefix, mask;
+                uint32_t n_live = warp_compact_ge(keys, total, 0ull, 0ull);   // drops the zeroed entries
+                if (n_live > k) {
+                    warp_radix_kth(keys, n_live, k, hist, prefix, mask);
+                    n_live = warp_compact_ge(keys, n_live, prefix, mask);
+                }
+                for (uint32_t t = n_live + lane; t < uint32_t(p.n_sort); t += 32) keys[t] = 0ull;
                 __syncwarp();
-                if (n_more > 0) rescore(n_more);
-            }
-            // ---- top-k of the re-scored candidates ----------------------------------------------------------
-            uint32_t n_live = warp_compact_ge(keys, total, 0ull, 0ull);   // drops the zeroed entries
-            if (n_live > k) {
-                warp_radix_kth(keys, n_live, k, hist, prefix, mask);
-                n_live = warp_compact_ge(keys, n_live, prefix, mask);
-            }
-            for (uint32_t t = n_live + lane; t < uint32_t(p.n_sort); t += 32) keys[t] = 0ull;
-            __syncwarp();
-            warp_bitonic_sort_desc(keys, uint32_t(p.n_sort));
-            // ---- certificate: items that were never pushed have S <= UB <= T (all in scaled units) ---------
-            if (int64_t(total) < p.n_items && thr_ord > lowest) {
-                const float kth_scaled = key_score(keys[need - 1]) * to_scaled;
-                if (!(kth_scaled > ordered_to_float(thr_ord))) redo = true;
-            }
-            if (!redo) {
-                for (uint32_t t = lane; t < k; t += 32) {
-                    const uint64_t key = keys[t];
-                    const bool ok = key != 0ull;
-                    p.out_vals[int64_t(row) * k + t] = ok ? key_score(key) : ANNCUR_PAD_VAL;
-                    p.out_idx[int64_t(row) * k + t] = ok ? int64_t(key_index(key)) + p.idx_offset : int64_t(-1);
+                warp_bitonic_sort_desc(keys, uint32_t(p.n_sort));
+                // ---- certificate: items that were never pushed have S <= UB <= T (all in scaled units) ---------
+                if (int64_t(total) < p.n_items && thr_ord > lowest) {
+                    const float kth_scaled = key_score(keys[need - 1]) * to_scaled;
+                    if (!(kth_scaled > ordered_to_float(thr_ord))) redo = true;
+                }
+                if (!redo) {
+                    for (uint32_t t = lane; t < k; t += 32) {
+                        const uint64_t key = keys[t];
+                        const bool ok = key != 0ull;
+                        p.out_vals[int64_t(row) * k + t] = ok ? key_score(key) : ANNCUR_PAD_VAL;
+                        p.out_idx[int64_t(row) * k + t] = ok ? int64_t(key_index(key)) + p.idx_offset : int64_t(-1);
+                    }
                 }
             }
-            __syncwarp();
         }
-        if (lane == 0) {
+        if (warp == 0 && lane == 0) {
             p.thr_shared[row] = float_to_ordered(redo ? -INFINITY : INFINITY);
             if (redo) {
                 atomicOr(p.mtile_flags + row / 128, 1u);
@@ -263,7 +311,7 @@ refine_topk_kernel(const RefineParams p) {
                 n_flagged[1 + atomicAdd(n_flagged, 1u)] = uint32_t(row);
             }
         }
-        __syncwarp();
+        cta_sync<W>();
     }
 }
 
@@ -278,21 +326,27 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
     while (n_sort < k) n_sort <<= 1;
     RefineParams p{cand, counts, n_lists, cap, n_rows, k, n_sort, n_items, idx_offset, Q, ldq, k_dim, ET, ld,
                    row_inv_scale, out_vals, out_idx, thr_shared, mtile_flags, m_tiles};
-    const size_t smem = size_t(kRefWarps) * (kRefCap * sizeof(uint64_t) + 256 * sizeof(uint32_t) + kRefCap * sizeof(uint16_t) +
-                                             (size_t(n_lists) + 1) * sizeof(uint32_t));
-    int grid = (n_rows + kRefWarps - 1) / kRefWarps;
-    if (grid > 8 * sm_count()) grid = 8 * sm_count();
+    const bool wide = n_rows <= 4 * sm_count();               // few rows: 4 warps per row
+    const int W = wide ? 4 : 1;
+    const size_t smem = (kRefCap + 2) * sizeof(uint64_t) + (256 + size_t(W) + 2 + size_t(n_lists) + 1) * sizeof(uint32_t);
+    const int grid = n_rows < 32 * sm_count() ? n_rows : 32 * sm_count();
     const int ld4 = ld >> 2;
     auto launch = [&](auto kernel) {
         ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kernel<<<grid, kRefWarps * 32, smem, stream>>>(p);
+        kernel<<<grid, W * 32, smem, stream>>>(p);
         ANNCUR_LAUNCH_OK("refine_topk_kernel");
         return ANNCUR_OK;
     };
-    if (ld4 <= 32) return launch(refine_topk_kernel<1>);
-    if (ld4 <= 64) return launch(refine_topk_kernel<2>);
-    if (ld4 <= 128) return launch(refine_topk_kernel<4>);
-    return launch(refine_topk_kernel<0>);
+    if (wide) {
+        if (ld4 <= 32) return launch(refine_topk_kernel<1, 4>);
+        if (ld4 <= 64) return launch(refine_topk_kernel<2, 4>);
+        if (ld4 <= 128) return launch(refine_topk_kernel<4, 4>);
+        return launch(refine_topk_kernel<0, 4>);
+    }
+    if (ld4 <= 32) return launch(refine_topk_kernel<1, 1>);
+    if (ld4 <= 64) return launch(refine_topk_kernel<2, 1>);
+    if (ld4 <= 128) return launch(refine_topk_kernel<4, 1>);
+    return launch(refine_topk_kernel<0, 1>);
 }
 
 }  // namespace anncur

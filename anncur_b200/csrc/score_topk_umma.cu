@@ -322,6 +322,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
 
+    // REDO launch without a flagged row (the normal case): nothing to do, leave before any TMEM / barrier set-up
+    if (p.mtile_flags != nullptr && __ldg(p.mtile_flags + p.m_tiles) == 0u) return;
+
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
@@ -938,6 +941,57 @@ sample_threshold_kernel(const float* __restrict__ smax, int n_smax, int n_querie
     }
 }
 
+// Same result, one WARP per row with the row's group maxima in registers (n_smax <= 32 VPL): the j-th largest key is
+// found bit by bit (largest v with #{keys >= v} >= j; 32 rounds of VPL compares + one warp sum) -- no shared memory,
+// no block barriers.  Large batches: 23 -> ~5 us at C2 (4096 rows x 200 maxima).
+template <int VPL>
+__global__ void __launch_bounds__(128)
+sample_threshold_warp_kernel(const float* __restrict__ smax, int n_smax, int n_queries, int j, const float* __restrict__ row_delta,
+                             uint32_t* __restrict__ thr_shared) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= n_queries) return;
+    const int lane = int(lane_id());
+    const float* v = smax + int64_t(row) * n_smax;
+    uint32_t key[VPL];
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+        const int t = u * 32 + lane;
+        key[u] = t < n_smax ? float_to_ordered(__ldcg(v + t)) : 0u;
+    }
+    uint32_t result = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = result | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) cnt += key[u] >= trial ? 1 : 0;
+        cnt = warp_sum(cnt);
+        if (cnt >= j) result = trial;
+    }
+    if (lane == 0) {
+        const uint32_t lowest = float_to_ordered(-INFINITY);
+        uint32_t bound = lowest;
+        if (n_smax >= j && result > lowest) {
+            const float t = ordered_to_float(result) - row_delta[row];      // see pack_queries_kernel
+            bound = float_to_ordered(t);
+            bound = bound > lowest ? bound - 1u : lowest;
+        }
+        thr_shared[row] = bound;
+    }
+}
+
+static int launch_sample_threshold(const float* smax, int n_smax, int n_queries, int j, const float* row_delta, uint32_t* thr,
+                                   cudaStream_t stream) {
+    const int wgrid = (n_queries + 3) / 4;
+    if (n_smax <= 256) sample_threshold_warp_kernel<8><<<wgrid, 128, 0, stream>>>(smax, n_smax, n_queries, j, row_delta, thr);
+    else if (n_smax <= 512) sample_threshold_warp_kernel<16><<<wgrid, 128, 0, stream>>>(smax, n_smax, n_queries, j, row_delta, thr);
+    else if (n_smax <= 1024) sample_threshold_warp_kernel<32><<<wgrid, 128, 0, stream>>>(smax, n_smax, n_queries, j, row_delta, thr);
+    else if (n_smax <= 2048 && n_queries >= 256) sample_threshold_warp_kernel<64><<<wgrid, 128, 0, stream>>>(smax, n_smax, n_queries, j, row_delta, thr);
+    else sample_threshold_kernel<<<n_queries, THR_THREADS, 0, stream>>>(smax, n_smax, n_queries, j, row_delta, thr);
+    ANNCUR_LAUNCH_OK("sample_threshold_kernel");
+    return ANNCUR_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1353,8 +1407,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         else rc = bf16 ? launch_fused<1, true, 8, 1>(a0, a0, s0, s0, sp, false, stream)
                        : launch_fused<1, false, 8, 1>(a0, a0, s0, s0, sp, false, stream);
         if (rc != ANNCUR_OK) return rc;
-        sample_threshold_kernel<<<n_queries, THR_THREADS, 0, stream>>>(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr);
-        ANNCUR_LAUNCH_OK("sample_threshold_kernel");
+        if ((rc = launch_sample_threshold(smax, pl.n_smax, n_queries, pl.sample_rank, delta, thr, stream)) != ANNCUR_OK) return rc;
     }
     // MAIN
     fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;

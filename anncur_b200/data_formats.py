@@ -110,7 +110,7 @@ def retrieval_grids(n_ent, method="cur"):
 
 
 def run_cur_method(test_data_file, train_data_file, seed, *, n_ent_anchors_vals=None, top_k_retr_vals=None,
-                   precision="f32x3"):
+                   precision="f32r"):
     """``run_eval_method(curr_method="cur", ...)`` (:209-443) on the GPU: load the two split pickles, replay the
     anchor draws, build one index per k_i, retrieve once at the largest k_r and evaluate every (k, k_r).
     Returns (eval_res, retrieval_params) in the reference's layout.  The optional grids restrict the sweep (the

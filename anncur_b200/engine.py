@@ -148,7 +148,7 @@ def gemm(A, B):
 class PackedItems:
     """E = latent_cols (k_dim x N) in the TMA/tcgen05 streaming layout of one precision kind."""
 
-    def __init__(self, E, kind="f32x3"):
+    def __init__(self, E, kind="f32r"):
         lib = _lib.load()
         E = _f32(E)
         assert E.dim() == 2

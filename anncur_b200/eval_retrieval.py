@@ -95,7 +95,7 @@ def eval_approx_score_mat(all_ment_to_ent_scores, approx_ment_to_ent_scores, top
 
 
 def run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors, n_ent_anchors, top_k, top_k_retvr,
-                           seed, precomp_approx_ment_to_ent_scores=None, *, precision="f32x3"):
+                           seed, precomp_approx_ment_to_ent_scores=None, *, precision="f32r"):
     engine.require_cuda()
     A = engine._f32(all_ment_to_ent_scores)
     n_ments, n_ents = A.shape
@@ -146,7 +146,7 @@ def run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors
 
 
 def fixed_split_cur_eval(train_scores, test_scores, n_ent_anchors_vals, top_k_vals, top_k_retvr_vals, seed,
-                         *, precision="f32x3", only_k_i=None):
+                         *, precision="f32r", only_k_i=None):
     """The ``cur`` method of run_eval_method (..._w_fixed_train_test_splits.py:286-303 + :403-429) end to end on
     the GPU: ONE numpy Generator replayed across the k_i grid, every training row an anchor query, and for each
     (k_r, k_i) the all-top-k evaluation.  Returns {f"top_k={k}": {f"k_retvr={k_r}": {f"anc_n_m={n_train}_anc_n_e={k_i}": metrics}}}

@@ -28,7 +28,7 @@ def _as_index_tensor(idx, device):
 class CURApprox(object):
     """M (n x m) ~= C . U . R with C (n x k_c) anchor-item columns, R (k_r x m) anchor-query rows."""
 
-    def __init__(self, rows, cols, row_idxs, col_idxs, approx_preference, A=None, *, precision="f32x3",
+    def __init__(self, rows, cols, row_idxs, col_idxs, approx_preference, A=None, *, precision="f32r",
                  check=False, rcond=1e-15, device=None):
         engine.require_cuda()
         rows = torch.as_tensor(rows)

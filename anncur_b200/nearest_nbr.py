@@ -20,7 +20,7 @@ LOGGER = logging.getLogger(__name__)
 class FlatIPIndex:
     """Exact maximum-inner-product index over N d-dimensional embeddings (faiss.IndexFlatIP surface)."""
 
-    def __init__(self, d, precision="f32x3", device=None):
+    def __init__(self, d, precision="f32r", device=None):
         engine.require_cuda()
         self.d = int(d)
         self.precision = precision
@@ -54,7 +54,7 @@ class FlatIPIndex:
         return D.cpu().numpy(), I.cpu().numpy()
 
 
-def build_flat_or_ivff_index(embeds, force_exact_search, probe_mult_factor=1, precision="f32x3", device=None):
+def build_flat_or_ivff_index(embeds, force_exact_search, probe_mult_factor=1, precision="f32r", device=None):
     LOGGER.info(f"Beginning indexing given {len(embeds)} embeddings")
     if type(embeds) is not np.ndarray:
         if torch.is_tensor(embeds):

@@ -35,7 +35,7 @@ def build_parser():
     p.add_argument("--mode", type=str, choices=["eval", "plot", "eval_n_plot"], default="eval")
     p.add_argument("--misc", type=str, default="", help="Misc suffix")
     p.add_argument("--use_wandb", type=int, default=0, choices=[0, 1])
-    p.add_argument("--precision", type=str, default="f32x3", choices=["f32x3", "bf16", "f32"])
+    p.add_argument("--precision", type=str, default="f32r", choices=["f32r", "f32x3", "bf16", "f32"])
     p.add_argument("--k_i", type=int, nargs="*", default=None, help="restrict the anchor-item grid to these values")
     p.add_argument("--k_r", type=int, nargs="*", default=None, help="restrict the retrieved-k grid to these values")
     return p

@@ -37,7 +37,7 @@ def unpack_candidates(buf, k):
 class ShardedIndex:
     """This rank's slice of the item-embedding matrix plus the collective search."""
 
-    def __init__(self, E_local, lo, n_items_total, *, precision="f32x3", group=None, local_search=None, merge=None,
+    def __init__(self, E_local, lo, n_items_total, *, precision="f32r", group=None, local_search=None, merge=None,
                  packed=None):
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1

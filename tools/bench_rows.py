@@ -94,7 +94,7 @@ s_cpu = cpu_s(lambda: Qh[:1024] @ Eh) * (B / 1024)
 emit("A3", f"scores = Q[{B}x{K_I}] @ E[{K_I}x{N}] dense (get_complete_row)", t, s_cpu, "1024 of 4096 rows, torch.matmul",
      flops=fl, tflops=round(fl / t / 1e9, 1), bound="fp32 FFMA pipe; writes the 1.6 GB score matrix")
 # A4 fused
-for kind in ("f32x3", "bf16"):
+for kind in ("f32r", "f32x3", "bf16"):
     packed = engine.PackedItems(E, kind)
     ov = torch.empty((B, K), dtype=torch.float32, device=dev)
     oi = torch.empty((B, K), dtype=torch.int64, device=dev)
@@ -106,7 +106,7 @@ for kind in ("f32x3", "bf16"):
 t1 = gpu_ms(lambda: engine.topk_rows(A_test, K))
 byts = 4.0 * B * N
 ex_v, ex_i = engine.topk_rows(A_test, K)
-ap_v, ap_i = engine.score_topk(Q, engine.PackedItems(E, "f32x3"), K_R)
+ap_v, ap_i = engine.score_topk(Q, engine.PackedItems(E, "f32r"), K_R)
 t2 = gpu_ms(lambda: engine.rerank_overlap(A_test, ap_i, ex_i, [1, 10, 50, 100]))
 Ah = A_test[:64].cpu()
 approx_h = (Qh[:64] @ Eh)

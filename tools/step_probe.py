@@ -16,7 +16,7 @@ ap.add_argument("--n", type=int, default=100000)
 ap.add_argument("--ki", type=int, default=500)
 ap.add_argument("--b", type=int, default=4096)
 ap.add_argument("--k", type=int, default=100)
-ap.add_argument("--precision", default="f32x3")
+ap.add_argument("--precision", default="f32r")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--streams", type=int, default=1)
