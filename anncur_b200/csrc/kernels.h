@@ -23,7 +23,7 @@ int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_c
 int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lists, int cap, int n_rows, int k,
                          int64_t idx_offset, const float* Q, int ldq, int k_dim, const float* ET, int ld,
                          const float* row_inv_scale, float* out_vals, int64_t* out_idx, uint32_t* thr_shared,
-                         uint32_t* mtile_flags, int m_tiles, int64_t n_items, cudaStream_t stream);
+                         uint32_t* mtile_flags, int m_tiles, int64_t n_items, int row_cap, cudaStream_t stream);
 
 // sgemm.cu
 int sgemm_rowmajor(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int m,

@@ -1412,7 +1412,13 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     // MAIN
     fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
     fp.close_compact = sampled ? 0 : 1;
-    if (refine && sampled) {
+    // F32R keeps a row's candidates in shared memory while it re-scores them: 1024 (k up to ~200) or 4096 per row; past
+    // that (cannot happen for k <= 1024) the call is served by the 3-pass launch
+    const double expect_row = sampled ? 1.25 * pl.sample_rank * pl.sample_stride : 0.0;
+    const int row_cap = 1.8 * expect_row <= 1024.0 ? 1024 : 4096;
+    // Re-scoring costs ~k x 2 KB of gathered reads per row (measured 1.9 us of kernel time per unit of k at B = 4096), the
+    // two extra tensor passes ~4.6 ns per item: beyond k ~ N / 400 the 3-pass launch is the faster way to the same answer.
+    if (refine && sampled && 1.5 * expect_row <= 4096.0 && int64_t(k) * 400 <= n_items) {
         // one f16 pass of upper bounds, then the exact re-scoring of the candidates (refine_topk.cu)
         fp.a_last_kb = akb_upper; fp.filter = 1;
         rc = cg == 2 ? dispatch_cap<1, false, 2>(pl.cap, a0, a0, b0, b0, fp, true, stream)
@@ -1420,7 +1426,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
         if (rc != ANNCUR_OK) return rc;
         rc = refine_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, Q, ldq, k_dim,
                                   reinterpret_cast<const float*>(items + L.off_et), et_ld(k_dim), inv_scale, out_vals, out_idx,
-                                  thr, flags, pl.m_tiles, n_items, stream);
+                                  thr, flags, pl.m_tiles, n_items, row_cap, stream);
         if (rc != ANNCUR_OK) return rc;
         fp.a_last_kb = akb_plain; fp.filter = 0;
     } else {
