@@ -2,7 +2,7 @@
 """Benchmark of the ANNCUR test-time search path (score + top-100) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|n1m|c4] [--precision f32x3|bf16] [--shard queries|items]
+                    [--workload c2|n1m|c4] [--precision f32r|f32x3|bf16] [--shard queries|items]
 
 One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch of B queries:
 ``CURApprox.topk_in_row`` = ``torch.topk(Q @ E, k, dim=1)`` (eval/matrix_approx_zeshel.py:109-126 of the
@@ -16,8 +16,9 @@ reference).  Workloads (BASELINE.json ``configs``):
 ``e2e``    : the same through the host-buffer C-ABI entry (anncur_search_host): pinned host Q -> H2D ->
              kernels -> D2H of (values, indices) every step.
 ``roofline``: dominant kernel (fused tcgen05 score + top-k), per-launch CUDA events recorded inside the
-             library on the launching stream; algorithmic flops 2*B*k_i*N (counted once for the 3-pass
-             fp32-grade kind), peak = MEASURED_PEAKS.json.
+             library on the launching stream; algorithmic flops 2*B*k_i*N (counted once, also for the 3-pass
+             kind), peak = MEASURED_PEAKS.json.  Default precision f32r: fp32 results from ONE f16 tensor pass
+             of rigorous score upper bounds + fp32 re-scoring of the ~k candidates per row.
 ``cpu_baseline`` / ``--impl reference``: the oracle's CPU restatement of the reference path
              (torch.matmul + torch.topk on all host threads) -- the only place bench executes oracle/.
 
@@ -421,7 +422,8 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of the MAIN kernel, one `ncu --set full` capture per (workload, kind)
     # (profiles/r1_ncu_fused_c2_f32x3_v8_details.txt); null where no capture was taken
-    NCU_TRAFFIC = {("c2", "f32x3"): 238.13e6 + 16.71e6}
+    # and profiles/r1_ncu_fused_c2_f32r_v13_details.txt
+    NCU_TRAFFIC = {("c2", "f32x3"): 238.13e6 + 16.71e6, ("c2", "f32r"): 110.78e6 + 12.60e6}
     roofline = {
         "kernel": "fused_score_topk_kernel (tcgen05 score GEMM + streaming top-k)",
         "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (tf / peak_tf) if tf else None,
