@@ -107,6 +107,34 @@ int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed
                             out_idx, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+size_t anncur_score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int kind) {
+    return score_dense_workspace_bytes(n_queries, n_items, k_dim, kind);
+}
+
+int anncur_score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                       int k_dim, int kind, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim > 0, "score_dense: bad shape");
+    if (n_queries == 0 || n_items == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(Q && packed_items && e_scale && out && workspace && ldq >= k_dim && ldo >= n_items, "score_dense: null pointer or short leading dimension");
+    return score_dense(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, out, ldo, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
+int anncur_recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                              int64_t n_items, int k_dim, int kind, const float* A, int64_t lda, double* out_err2,
+                              double* out_norm2, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim > 0, "recon_error_packed: bad shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(out_err2 && out_norm2, "recon_error_packed: null output");
+    if (n_items == 0) {
+        ANNCUR_CUDA_OK(cudaMemsetAsync(out_err2, 0, sizeof(double) * size_t(n_queries), cudaStream_t(stream)));
+        ANNCUR_CUDA_OK(cudaMemsetAsync(out_norm2, 0, sizeof(double) * size_t(n_queries), cudaStream_t(stream)));
+        return ANNCUR_OK;
+    }
+    ANNCUR_REQUIRE(Q && packed_items && e_scale && A && workspace && ldq >= k_dim && lda >= n_items, "recon_error_packed: null pointer or short leading dimension");
+    return recon_error_packed(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, A, lda, out_err2, out_norm2, workspace,
+                              workspace_bytes, cudaStream_t(stream));
+}
+
 int anncur_score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind,
                                 int* redo_rows_host, void* stream) {
     ANNCUR_REQUIRE(workspace && redo_rows_host, "score_topk_redo_rows: null pointer");

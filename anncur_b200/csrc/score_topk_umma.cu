@@ -93,6 +93,8 @@ template <int PASSES, int CG> struct StageCfg {
 };
 
 enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
+// epilogue family (compile time): per-row top-k (MAIN / SAMPLE), dense store of the scores, or squared reconstruction error
+enum : int { EPI_TOPK = 0, EPI_DENSE = 1, EPI_ERR = 2 };
 
 struct FusedParams {
     int mode;                // MODE_MAIN: push survivors;  MODE_SAMPLE: record 32-column group maxima
@@ -114,6 +116,11 @@ struct FusedParams {
     int filter;              // MODE_MAIN, F32R: scores are upper bounds -> lists are never cut back; a list that fills up is
                              // marked (top bit of its count) and the row goes to REDO
     int* error_flag;
+    // EPI_DENSE: out[row][col] = score; EPI_ERR: err2[row] += (score - exact[row][col])^2, norm2[row] += exact[row][col]^2
+    const float* row_inv_scale;     // accumulator (scaled units) * row_inv_scale[row] = score
+    float* dense_out;  int64_t ldo;
+    const float* exact; int64_t lda;
+    double* err2; double* norm2;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -297,7 +304,7 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, uint32_t n
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int PASSES, bool BF16, int CPL, int CG>
+template <int PASSES, bool BF16, int CPL, int CG, int EPI>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -485,10 +492,52 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             uint32_t cnt = 0, overflow = 0;
             float thr_own = -INFINITY;
             float thr = INFINITY;
+            const float row_scale = (EPI != EPI_TOPK && row_ok) ? __ldg(p.row_inv_scale + row) : 0.f;
+            double err_acc = 0.0, norm_acc = 0.0;
 
             // one 32-column group of this thread's row, already in registers
             auto process = [&](const uint32_t (&r)[32], int tile, int c) {
                 const int col0 = tile * BLOCK_N + c * 32;
+                if constexpr (EPI == EPI_DENSE) {
+                    // this thread's 32 consecutive scores of one row: 128 contiguous bytes of the output
+                    if (!row_ok) return;
+                    float* dst = p.dense_out + int64_t(row) * p.ldo + col0;
+                    if (col0 + 32 <= p.n_items && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            __stcs(reinterpret_cast<float4*>(dst + j),
+                                   make_float4(__uint_as_float(r[j]) * row_scale, __uint_as_float(r[j + 1]) * row_scale,
+                                               __uint_as_float(r[j + 2]) * row_scale, __uint_as_float(r[j + 3]) * row_scale));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n_items) dst[j] = __uint_as_float(r[j]) * row_scale;
+                    }
+                    return;
+                } else if constexpr (EPI == EPI_ERR) {
+                    if (!row_ok) return;
+                    const float* a = p.exact + int64_t(row) * p.lda + col0;
+                    float e2 = 0.f, n2 = 0.f;
+                    if (col0 + 32 <= p.n_items && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 v = __ldcs(reinterpret_cast<const float4*>(a + j));
+                            const float d0 = __uint_as_float(r[j]) * row_scale - v.x, d1 = __uint_as_float(r[j + 1]) * row_scale - v.y;
+                            const float d2 = __uint_as_float(r[j + 2]) * row_scale - v.z, d3 = __uint_as_float(r[j + 3]) * row_scale - v.w;
+                            e2 = fmaf(d0, d0, e2); e2 = fmaf(d1, d1, e2); e2 = fmaf(d2, d2, e2); e2 = fmaf(d3, d3, e2);
+                            n2 = fmaf(v.x, v.x, n2); n2 = fmaf(v.y, v.y, n2); n2 = fmaf(v.z, v.z, n2); n2 = fmaf(v.w, v.w, n2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n_items) {
+                                const float v = a[j], d = __uint_as_float(r[j]) * row_scale - v;
+                                e2 = fmaf(d, d, e2); n2 = fmaf(v, v, n2);
+                            }
+                    }
+                    err_acc += double(e2); norm_acc += double(n2);       // fp32 inside 32 columns, fp64 across them
+                    return;
+                }
                 float g[4], g4[8];
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
@@ -560,7 +609,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             for (int tile = t0; tile < t1; ++tile) {
                 // the cross-chunk bound (exclusive): fixed for the whole pass when it was sampled, refreshed per tile
                 // in streaming mode (other chunks of the row tighten it as they compact)
-                if (!sample && (tile == t0 || p.close_compact != 0)) {
+                if (EPI == EPI_TOPK && !sample && (tile == t0 || p.close_compact != 0)) {
                     thr = INFINITY;
                     if (row_ok && overflow == 0u) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
                 }
@@ -574,7 +623,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                 for (int c = c_begin; c < c_end; c += 2) {
                     tmem_ld_wait(ra);
                     tmem_ld_issue(taddr + uint32_t((c + 1) * 32), rb);
-                    if (!sample) make_room();
+                    if (EPI == EPI_TOPK && !sample) make_room();
                     process(ra, tile, c);
                     tmem_ld_wait(rb);
                     if (c + 2 < c_end) {
@@ -585,12 +634,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                         __syncwarp();
                         if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(buf)); else mbar_arrive(tempty_bar(buf)); }
                     }
-                    if (!sample) make_room();
+                    if (EPI == EPI_TOPK && !sample) make_room();
                     process(rb, tile, c + 1);
                 }
                 if (++buf == 2) { buf = 0; acc_phase ^= 1u; }
             }
-            if (sample) continue;
+            if (EPI == EPI_ERR && row_ok) {
+                atomicAdd(p.err2 + row, err_acc);
+                atomicAdd(p.norm2 + row, norm_acc);
+            }
+            if (EPI != EPI_TOPK || sample) continue;
             // close the work item (streaming mode): lists longer than k are cut back, which publishes a tighter bound
             uint32_t over_mask = __ballot_sync(0xffffffffu, p.close_compact != 0 && row_ok && cnt > k);
             while (over_mask) {
@@ -1260,12 +1313,12 @@ int profile_read(double* ms_sum, int* launches) {
     return ANNCUR_OK;
 }
 
-template <int PASSES, bool BF16, int CPL, int CG>
+template <int PASSES, bool BF16, int CPL, int CG, int EPI = EPI_TOPK>
 static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                         const FusedParams& fp, bool timed, cudaStream_t stream) {
     using Cfg = StageCfg<PASSES, CG>;
     const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4;
-    auto kernel = fused_score_topk_kernel<PASSES, BF16, CPL, CG>;
+    auto kernel = fused_score_topk_kernel<PASSES, BF16, CPL, CG, EPI>;
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // persistent: one CTA (pair) per SM (pair), never more CTAs than work items
     const long long units = 1ll * ((fp.m_tiles + CG - 1) / CG) * fp.n_chunks;
@@ -1441,6 +1494,108 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     if ((rc = launch_full(fp, false)) != ANNCUR_OK) return rc;
     return select_topk_keylists(cand, counts, pl.n_chunks * EPI_HALVES, int(pl.cap), n_queries, k, idx_offset, inv_scale, out_vals,
                                 out_idx, 2, thr, flags, pl.m_tiles, n_items, big_rows, stream);
+}
+
+// ---- dense products on the same pipeline -----------------------------------------------------------------------------
+// out = Q . E (EPI_DENSE) or per-row sum_j (Q . E - A)^2, sum_j A^2 (EPI_ERR) with the 3-pass fp32-grade arithmetic of
+// kind F32X3 (also on the planes of an F32R index).  Replaces the FFMA GEMM for the dense getters
+// (eval/matrix_approx_zeshel.py:71-119), the item-embedding build U @ R (:65; pack R, pass U as the queries) and the
+// Frobenius errors (eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147).
+struct DensePlan {
+    int num_kb, m_tiles, n_tiles, n_chunks;
+    size_t off_qplanes, off_inv_scale, off_delta, off_thr, off_flags, off_err, total;
+};
+
+static DensePlan make_dense_plan(int n_queries, int64_t n_items, int k_dim, int kind) {
+    DensePlan pl{};
+    pl.num_kb = num_kb_for(k_dim, kind);
+    pl.m_tiles = (n_queries + BLOCK_M - 1) / BLOCK_M;
+    pl.n_tiles = int((n_items + BLOCK_N - 1) / BLOCK_N);
+    const int cg = cta_group_for(pl.m_tiles);
+    const int units = sm_count() / cg > 0 ? sm_count() / cg : 1;
+    pl.n_chunks = choose_chunks((pl.m_tiles + cg - 1) / cg, pl.n_tiles > 0 ? pl.n_tiles : 1, units, 0.0);
+    size_t off = 0;
+    pl.off_qplanes = off; off += 2 * plane_bytes(n_queries, q_plane_kb(pl.num_kb, kind));
+    pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
+    pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
+    pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
+    pl.off_flags = off; off += align_up(sizeof(uint32_t) * (size_t(pl.m_tiles) + 2), 256);
+    pl.off_err = off; off += 256;
+    pl.total = off;
+    return pl;
+}
+
+size_t score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int kind) {
+    if (n_queries <= 0 || n_items <= 0 || k_dim <= 0) return 256;
+    return make_dense_plan(n_queries, n_items, k_dim, kind).total;
+}
+
+static int run_dense(int epi, const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                     int64_t n_items, int k_dim, int kind, float* out, int64_t ldo, const float* exact, int64_t lda,
+                     double* err2, double* norm2, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_F32R) { set_error("score_dense: kind %d has no fp32-grade planes", kind); return ANNCUR_E_INVALID; }
+    if (n_queries <= 0 || n_items <= 0) return ANNCUR_OK;
+    if (k_dim <= 0) { set_error("score_dense: k_dim must be positive"); return ANNCUR_E_INVALID; }
+    if (n_items >= (int64_t(1) << 31) - BLOCK_N) { set_error("score_dense: n_items %lld too large", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
+    const DensePlan pl = make_dense_plan(n_queries, n_items, k_dim, kind);
+    if (workspace_bytes < pl.total) { set_error("score_dense workspace too small: %zu < %zu", workspace_bytes, pl.total); return ANNCUR_E_WORKSPACE; }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(packed_items) & 255)) {
+        set_error("score_dense: workspace and packed_items must be 256-byte aligned");
+        return ANNCUR_E_INVALID;
+    }
+    char* ws = reinterpret_cast<char*>(workspace);
+    const int q_kb = q_plane_kb(pl.num_kb, kind);
+    const size_t qpb = plane_bytes(n_queries, q_kb);
+    uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
+    uint16_t* q_l = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
+    float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
+    float* delta = reinterpret_cast<float*>(ws + pl.off_delta);
+    uint32_t* thr = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
+    int* err = reinterpret_cast<int*>(ws + pl.off_err);
+    const PackedLayout L = packed_layout(n_items, k_dim, kind);
+    const char* items = reinterpret_cast<const char*>(packed_items);
+    const float* e_rowmax = reinterpret_cast<const float*>(items + L.off_rowmax);
+    const int qgrid = (n_queries + 7) / 8;
+    if (kind == ANNCUR_KIND_F32R) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    ANNCUR_LAUNCH_OK("pack_queries_kernel");
+    if (epi == EPI_ERR) {
+        ANNCUR_CUDA_OK(cudaMemsetAsync(err2, 0, sizeof(double) * size_t(n_queries), stream));
+        ANNCUR_CUDA_OK(cudaMemsetAsync(norm2, 0, sizeof(double) * size_t(n_queries), stream));
+    }
+    const int cg = cta_group_for(pl.m_tiles);
+    const int b_box = BLOCK_N / cg;
+    CUtensorMap a0, a1, b0, b1;
+    int rc;
+    if ((rc = make_plane_map(&a0, q_h, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&a1, q_l, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&b1, items + L.plane, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
+    FusedParams fp{};
+    fp.mode = MODE_MAIN; fp.n_queries = n_queries; fp.n_items = int(n_items); fp.num_kb = pl.num_kb; fp.k = 1;
+    fp.m_tiles = pl.m_tiles; fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks; fp.error_flag = err;
+    fp.a_last_kb = kind == ANNCUR_KIND_F32R ? pl.num_kb + 1 : pl.num_kb - 1;     // plain scores: bound slot = 0
+    fp.row_inv_scale = inv_scale; fp.dense_out = out; fp.ldo = ldo; fp.exact = exact; fp.lda = lda; fp.err2 = err2; fp.norm2 = norm2;
+    fp.smax = reinterpret_cast<float*>(ws); fp.cand = reinterpret_cast<uint64_t*>(ws); fp.counts = thr; fp.thr_shared = thr;   // unused by these epilogues
+    if (epi == EPI_DENSE)
+        return cg == 2 ? launch_fused<3, false, 8, 2, EPI_DENSE>(a0, a1, b0, b1, fp, true, stream)
+                       : launch_fused<3, false, 8, 1, EPI_DENSE>(a0, a1, b0, b1, fp, true, stream);
+    return cg == 2 ? launch_fused<3, false, 8, 2, EPI_ERR>(a0, a1, b0, b1, fp, true, stream)
+                   : launch_fused<3, false, 8, 1, EPI_ERR>(a0, a1, b0, b1, fp, true, stream);
+}
+
+int score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                int k_dim, int kind, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return run_dense(EPI_DENSE, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, out, ldo, nullptr, 0, nullptr,
+                     nullptr, workspace, workspace_bytes, stream);
+}
+
+int recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                       int k_dim, int kind, const float* A, int64_t lda, double* out_err2, double* out_norm2, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+    return run_dense(EPI_ERR, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, nullptr, 0, A, lda, out_err2,
+                     out_norm2, workspace, workspace_bytes, stream);
 }
 
 }  // namespace anncur

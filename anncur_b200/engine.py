@@ -168,8 +168,9 @@ class PackedItems:
 
 
 # ---- K3 + K4 --------------------------------------------------------------------------------------
-def score_topk(Q, packed, k, idx_offset=0, out=None):
-    """Fused tensor-core approximate score + top-k (eval/matrix_approx_zeshel.py:109-126)."""
+def score_topk(Q, packed, k, idx_offset=0, out=None, ws=None):
+    """Fused tensor-core approximate score + top-k (eval/matrix_approx_zeshel.py:109-126).  ``ws``: caller-owned
+    workspace (uint8 CUDA tensor of anncur_score_topk_workspace_bytes); default = the per-device cached one."""
     lib = _lib.load()
     Q = _f32(Q, device=packed.device)
     assert Q.dim() == 2 and Q.shape[1] == packed.k_dim, (Q.shape, packed.k_dim)
@@ -181,12 +182,99 @@ def score_topk(Q, packed, k, idx_offset=0, out=None):
         vals, idx = out
     if B > 0:
         nbytes = lib.anncur_score_topk_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
-        ws = WORKSPACE.get("score_topk", nbytes, Q.device)
+        if ws is None:
+            ws = WORKSPACE.get("score_topk", nbytes, Q.device)
+        assert ws.numel() >= nbytes and ws.device == Q.device
         with torch.cuda.device(Q.device):
             _lib.check(lib.anncur_score_topk(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), packed.n_items,
                                              packed.k_dim, packed.kind, int(k), int(idx_offset), _ptr(vals), _ptr(idx),
                                              _ptr(ws), ws.numel(), _stream()))
     return vals, idx
+
+
+def score_dense(Q, packed, out=None):
+    """Dense Q . E (B x N fp32) on the tensor-core pipeline (anncur_score_dense): the fp32-grade 3-pass arithmetic on a
+    packed index of kind f32x3 / f32r.  eval/matrix_approx_zeshel.py:71-119 when the full matrix is wanted."""
+    lib = _lib.load()
+    Q = _f32(Q, device=packed.device)
+    assert Q.dim() == 2 and Q.shape[1] == packed.k_dim, (Q.shape, packed.k_dim)
+    assert packed.kind in (KIND_F32X3, KIND_F32R), "score_dense needs an fp32-grade index"
+    B, N = int(Q.shape[0]), packed.n_items
+    if out is None:
+        out = torch.empty((B, N), dtype=torch.float32, device=Q.device)
+    assert out.shape == (B, N) and out.dtype == torch.float32 and out.stride(1) == 1
+    if B > 0 and N > 0:
+        nbytes = lib.anncur_score_dense_workspace_bytes(B, N, packed.k_dim, packed.kind)
+        ws = WORKSPACE.get("score_dense", nbytes, Q.device)
+        with torch.cuda.device(Q.device):
+            _lib.check(lib.anncur_score_dense(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), N, packed.k_dim,
+                                              packed.kind, _ptr(out), _ld(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def gemm_tc(A, B, min_flops=2e9):
+    """A (m x k) @ B (k x n) through the tensor-core pipeline: B is packed as a throw-away fp32-grade index and A plays
+    the queries (the item-embedding build U @ R, eval/matrix_approx_zeshel.py:65).  Small products go to the FFMA GEMM."""
+    A = _f32(A)
+    B = _f32(B, device=A.device)
+    m, k = A.shape
+    n = B.shape[1]
+    if k == 0 or 2.0 * m * n * k < min_flops:
+        return gemm(A, B)
+    return score_dense(A, PackedItems(B, "f32x3"))
+
+
+def recon_error_packed(Q, packed, A):
+    """Per-row sum_j (Q . E - A)^2 and sum_j A^2 (fp64) without materialising Q . E, on the tensor-core pipeline."""
+    lib = _lib.load()
+    Q = _f32(Q, device=packed.device)
+    A = _f32(A, device=packed.device)
+    B, N = int(Q.shape[0]), packed.n_items
+    assert A.shape == (B, N) and Q.shape[1] == packed.k_dim
+    err2 = torch.empty(B, dtype=torch.float64, device=Q.device)
+    norm2 = torch.empty(B, dtype=torch.float64, device=Q.device)
+    if B > 0:
+        nbytes = lib.anncur_score_dense_workspace_bytes(B, N, packed.k_dim, packed.kind)
+        ws = WORKSPACE.get("score_dense", nbytes, Q.device)
+        with torch.cuda.device(Q.device):
+            _lib.check(lib.anncur_recon_error_packed(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), N, packed.k_dim,
+                                                     packed.kind, _ptr(A), _ld(A), _ptr(err2), _ptr(norm2), _ptr(ws),
+                                                     ws.numel(), _stream()))
+    return err2, norm2
+
+
+class GraphedSearch:
+    """score_topk for one fixed (batch, k) captured as a CUDA graph: a search is then ONE graph launch instead of the
+    7-9 kernel launches + a memset of the eager call -- what matters for small batches, where the step is a few tens
+    of microseconds and launch gaps are a large part of it.  Every library call is asynchronous on the caller's stream
+    and allocates nothing, so the capture needs no special path.
+
+        g = GraphedSearch(packed, B, k); vals, idx = g(Q)      # vals / idx are the graph's own output buffers
+    """
+
+    def __init__(self, packed, n_queries, k, idx_offset=0):
+        lib = _lib.load()
+        dev = packed.device
+        self.packed, self.k = packed, int(k)
+        self.q = torch.zeros((n_queries, packed.k_dim), dtype=torch.float32, device=dev)
+        self.vals = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        self.idx = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        nbytes = lib.anncur_score_topk_workspace_bytes(n_queries, packed.n_items, packed.k_dim, k, packed.kind)
+        self.ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside the capture (function attributes, TMA encode entry)
+            score_topk(self.q, packed, k, idx_offset, out=(self.vals, self.idx), ws=self.ws)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            score_topk(self.q, packed, k, idx_offset, out=(self.vals, self.idx), ws=self.ws)
+
+    def __call__(self, Q):
+        self.q.copy_(Q, non_blocking=True)
+        self.graph.replay()
+        return self.vals, self.idx
 
 
 def last_redo_rows(n_queries, packed, k):

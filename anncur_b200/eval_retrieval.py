@@ -120,7 +120,10 @@ def run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors
         else:
             v, i = engine.score_topk_f32(cur._latent_rows_dev, cur._latent_cols_dev, int(top_k_retvr))
         approx_topk = (v, i)
-        err2, norm2 = engine.recon_error_rows(cur._latent_rows_dev, cur._latent_cols_dev, A)
+        if precision in ("f32r", "f32x3") and 2.0 * A.shape[0] * A.shape[1] * cur._latent_cols_dev.shape[0] >= 2e9:
+            err2, norm2 = engine.recon_error_packed(cur._latent_rows_dev, cur.packed_items(), A)      # tcgen05, fp32-grade
+        else:
+            err2, norm2 = engine.recon_error_rows(cur._latent_rows_dev, cur._latent_cols_dev, A)
     else:
         raise NotImplementedError(f"approx_method = {approx_method} not supported")
 

@@ -75,7 +75,8 @@ class CURApprox(object):
             self._latent_cols_dev = self._R_dev                              # k_r x m
         else:                                                                # reference :63-65
             self._latent_rows_dev = self._C_dev                              # n x k_c
-            self._latent_cols_dev = engine.gemm(U, self._R_dev)              # k_c x m   == E
+            # k_c x m == E; large builds run on the tensor-core pipeline (fp32-grade 3-pass), precision "f32" keeps FFMA
+            self._latent_cols_dev = engine.gemm(U, self._R_dev) if precision == "f32" else engine.gemm_tc(U, self._R_dev)
         self._packed = {}
         self._home_cache = {}
 
@@ -150,7 +151,11 @@ class CURApprox(object):
     def get_complete_row(self, sparse_rows):
         if self.approx_preference != "rows":
             raise NotImplementedError("This is not designed to give good approx of rows as C and U matrix are multiplied together. Build index w/ approx_preference = rows instead.")
-        return self._out(engine.gemm(torch.as_tensor(sparse_rows).to(self._dev, torch.float32), self._latent_cols_dev))
+        Q = torch.as_tensor(sparse_rows).to(self._dev, torch.float32)
+        precision = self.precision if self.precision in ("f32r", "f32x3") else None
+        if precision is None or 2.0 * Q.shape[0] * Q.shape[1] * self.m < 2e9:
+            return self._out(engine.gemm(Q, self._latent_cols_dev))
+        return self._out(engine.score_dense(Q, self.packed_items(precision)))      # tcgen05, fp32-grade
 
     def packed_items(self, precision=None):
         """The item-embedding matrix in the tensor-core streaming layout (built once per precision)."""

@@ -105,6 +105,22 @@ ANNCUR_API int anncur_score_topk(const float* Q, int ldq, int n_queries, const v
                       int64_t idx_offset, float* out_vals, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- dense products on the tensor-core pipeline ---------------------------------------------------
+ * out[B x N] = Q . E with the fp32-grade 3-pass arithmetic on a packed index of kind F32X3 or F32R: the tcgen05 form of
+ * CURApprox.get_complete_row / get_rows / get (eval/matrix_approx_zeshel.py:71-119) and of the item-embedding build
+ * latent_cols = U @ R (:65 -- pack R with anncur_pack_items, pass U as Q).  ~10x the FFMA rate of anncur_gemm_f32;
+ * operands carry 22-23 significant bits (relative error ~1e-6 of sum_i |q_i e_in|). */
+ANNCUR_API size_t anncur_score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int kind);
+ANNCUR_API int anncur_score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                       int64_t n_items, int k_dim, int kind, float* out, int64_t ldo,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* K7 on the same pipeline (replaces torch.norm((approx - A)[rows,:]), torch.norm(A[rows,:]),
+ * eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147): out_err2[r] = sum_j (Q[r,:].E[:,j] - A[r,j])^2,
+ * out_norm2[r] = sum_j A[r,j]^2 in fp64; Q . E is never written.  Workspace: anncur_score_dense_workspace_bytes. */
+ANNCUR_API int anncur_recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                              int64_t n_items, int k_dim, int kind, const float* A, int64_t lda,
+                              double* out_err2, double* out_norm2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Introspection: how many query rows of the LAST anncur_score_topk call that used `workspace` (same shape arguments)
  * were recomputed by the fallback pass (sampled threshold missed; kind F32R: a candidate list filled up or the exactness
  * certificate failed).  Results are correct either way -- this is the number that tells whether the fast path served

@@ -157,6 +157,21 @@ def test_fused_f32r_search_host_and_c2_sample(eng):
     assert torch.equal(ih, i.cpu()) and torch.equal(vh, v.cpu())
 
 
+def test_score_topk_captured_as_cuda_graph(eng):
+    """The whole call (pack, SAMPLE, threshold, MAIN, refine, REDO, select) is capturable: a replayed graph gives the
+    eager answer on fresh queries, for the sampled fast path and for the small unsampled one."""
+    for (B, K, N, k, kind) in [(64, 500, 60000, 100, "f32r"), (64, 96, 3000, 10, "f32r"), (200, 64, 70000, 20, "bf16")]:
+        E = _rand((K, N), 51)
+        packed = eng.PackedItems(E.cuda(), kind)
+        g = eng.GraphedSearch(packed, B, k, idx_offset=5)
+        for seed in (52, 53):
+            Q = _rand((B, K), seed).cuda()
+            gv, gi = g(Q)
+            ev, ei = eng.score_topk(Q, packed, k, idx_offset=5)
+            torch.cuda.synchronize()
+            assert torch.equal(gi, ei) and torch.equal(gv, ev)
+
+
 def test_fused_k_larger_than_items_pads(eng):
     _check(eng, _rand((5, 16), 1), _rand((16, 40), 2), 64)
 

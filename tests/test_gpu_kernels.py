@@ -234,3 +234,38 @@ def test_overlap_counts_set_semantics(eng):
         got = eng.overlap_counts(torch.from_numpy(a), torch.from_numpy(b)).cpu().numpy()
         want = np.array([len(set(a[r].tolist()) & set(b[r].tolist())) for r in range(n)])
         assert np.array_equal(got, want)
+
+
+# ---- dense products on the tcgen05 pipeline (anncur_score_dense / anncur_recon_error_packed) -------------------------
+@pytest.mark.parametrize("B,K,N,kind", [
+    (500, 2000, 30000, "f32x3"),     # the item-embedding build U @ R: 63 k-blocks
+    (300, 500, 70001, "f32r"),       # get_complete_row on an F32R index (bound slot must not leak), ragged N (unaligned rows)
+    (7, 50, 257, "f32x3"),           # tiny / ragged everything, single CTA
+    (129, 64, 4096, "f32r"),         # K % 32 == 0 on F32R: extra k-block
+])
+def test_score_dense_matches_fp64(eng, B, K, N, kind):
+    rng = np.random.default_rng(B + K + N)
+    Q = torch.from_numpy(rng.standard_normal((B, K), dtype=np.float32) * np.logspace(-2, 2, B, dtype=np.float32)[:, None])
+    E = torch.from_numpy(rng.standard_normal((K, N), dtype=np.float32))
+    out = eng.score_dense(Q.cuda(), eng.PackedItems(E.cuda(), kind)).cpu().double()
+    ref = Q.double() @ E.double()
+    scale = (Q.double().abs() @ E.double().abs()).clamp_min(1e-30)          # sum_i |q_i e_in|
+    assert ((out - ref).abs() / scale).max().item() < 2e-6
+
+
+def test_gemm_tc_and_recon_error_packed(eng):
+    rng = np.random.default_rng(9)
+    U = torch.from_numpy(rng.standard_normal((200, 700), dtype=np.float32))
+    R = torch.from_numpy(rng.standard_normal((700, 50000), dtype=np.float32))
+    E = eng.gemm_tc(U.cuda(), R.cuda())
+    ref = U.double() @ R.double()
+    assert ((E.cpu().double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    Q = torch.from_numpy(rng.standard_normal((333, 200), dtype=np.float32))
+    # "exact" matrix = approximation + noise of 5 % of the score scale (the errors being summed are far above fp32 rounding)
+    S = Q.double() @ ref
+    A = (S + torch.from_numpy(rng.standard_normal((333, 50000))) * 0.05 * S.std()).float()
+    for kind in ("f32x3", "f32r"):
+        e2, n2 = eng.recon_error_packed(Q.cuda(), eng.PackedItems(E, kind), A.cuda())
+        want_e2 = ((Q.double() @ E.cpu().double() - A.double()) ** 2).sum(1)
+        want_n2 = (A.double() ** 2).sum(1)
+        assert torch.allclose(e2.cpu(), want_e2, rtol=1e-4) and torch.allclose(n2.cpu(), want_n2, rtol=1e-5)

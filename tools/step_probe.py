@@ -20,6 +20,7 @@ ap.add_argument("--precision", default="f32r")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--streams", type=int, default=1)
+ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (engine.GraphedSearch)")
 a = ap.parse_args()
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
@@ -32,7 +33,10 @@ packed = engine.PackedItems(E, a.precision)
 ov = [torch.empty((a.b, a.k), dtype=torch.float32, device=dev) for _ in range(a.streams)]
 oi = [torch.empty((a.b, a.k), dtype=torch.int64, device=dev) for _ in range(a.streams)]
 streams = [torch.cuda.Stream() for _ in range(a.streams)] if a.streams > 1 else [torch.cuda.current_stream()]
+graphed = engine.GraphedSearch(packed, a.b, a.k) if a.graph else None
 def step(j):
+    if graphed is not None:
+        return graphed(Q[j % 2])
     s = j % a.streams
     with torch.cuda.stream(streams[s]):
         engine.score_topk(Q[j % 2], packed, a.k, out=(ov[s], oi[s]))
