@@ -116,9 +116,16 @@ class CURApprox(object):
         return t if t.device == self._home else t.to(self._home)
 
     # -- dense getters (reference :71-86) ----------------------------------------------------------
+    def _rows_times_latent_cols(self, Q):
+        """Q (B x k_c) @ latent_cols: tcgen05 fp32-grade pipeline for large products, FFMA for small ones / precision f32."""
+        precision = self.precision if self.precision in ("f32r", "f32x3") else None
+        if precision is None or 2.0 * Q.shape[0] * Q.shape[1] * self.m < 2e9:
+            return engine.gemm(Q, self._latent_cols_dev)
+        return engine.score_dense(Q, self.packed_items(precision))
+
     def get_rows(self, row_idxs):
         r = _as_index_tensor(row_idxs, self._dev)
-        return self._out(engine.gemm(self._latent_rows_dev.index_select(0, r), self._latent_cols_dev))
+        return self._out(self._rows_times_latent_cols(self._latent_rows_dev.index_select(0, r)))
 
     def get_cols(self, col_idxs):
         c = _as_index_tensor(col_idxs, self._dev)
@@ -129,8 +136,8 @@ class CURApprox(object):
         c = _as_index_tensor(col_idxs, self._dev)
         lc = self._latent_cols_dev
         if not (c.numel() == lc.shape[1] and bool((c == torch.arange(lc.shape[1], device=c.device)).all())):
-            lc = lc.index_select(1, c)
-        return self._out(engine.gemm(self._latent_rows_dev.index_select(0, r), lc))
+            return self._out(engine.gemm(self._latent_rows_dev.index_select(0, r), lc.index_select(1, c)))
+        return self._out(self._rows_times_latent_cols(self._latent_rows_dev.index_select(0, r)))
 
     # -- column side (reference :88-106) ------------------------------------------------------------
     def get_complete_col(self, sparse_cols):
@@ -151,11 +158,7 @@ class CURApprox(object):
     def get_complete_row(self, sparse_rows):
         if self.approx_preference != "rows":
             raise NotImplementedError("This is not designed to give good approx of rows as C and U matrix are multiplied together. Build index w/ approx_preference = rows instead.")
-        Q = torch.as_tensor(sparse_rows).to(self._dev, torch.float32)
-        precision = self.precision if self.precision in ("f32r", "f32x3") else None
-        if precision is None or 2.0 * Q.shape[0] * Q.shape[1] * self.m < 2e9:
-            return self._out(engine.gemm(Q, self._latent_cols_dev))
-        return self._out(engine.score_dense(Q, self.packed_items(precision)))      # tcgen05, fp32-grade
+        return self._out(self._rows_times_latent_cols(torch.as_tensor(sparse_rows).to(self._dev, torch.float32)))
 
     def packed_items(self, precision=None):
         """The item-embedding matrix in the tensor-core streaming layout (built once per precision)."""

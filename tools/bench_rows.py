@@ -86,6 +86,9 @@ Uh, Rh = U.cpu(), R.cpu()
 fl = 2.0 * K_I * N_TRAIN * N
 emit("A2", f"E = U[{K_I}x{N_TRAIN}] @ R[{N_TRAIN}x{N}]  (fp32 FFMA)", t, cpu_s(lambda: Uh @ Rh), "full size, torch.matmul",
      flops=fl, tflops=round(fl / t / 1e9, 1), bound="fp32 FFMA pipe (no fp32 tensor path that keeps fp32 products)")
+t = gpu_ms(lambda: engine.gemm_tc(U, R))
+emit("A2", f"E = U @ R on the tcgen05 pipeline (fp32-grade 3-pass; packs R first)", t, cpu_s(lambda: Uh @ Rh), "full size, torch.matmul",
+     flops=fl, tflops=round(fl / t / 1e9, 1), bound="tensor pipe at 1/3 rate + one packing pass over R (0.8 GB read, 0.8 GB written)")
 # A3 dense scores
 t = gpu_ms(lambda: engine.gemm(Q, E))
 Qh, Eh = Q.cpu(), E.cpu()
@@ -93,6 +96,12 @@ fl = 2.0 * B * K_I * N
 s_cpu = cpu_s(lambda: Qh[:1024] @ Eh) * (B / 1024)
 emit("A3", f"scores = Q[{B}x{K_I}] @ E[{K_I}x{N}] dense (get_complete_row)", t, s_cpu, "1024 of 4096 rows, torch.matmul",
      flops=fl, tflops=round(fl / t / 1e9, 1), bound="fp32 FFMA pipe; writes the 1.6 GB score matrix")
+packed_r = engine.PackedItems(E, "f32r")
+dense_out = torch.empty((B, N), dtype=torch.float32, device=dev)
+t = gpu_ms(lambda: engine.score_dense(Q, packed_r, out=dense_out))
+emit("A3", f"scores = Q @ E dense on the tcgen05 pipeline (fp32-grade 3-pass, F32R index)", t, s_cpu, "1024 of 4096 rows, torch.matmul",
+     flops=fl, tflops=round(fl / t / 1e9, 1), bound="tensor pipe at 1/3 rate; writes the 1.6 GB score matrix")
+del dense_out
 # A4 fused
 for kind in ("f32r", "f32x3", "bf16"):
     packed = engine.PackedItems(E, kind)
@@ -120,6 +129,9 @@ t = gpu_ms(lambda: engine.recon_error_rows(Q, E, A_test))
 s_cpu = cpu_s(lambda: (torch.norm(Qh[:1024] @ Eh - A_test[:1024].cpu()), torch.norm(A_test[:1024].cpu()))) * (B / 1024)
 emit("A7", f"|Q E - A|_F and |A|_F over {B}x{N} (never materialises Q E)", t, s_cpu, "1024 of 4096 rows, torch",
      flops=fl, tflops=round(fl / t / 1e9, 1), bound="fp32 FFMA pipe + one HBM read of A")
+t = gpu_ms(lambda: engine.recon_error_packed(Q, packed_r, A_test))
+emit("A7", f"|Q E - A|_F and |A|_F on the tcgen05 pipeline (fp32-grade 3-pass)", t, s_cpu, "1024 of 4096 rows, torch",
+     flops=fl, tflops=round(fl / t / 1e9, 1), bound="tensor pipe at 1/3 rate + one HBM read of A (1.6 GB)")
 # A8 adaptive round (m = 250 anchors per query, k_q = 500 anchor queries, next 125)
 Bq, m, k_q = 256, 250, 500
 R_anc = R[:k_q].contiguous()
