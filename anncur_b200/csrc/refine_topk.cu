@@ -71,18 +71,24 @@ __device__ __forceinline__ float rescore_batch(const float4 (&qv)[U], const floa
             asm volatile("" : "+f"(e[c][u].x), "+f"(e[c][u].y), "+f"(e[c][u].z), "+f"(e[c][u].w));
         }
     }
+    // packed fp32x2 FMAs (sm_100: fma.rn.f32x2): the (x, y) and (z, w) halves of a float4 accumulate side by side
     float s[kRefBatch];
 #pragma unroll
     for (int c = 0; c < kRefBatch; ++c) {
-        float acc = 0.f;
+        uint64_t acc2 = 0ull;                                            // (0.f, 0.f)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            acc = fmaf(qv[u].x, e[c][u].x, acc);
-            acc = fmaf(qv[u].y, e[c][u].y, acc);
-            acc = fmaf(qv[u].z, e[c][u].z, acc);
-            acc = fmaf(qv[u].w, e[c][u].w, acc);
+            uint64_t q_lo, q_hi, e_lo, e_hi;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(q_lo) : "f"(qv[u].x), "f"(qv[u].y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(q_hi) : "f"(qv[u].z), "f"(qv[u].w));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(e_lo) : "f"(e[c][u].x), "f"(e[c][u].y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(e_hi) : "f"(e[c][u].z), "f"(e[c][u].w));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(q_lo), "l"(e_lo));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(q_hi), "l"(e_hi));
         }
-        s[c] = acc;
+        float a_lo, a_hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a_lo), "=f"(a_hi) : "l"(acc2));
+        s[c] = a_lo + a_hi;
     }
     const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
     float a = (hi16 ? s[2] : s[0]) + __shfl_xor_sync(0xffffffffu, hi16 ? s[0] : s[2], 16);
@@ -169,26 +175,22 @@ refine_topk_kernel(const RefineParams p) {
         const uint32_t thr_ord = __ldcg(p.thr_shared + row);
 
         if (!redo) {
-            // ---- gather (flat element -> (list, position) by binary search in the offsets) ---------------
-            for (uint32_t e0 = uint32_t(warp) * 128u; e0 < total; e0 += 128u * W) {
-                uint64_t reg[4];
+            // ---- gather: list by list (a list is a contiguous run of <= cap entries), the loads of 8 lists in flight ------
+            for (int l0 = warp * 8; l0 < p.n_lists; l0 += 8 * W) {
+                uint64_t reg[8];
+                uint32_t base[8], cnt[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t e = e0 + uint32_t(u) * 32u + lane;
-                    reg[u] = 0ull;
-                    if (e < total) {
-                        int lo = 0, hi = p.n_lists;
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (offs[mid] <= e) lo = mid; else hi = mid;
-                        }
-                        reg[u] = raw_to_key(__ldcg(p.cand + (int64_t(row) * p.n_lists + lo) * p.cap + (e - offs[lo])));
-                    }
+                for (int u = 0; u < 8; ++u) {
+                    const int l = l0 + u;
+                    base[u] = l < p.n_lists ? offs[l] : 0u;
+                    cnt[u] = l < p.n_lists ? offs[l + 1] - base[u] : 0u;
+                    reg[u] = lane < cnt[u] ? __ldcg(p.cand + (int64_t(row) * p.n_lists + l) * p.cap + lane) : 0ull;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t e = e0 + uint32_t(u) * 32u + lane;
-                    if (e < total) keys[e] = reg[u];
+                for (int u = 0; u < 8; ++u) {
+                    if (lane < cnt[u]) keys[base[u] + lane] = raw_to_key(reg[u]);
+                    for (uint32_t t = lane + 32u; t < cnt[u]; t += 32u)      // the rare list with more than 32 entries
+                        keys[base[u] + t] = raw_to_key(__ldcg(p.cand + (int64_t(row) * p.n_lists + l0 + u) * p.cap + t));
                 }
             }
             // ---- the query row, in registers (zero beyond k_dim: those lanes re-read element 0 of the item) ---
