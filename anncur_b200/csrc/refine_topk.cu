@@ -136,7 +136,8 @@ refine_topk_kernel(const RefineParams p) {
     uint32_t* hist = reinterpret_cast<uint32_t*>(sh64 + 2);               // [256]
     float* sh_min = reinterpret_cast<float*>(hist + 256);                 // [W]
     uint32_t* sh_total = reinterpret_cast<uint32_t*>(sh_min + W);         // [2]: total, marked
-    uint32_t* offs = sh_total + 2;                                        // [n_lists + 1]
+    uint16_t* work = reinterpret_cast<uint16_t*>(sh_total + 2) + warp * (kRefCap / W);   // [kRefCap / W] per warp: positions to re-score
+    uint32_t* offs = sh_total + 2 + kRefCap / 2;                          // [n_lists + 1]
     const uint32_t k = uint32_t(p.k);
     const int ld4 = p.ld >> 2;
     const uint32_t lowest = float_to_ordered(-INFINITY);
@@ -207,17 +208,16 @@ refine_topk_kernel(const RefineParams p) {
                 }
             }
             cta_sync<W>();
-            // re-score the candidates of keys[t0 .. t0 + 32) named by `ballot` (same value in all lanes), four at a time:
-            // keys[pos] becomes (S, item); s_min collects this lane's share of the minimum
+            // re-score the candidates at positions work[0 .. n_work), four at a time: keys[pos] becomes (S, item);
+            // s_min collects this lane's share of the minimum
             float s_min = INFINITY;
-            auto rescore = [&](uint32_t t0, uint32_t ballot) {
-                while (ballot) {
+            auto rescore = [&](uint32_t n_work) {
+                for (uint32_t i0 = 0; i0 < n_work; i0 += kRefBatch) {
                     uint32_t pos[kRefBatch], item[kRefBatch];
-                    int n = 0;
+                    const int n = int(min(uint32_t(kRefBatch), n_work - i0));
 #pragma unroll
                     for (int c = 0; c < kRefBatch; ++c) {
-                        if (ballot) { pos[c] = t0 + uint32_t(__ffs(int(ballot)) - 1); ballot &= ballot - 1u; n = c + 1; }
-                        else pos[c] = pos[0];
+                        pos[c] = work[min(i0 + uint32_t(c), n_work - 1u)];
                         item[c] = key_index(keys[pos[c]]);
                     }
                     const int c_own = int(lane >> 3);
@@ -248,16 +248,21 @@ refine_topk_kernel(const RefineParams p) {
             }
             cta_sync<W>();
             {
-                // (an L2 prefetch of the next chunk's winners was tried here: no gain -- the row's time goes to issue latency
+                // this warp's winners -> work list (so that every batch of the re-scoring is full), then the re-scoring.
+                // (an L2 prefetch of the next candidates was tried here: no gain -- the row's time goes to issue latency
                 // of the many small steps at 16 warps per SM, not to waiting for DRAM)
                 const uint64_t prefix = sh64[0], mask = sh64[1];
+                uint32_t n_work = 0;
                 for (uint32_t t0 = uint32_t(warp) * 32u; t0 < total; t0 += 32u * W) {
                     const uint32_t t = t0 + lane;
                     const bool win = t < total && (keys[t] & mask) >= prefix;
                     const uint32_t ballot = __ballot_sync(0xffffffffu, win);
+                    if (win) work[n_work + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
                     if (lane == 0) hist[t0 >> 5] = ballot;                 // who has been re-scored (hist is free here)
-                    rescore(t0, ballot);
+                    n_work += __popc(ballot);
                 }
+                __syncwarp();
+                rescore(n_work);
             }
             s_min = -warp_max_f(-s_min);
             if (W > 1) {
@@ -270,6 +275,7 @@ refine_topk_kernel(const RefineParams p) {
             if (total > k) {
                 const float s_min_scaled = s_min * to_scaled;
                 __syncwarp();
+                uint32_t n_work = 0;
                 for (uint32_t t0 = uint32_t(warp) * 32u; t0 < total; t0 += 32u * W) {
                     const uint32_t t = t0 + lane;
                     const bool done = (hist[t0 >> 5] >> lane) & 1u;
@@ -277,16 +283,18 @@ refine_topk_kernel(const RefineParams p) {
                     const bool more = open && key_score(keys[t]) >= s_min_scaled;
                     if (open && !more) keys[t] = 0ull;
                     const uint32_t ballot = __ballot_sync(0xffffffffu, more);
-                    __syncwarp();
-                    rescore(t0, ballot);
+                    if (more) work[n_work + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(t);
+                    n_work += __popc(ballot);
                 }
+                __syncwarp();
+                rescore(n_work);
             }
             cta_sync<W>();
             // ---- top-k of the re-scored candidates (warp 0) --------------------------------------------------
             if (warp == 0) {
                 uint64_t prefix, mask;
                 uint32_t n_live = warp_compact_ge(keys, total, 0ull, 0ull);   // drops the zeroed entries
-                if (n_live > k) {
+                if (n_live > uint32_t(p.n_sort)) {                          // otherwise the sort below orders them all
                     warp_radix_kth(keys, n_live, k, hist, prefix, mask);
                     n_live = warp_compact_ge(keys, n_live, prefix, mask);
                 }
@@ -335,7 +343,7 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
     const bool wide = n_rows <= 4 * sm_count();               // few rows: 4 warps per row
     const int W = wide ? 4 : 1;
     const bool big = row_cap > 1024;
-    const size_t smem = (size_t(row_cap) + 2) * sizeof(uint64_t) + (256 + size_t(W) + 2 + size_t(n_lists) + 1) * sizeof(uint32_t);
+    const size_t smem = (size_t(row_cap) + 2) * sizeof(uint64_t) + (256 + size_t(W) + 2 + size_t(row_cap) / 2 + size_t(n_lists) + 1) * sizeof(uint32_t);
     const int grid = n_rows < 32 * sm_count() ? n_rows : 32 * sm_count();
     const int ld4 = ld >> 2;
     auto launch = [&](auto kernel) {
