@@ -72,7 +72,7 @@ class ClockSampler:
         0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting", 0x10: "sync_boost",
     }
 
-    def __init__(self, dev_index, period_s=0.02):
+    def __init__(self, dev_index, period_s=0.005):
         self.samples, self.reason_bits, self.power = [], 0, []
         self.max_mhz = None
         self._stop = threading.Event()
