@@ -27,6 +27,7 @@ PROTOTYPES = {
     "anncur_score_topk": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_score_dense_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "anncur_score_dense": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),
+    "anncur_score_bounds_dense": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),
     "anncur_recon_error_packed": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_score_topk_redo_rows": (_i, [_vp, _i, _i64, _i, _i, _i, C.POINTER(C.c_int), _vp]),
     "anncur_search_host_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),

@@ -119,6 +119,14 @@ int anncur_score_dense(const float* Q, int ldq, int n_queries, const void* packe
     return score_dense(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, out, ldo, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+int anncur_score_bounds_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                              int k_dim, int sign, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim > 0, "score_bounds_dense: bad shape");
+    if (n_queries == 0 || n_items == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(Q && packed_items && e_scale && out && workspace && ldq >= k_dim && ldo >= n_items, "score_bounds_dense: null pointer or short leading dimension");
+    return score_bounds_dense(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, sign, out, ldo, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
 int anncur_recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
                               int64_t n_items, int k_dim, int kind, const float* A, int64_t lda, double* out_err2,
                               double* out_norm2, void* workspace, size_t workspace_bytes, void* stream) {

@@ -56,6 +56,8 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
 size_t score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int kind);
 int score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
                 int k_dim, int kind, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int score_bounds_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                       int k_dim, int sign, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
                        int k_dim, int kind, const float* A, int64_t lda, double* out_err2, double* out_norm2, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream);

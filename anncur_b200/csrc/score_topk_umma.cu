@@ -1530,9 +1530,10 @@ size_t score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, in
     return make_dense_plan(n_queries, n_items, k_dim, kind).total;
 }
 
-static int run_dense(int epi, const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
                      int64_t n_items, int k_dim, int kind, float* out, int64_t ldo, const float* exact, int64_t lda,
                      double* err2, double* norm2, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (bound_sign != 0 && kind != ANNCUR_KIND_F32R) { set_error("score bounds exist for kind F32R only"); return ANNCUR_E_INVALID; }
     if (kind != ANNCUR_KIND_F32X3 && kind != ANNCUR_KIND_F32R) { set_error("score_dense: kind %d has no fp32-grade planes", kind); return ANNCUR_E_INVALID; }
     if (n_queries <= 0 || n_items <= 0) return ANNCUR_OK;
     if (k_dim <= 0) { set_error("score_dense: k_dim must be positive"); return ANNCUR_E_INVALID; }
@@ -1578,6 +1579,12 @@ static int run_dense(int epi, const float* Q, int ldq, int n_queries, const void
     fp.a_last_kb = kind == ANNCUR_KIND_F32R ? pl.num_kb + 1 : pl.num_kb - 1;     // plain scores: bound slot = 0
     fp.row_inv_scale = inv_scale; fp.dense_out = out; fp.ldo = ldo; fp.exact = exact; fp.lda = lda; fp.err2 = err2; fp.norm2 = norm2;
     fp.smax = reinterpret_cast<float*>(ws); fp.cand = reinterpret_cast<uint64_t*>(ws); fp.counts = thr; fp.thr_shared = thr;   // unused by these epilogues
+    if (bound_sign != 0) {
+        // what SAMPLE (-) and MAIN (+) of kind F32R see: the one-pass score with the error-bound slot switched on
+        fp.a_last_kb = bound_sign > 0 ? pl.num_kb - 1 : pl.num_kb;
+        return cg == 2 ? launch_fused<1, false, 8, 2, EPI_DENSE>(a0, a0, b0, b0, fp, true, stream)
+                       : launch_fused<1, false, 8, 1, EPI_DENSE>(a0, a0, b0, b0, fp, true, stream);
+    }
     if (epi == EPI_DENSE)
         return cg == 2 ? launch_fused<3, false, 8, 2, EPI_DENSE>(a0, a1, b0, b1, fp, true, stream)
                        : launch_fused<3, false, 8, 1, EPI_DENSE>(a0, a1, b0, b1, fp, true, stream);
@@ -1587,14 +1594,20 @@ static int run_dense(int epi, const float* Q, int ldq, int n_queries, const void
 
 int score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
                 int k_dim, int kind, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    return run_dense(EPI_DENSE, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, out, ldo, nullptr, 0, nullptr,
+    return run_dense(EPI_DENSE, 0, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, out, ldo, nullptr, 0, nullptr,
                      nullptr, workspace, workspace_bytes, stream);
+}
+
+int score_bounds_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
+                       int k_dim, int sign, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return run_dense(EPI_DENSE, sign >= 0 ? 1 : -1, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, ANNCUR_KIND_F32R, out,
+                     ldo, nullptr, 0, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int recon_error_packed(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale, int64_t n_items,
                        int k_dim, int kind, const float* A, int64_t lda, double* out_err2, double* out_norm2, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream) {
-    return run_dense(EPI_ERR, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, nullptr, 0, A, lda, out_err2,
+    return run_dense(EPI_ERR, 0, Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, nullptr, 0, A, lda, out_err2,
                      out_norm2, workspace, workspace_bytes, stream);
 }
 

@@ -212,6 +212,22 @@ def score_dense(Q, packed, out=None):
     return out
 
 
+def score_bounds_dense(Q, packed, sign):
+    """Dense matrix of the score bounds kind f32r works with (anncur_score_bounds_dense): sign >= 0 upper, < 0 lower."""
+    lib = _lib.load()
+    Q = _f32(Q, device=packed.device)
+    assert packed.kind == KIND_F32R and Q.shape[1] == packed.k_dim
+    B, N = int(Q.shape[0]), packed.n_items
+    out = torch.empty((B, N), dtype=torch.float32, device=Q.device)
+    if B > 0 and N > 0:
+        nbytes = lib.anncur_score_dense_workspace_bytes(B, N, packed.k_dim, packed.kind)
+        ws = WORKSPACE.get("score_dense", nbytes, Q.device)
+        with torch.cuda.device(Q.device):
+            _lib.check(lib.anncur_score_bounds_dense(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), N, packed.k_dim,
+                                                     int(sign), _ptr(out), _ld(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
 def gemm_tc(A, B, min_flops=2e9):
     """A (m x k) @ B (k x n) through the tensor-core pipeline: B is packed as a throw-away fp32-grade index and A plays
     the queries (the item-embedding build U @ R, eval/matrix_approx_zeshel.py:65).  Small products go to the FFMA GEMM."""

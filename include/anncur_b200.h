@@ -114,6 +114,15 @@ ANNCUR_API size_t anncur_score_dense_workspace_bytes(int n_queries, int64_t n_it
 ANNCUR_API int anncur_score_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
                        int64_t n_items, int k_dim, int kind, float* out, int64_t ldo,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* The bounds kind F32R works with, as a dense matrix (verification / diagnostics): out[b][n] = the one-pass f16 score of
+ * (query b, item n) plus (sign >= 0) or minus (sign < 0) its error bound b_n -- exactly what the MAIN (upper bounds) and
+ * SAMPLE (lower bounds) launches of anncur_score_topk compare with their thresholds.  The guarantee the kind rests on is
+ * lower <= fp32 score <= upper for every pair; tests/test_gpu_fused.py checks it against fp64, also on operands built to
+ * make the fp16 rounding errors add up coherently.  packed_items must be of kind F32R. */
+ANNCUR_API int anncur_score_bounds_dense(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                              int64_t n_items, int k_dim, int sign, float* out, int64_t ldo,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* K7 on the same pipeline (replaces torch.norm((approx - A)[rows,:]), torch.norm(A[rows,:]),
  * eval/run_retrieval_eval_wrt_exact_crossenc.py:146-147): out_err2[r] = sum_j (Q[r,:].E[:,j] - A[r,j])^2,
  * out_norm2[r] = sum_j A[r,j]^2 in fp64; Q . E is never written.  Workspace: anncur_score_dense_workspace_bytes. */

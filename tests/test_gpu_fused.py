@@ -82,6 +82,41 @@ def test_fused_f32r_scale_extremes_and_offsets(eng):
     _check(eng, _rand((50, 100), 8), E, 100, kind="f32r", rel=1e-5)
 
 
+def test_fused_f32r_bounds_enclose_the_fp32_score(eng):
+    """The guarantee kind f32r rests on: lower <= fp32 score <= upper for EVERY (query, item) pair, where lower / upper are
+    what its SAMPLE / MAIN launches compare with the thresholds (anncur_score_bounds_dense).  Checked against fp64 on random
+    data, on per-row / per-item magnitudes spread over 8 decades, on a low-rank CUR index (cancelling terms), and on operands
+    built so that every fp16 rounding error has the same sign and nearly the worst size (x = 2^e (1 + 2^-11 + 2^-13) rounds
+    up by 3/4 of a half-ulp; all products positive) -- the coherent case a statistical error model would miss."""
+    rng = np.random.default_rng(17)
+    cases = []
+    Q, E = _rand((200, 500), 61), _rand((500, 20000), 62)
+    cases.append(("random", Q, E))
+    cases.append(("magnitudes", Q * torch.logspace(-4, 4, 200).unsqueeze(1), E * torch.logspace(-4, 4, 20000).unsqueeze(0)))
+    A = torch.from_numpy(O.synthetic_scores(400, 20000, rank=64, noise=0.05, seed=3))
+    rows_i, cols_i = O.sample_anchors(400, 20000, 150, 300, 3)
+    f = O.cur_build(A[rows_i, :], A[:, cols_i], rows_i, cols_i, "rows", check=False)
+    cases.append(("cur", A[:, cols_i].contiguous(), f.latent_cols.contiguous()))
+    worst = np.float32(1.0 + 2.0 ** -11 + 2.0 ** -13)
+    Qw = torch.from_numpy((worst * 2.0 ** rng.integers(-3, 4, (130, 512))).astype(np.float32))
+    Ew = torch.from_numpy((worst * 2.0 ** rng.integers(-3, 4, (512, 9000))).astype(np.float32))
+    cases.append(("coherent worst case", Qw, Ew))
+    cases.append(("coherent, mixed signs", Qw * torch.from_numpy(rng.choice([-1.0, 1.0], (130, 512)).astype(np.float32)), -Ew))
+    for name, Q, E in cases:
+        packed = eng.PackedItems(E.cuda(), "f32r")
+        ub = eng.score_bounds_dense(Q.cuda(), packed, +1).cpu().double()
+        lb = eng.score_bounds_dense(Q.cuda(), packed, -1).cpu().double()
+        S = Q.double() @ E.double()
+        S32 = (Q.cuda() @ E.cuda()).cpu().double()            # an fp32 evaluation (cuBLAS), for the "fp32 score" side of the claim
+        slack = (ub - lb) / 2                                  # = b_n
+        assert (ub >= S).all() and (lb <= S).all(), name
+        assert (ub >= S32).all() and (lb <= S32).all(), name
+        used = ((S - (ub + lb) / 2).abs() / slack.clamp_min(1e-300)).max().item()
+        assert used <= 0.97, (name, used)                      # the bound is never exhausted (the 5 % reserve stays)
+        if name == "coherent worst case":
+            assert used > 0.2, used                            # ... and this case really does stress it
+
+
 def test_fused_f32r_fast_path_serves_generic_inputs(eng):
     """Generic inputs must not lean on the fallback: no row of a random / low-rank batch goes to REDO, while the
     adversarial batch (all-equal scores) is entirely recomputed there."""
