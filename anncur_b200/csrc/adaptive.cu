@@ -12,7 +12,7 @@
 
 namespace anncur {
 
-constexpr int AD_QB = 128;          // queries per block
+constexpr int AD_QB = 384;          // queries per block (the Cholesky kernel runs one CTA per query: ~3 per SM keep the SMs busy)
 
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int64_t cols,
                                  float* __restrict__ out /* cols x rows */) {
@@ -41,107 +41,195 @@ __global__ void gather_anchor_rows_kernel(const float* __restrict__ Rt, int k_q,
     for (int t = lane_id(); t < k_q; t += 32) dst[t] = src[t];
 }
 
-// G[b] = Mt[b] . Mt[b]^T  (m x m, fp64 accumulate), 32 x 32 output tile per CTA
+// G[b] = Mt[b] . Mt[b]^T  (m x m lower triangle, fp64 accumulate), 64 x 64 output tile per CTA, 4 x 4 per thread
+// (operands are converted to fp64 once, on their way into shared memory: the inner loop is 4 x LDS.128 + 16 DFMA).
+// G has row stride m and (m + 1) rows per query: row m is the right-hand side c of the solve (see below).
+constexpr int GR_T = 64, GR_K = 16;
 __global__ void __launch_bounds__(256)
 gram_kernel(const float* __restrict__ Mt, int m, int k_q, double* __restrict__ G) {
-    __shared__ float As[32][33], Bs[32][33];
+    __shared__ __align__(16) double As[GR_K][GR_T + 2], Bs[GR_K][GR_T + 2];
     const int b = blockIdx.z;
-    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int i0 = blockIdx.y * GR_T, j0 = blockIdx.x * GR_T;
     if (j0 > i0) return;                                   // lower triangle only
     const float* M = Mt + int64_t(b) * m * k_q;
-    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
-    double acc[4] = {0, 0, 0, 0};
-    for (int k0 = 0; k0 < k_q; k0 += 32) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, each a 4 x 4 block (rows ty*4.., cols tx*4..)
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int k0 = 0; k0 < k_q; k0 += GR_K) {
+        // 64 rows x 16 k of each operand: thread loads 4 elements of each (k fastest in global memory)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            int r = ty + s * 8;
-            As[r][tx] = (i0 + r < m && k0 + tx < k_q) ? M[int64_t(i0 + r) * k_q + k0 + tx] : 0.f;
-            Bs[r][tx] = (j0 + r < m && k0 + tx < k_q) ? M[int64_t(j0 + r) * k_q + k0 + tx] : 0.f;
+            const int e = threadIdx.x + s * 256;           // 0 .. 1023
+            const int r = e >> 4, kk = e & 15;
+            As[kk][r] = (i0 + r < m && k0 + kk < k_q) ? double(M[int64_t(i0 + r) * k_q + k0 + kk]) : 0.0;
+            Bs[kk][r] = (j0 + r < m && k0 + kk < k_q) ? double(M[int64_t(j0 + r) * k_q + k0 + kk]) : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) {
-            double bv = double(Bs[tx][kk]);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) acc[s] = fma(double(As[ty + s * 8][kk]), bv, acc[s]);
+        for (int kk = 0; kk < GR_K; ++kk) {
+            const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]), a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]), b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], bb[c], acc[r][c]);
         }
         __syncthreads();
     }
-    double* Gb = G + int64_t(b) * m * m;
+    double* Gb = G + int64_t(b) * (m + 1) * m;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        int i = i0 + ty + s * 8, j = j0 + tx;
-        if (i < m && j < m) { Gb[int64_t(i) * m + j] = acc[s]; Gb[int64_t(j) * m + i] = acc[s]; }
-    }
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+            if (i < m && j <= i) Gb[int64_t(i) * m + j] = acc[r][c];
+        }
 }
 
-// One CTA per query: in-place Cholesky G = L L^T (lower), forward/back substitution for y, then
-// e = y^T Mt  (1 x k_q).  Dropped pivots zero the matching coordinate of y.
+// One CTA per query: blocked right-looking Cholesky G = L L^T of the lower triangle (panels of 32 columns held in shared
+// memory), the solve G y = c, then e = y^T Mt (1 x k_q).
+//  * The right-hand side rides along as row m of the matrix: after the factorisation that row holds z = L^-1 c (forward
+//    substitution for free -- it takes part in the panel factorisations and is skipped by the trailing updates' diagonal).
+//  * Back substitution L^T y = z walks the panels in reverse, again from shared memory.
+//  * A pivot at or below rcond^2 * max diagonal is dropped: its column is zeroed and y_j = 0 (the min-norm rule of pinv
+//    restricted to the kept coordinates).
+// Per query: one pass over the trailing matrix per panel (m^3/6 fp64 FMAs from shared-memory operands), instead of one
+// pass per COLUMN over global memory with strided accesses as in the first version (7.7 ms per 256 queries at m = 250).
+constexpr int CH_NB = 32;
+constexpr int CH_LD = CH_NB + 1;          // panel row stride in doubles (bank-conflict padding)
+
 __global__ void __launch_bounds__(256)
 cholesky_solve_kernel(double* __restrict__ G, const float* __restrict__ c, const float* __restrict__ Mt, int m, int k_q,
                       double rcond, double* __restrict__ ybuf, float* __restrict__ e_out) {
-    const int b = blockIdx.x, tid = threadIdx.x;
-    double* L = G + int64_t(b) * m * m;
-    double* y = ybuf + int64_t(b) * m;
+    extern __shared__ __align__(16) double ch_smem[];
+    double* P = ch_smem;                                   // [(m + 1) rows][CH_LD]
+    double* ys = ch_smem + size_t(m + 1) * CH_LD;          // [m] solution vector (back substitution)
     __shared__ double s_piv, s_maxd;
     __shared__ double red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    double* L = G + int64_t(b) * (m + 1) * m;
+    double* y = ybuf + int64_t(b) * m;
+    // row m <- c
+    for (int i = tid; i < m; i += 256) L[int64_t(m) * m + i] = double(c[int64_t(b) * m + i]);
     // max diagonal -> drop tolerance
     double md = 0.0;
     for (int i = tid; i < m; i += 256) md = fmax(md, L[int64_t(i) * m + i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
-    if ((tid & 31) == 0) red[tid >> 5] = md;
+    if (tx == 0) red[ty] = md;
     __syncthreads();
     if (tid == 0) { double v = 0; for (int w = 0; w < 8; ++w) v = fmax(v, red[w]); s_maxd = v; }
     __syncthreads();
     const double drop = fmax(rcond * rcond, 1e-28) * s_maxd;   // pivots are squared singular-value scale
-    for (int j = 0; j < m; ++j) {
-        if (tid == 0) {
-            double d = L[int64_t(j) * m + j];
-            s_piv = d > drop ? sqrt(d) : 0.0;
-            L[int64_t(j) * m + j] = s_piv;
-        }
+
+    for (int j0 = 0; j0 < m; j0 += CH_NB) {
+        const int nb = m - j0 < CH_NB ? m - j0 : CH_NB;
+        const int rows = m + 1 - j0;                        // panel rows: matrix rows j0 .. m (row m = right-hand side)
+        // 1. panel -> shared memory
+        for (int r = ty; r < rows; r += 8)
+            if (tx < nb) P[r * CH_LD + tx] = (r >= tx || r >= nb) ? L[int64_t(j0 + r) * m + j0 + tx] : 0.0;
         __syncthreads();
-        const double piv = s_piv;
-        if (piv == 0.0) {
-            for (int i = j + 1 + tid; i < m; i += 256) L[int64_t(i) * m + j] = 0.0;
+        // 2. factor the panel column by column (diagonal block and everything below it)
+        for (int jj = 0; jj < nb; ++jj) {
+            if (tid == 0) {
+                const double d = P[jj * CH_LD + jj];
+                s_piv = d > drop ? sqrt(d) : 0.0;
+                P[jj * CH_LD + jj] = s_piv;
+            }
             __syncthreads();
-            continue;
+            const double piv = s_piv;
+            if (piv == 0.0) {
+                for (int r = jj + 1 + tid; r < rows; r += 256) P[r * CH_LD + jj] = 0.0;
+                __syncthreads();
+                continue;
+            }
+            const double inv = 1.0 / piv;
+            for (int r = jj + 1 + tid; r < rows; r += 256) P[r * CH_LD + jj] *= inv;
+            __syncthreads();
+            // P[r][t] -= P[r][jj] * P[t][jj] for jj < t < nb, r >= t
+            const int t = jj + 1 + tx;
+            if (t < nb) {
+                const double ptj = P[t * CH_LD + jj];
+                for (int r = t + ty; r < rows; r += 8) P[r * CH_LD + t] -= P[r * CH_LD + jj] * ptj;
+            }
+            __syncthreads();
         }
-        const double inv = 1.0 / piv;
-        for (int i = j + 1 + tid; i < m; i += 256) L[int64_t(i) * m + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: L[i][t] -= L[i][j] * L[t][j], j < t <= i
-        const int rem = m - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            int i = j + 1 + e / rem, t = j + 1 + e % rem;
-            if (t <= i) L[int64_t(i) * m + t] -= L[int64_t(i) * m + j] * L[int64_t(t) * m + j];
+        // 3. panel back to global memory
+        for (int r = ty; r < rows; r += 8)
+            if (tx < nb && (r >= tx || r >= nb)) L[int64_t(j0 + r) * m + j0 + tx] = P[r * CH_LD + tx];
+        // 4. trailing update: L[i][t] -= sum_k P[i][k] P[t][k] for j0 + nb <= t <= i <= m (t < m), 32 x 32 tiles
+        const int base = j0 + nb;
+        const int n_tr = m + 1 - base;                      // trailing rows (incl. the right-hand side row)
+        const int n_tc = m - base;                          // trailing columns
+        for (int ti = 0; ti < n_tr; ti += 32) {
+            for (int tt = 0; tt <= ti && tt < n_tc; tt += 32) {
+                const int tcol = tt + tx;                   // column (relative to base) of this thread
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                if (tcol < n_tc) {
+                    const double* pt = P + (nb + tcol) * CH_LD;
+                    for (int k = 0; k < nb; ++k) {
+                        const double v = pt[k];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int ri = ti + ty + q * 8;
+                            if (ri < n_tr) acc[q] = fma(P[(nb + ri) * CH_LD + k], v, acc[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ri = ti + ty + q * 8;
+                        if (ri < n_tr && tcol <= ri) L[int64_t(base + ri) * m + base + tcol] -= acc[q];
+                    }
+                }
+            }
         }
         __syncthreads();
     }
-    // forward substitution L z = c (thread 0 pivots, all threads update), z stored in y
-    for (int i = tid; i < m; i += 256) y[i] = double(c[int64_t(b) * m + i]);
+    // back substitution L^T y = z (z = row m), panels in reverse
+    for (int i = tid; i < m; i += 256) ys[i] = 0.0;
     __syncthreads();
-    for (int j = 0; j < m; ++j) {
-        if (tid == 0) { double p = L[int64_t(j) * m + j]; y[j] = p > 0.0 ? y[j] / p : 0.0; }
+    const int n_panels = (m + CH_NB - 1) / CH_NB;
+    for (int pi = n_panels - 1; pi >= 0; --pi) {
+        const int j0 = pi * CH_NB;
+        const int nb = m - j0 < CH_NB ? m - j0 : CH_NB;
+        const int rows = m + 1 - j0;
+        for (int r = ty; r < rows; r += 8)
+            if (tx < nb) P[r * CH_LD + tx] = (r >= tx || r >= nb) ? L[int64_t(j0 + r) * m + j0 + tx] : 0.0;
         __syncthreads();
-        const double yj = y[j];
-        for (int i = j + 1 + tid; i < m; i += 256) y[i] -= L[int64_t(i) * m + j] * yj;
+        // rhs_k = z_k - sum_{i >= j0 + nb} L[i][k] y_i : one warp per column k (stride 8), lanes over the rows
+        for (int k = ty; k < nb; k += 8) {
+            double part = 0.0;
+            for (int r = nb + tx; r < rows - 1; r += 32) part = fma(P[r * CH_LD + k], ys[j0 + r], part);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (tx == 0) P[(rows - 1) * CH_LD + k] -= part;           // z_k (row m of the panel) becomes the block's right-hand side
+        }
+        __syncthreads();
+        // the nb x nb triangle, backwards, by one warp
+        if (ty == 0) {
+            for (int jj = nb - 1; jj >= 0; --jj) {
+                const double piv = P[jj * CH_LD + jj];
+                const double yj = piv > 0.0 ? P[(rows - 1) * CH_LD + jj] / piv : 0.0;
+                __syncwarp();
+                if (tx == 0) ys[j0 + jj] = yj;
+                if (tx < jj) P[(rows - 1) * CH_LD + tx] -= P[jj * CH_LD + tx] * yj;
+                __syncwarp();
+            }
+        }
         __syncthreads();
     }
-    // back substitution L^T y = z
-    for (int j = m - 1; j >= 0; --j) {
-        if (tid == 0) { double p = L[int64_t(j) * m + j]; y[j] = p > 0.0 ? y[j] / p : 0.0; }
-        __syncthreads();
-        const double yj = y[j];
-        for (int i = tid; i < j; i += 256) y[i] -= L[int64_t(j) * m + i] * yj;
-        __syncthreads();
-    }
+    for (int i = tid; i < m; i += 256) y[i] = ys[i];
     // e = y^T Mt
     const float* M = Mt + int64_t(b) * m * k_q;
     for (int t = tid; t < k_q; t += 256) {
         double acc = 0.0;
-        for (int i = 0; i < m; ++i) acc = fma(y[i], double(M[int64_t(i) * k_q + t]), acc);
+        for (int i = 0; i < m; ++i) acc = fma(ys[i], double(M[int64_t(i) * k_q + t]), acc);
         e_out[int64_t(b) * k_q + t] = float(acc);
     }
 }
@@ -158,7 +246,7 @@ static AdaptivePlan adaptive_plan(int k_q, int m, int64_t n_items) {
     size_t off = 0;
     p.off_rt = off; off += align_up(sizeof(float) * size_t(n_items) * k_q, 256);
     p.off_mt = off; off += align_up(sizeof(float) * size_t(AD_QB) * m * k_q, 256);
-    p.off_g = off; off += align_up(sizeof(double) * size_t(AD_QB) * m * m, 256);
+    p.off_g = off; off += align_up(sizeof(double) * size_t(AD_QB) * (m + 1) * m, 256);
     p.off_y = off; off += align_up(sizeof(double) * size_t(AD_QB) * m, 256);
     p.off_e = off; off += align_up(sizeof(float) * size_t(AD_QB) * k_q, 256);
     p.off_s = off; off += align_up(sizeof(float) * size_t(AD_QB) * n_items, 256);
@@ -186,6 +274,9 @@ int adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, co
     float* e = reinterpret_cast<float*>(ws + pl.off_e);
     float* S = reinterpret_cast<float*>(ws + pl.off_s);
 
+    const size_t ch_smem = sizeof(double) * (size_t(m + 1) * CH_LD + size_t(m));
+    if (ch_smem > 200 * 1024) { set_error("adaptive_round: m = %d anchors need %zu bytes of shared memory per query", m, ch_smem); return ANNCUR_E_UNSUPPORTED; }
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(cholesky_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ch_smem)));
     dim3 tgrid(unsigned((n_items + 31) / 32), unsigned((k_q + 31) / 32));
     transpose_kernel<<<tgrid, dim3(32, 8), 0, stream>>>(R_anc, ldr, k_q, n_items, Rt);
     ANNCUR_LAUNCH_OK("transpose_kernel");
@@ -195,10 +286,10 @@ int adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, co
         const int64_t warps = int64_t(nq) * m;
         gather_anchor_rows_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, stream>>>(Rt, k_q, anc, m, nq, Mt);
         ANNCUR_LAUNCH_OK("gather_anchor_rows_kernel");
-        dim3 ggrid(unsigned((m + 31) / 32), unsigned((m + 31) / 32), unsigned(nq));
+        dim3 ggrid(unsigned((m + GR_T - 1) / GR_T), unsigned((m + GR_T - 1) / GR_T), unsigned(nq));
         gram_kernel<<<ggrid, 256, 0, stream>>>(Mt, m, k_q, G);
         ANNCUR_LAUNCH_OK("gram_kernel");
-        cholesky_solve_kernel<<<nq, 256, 0, stream>>>(G, c + int64_t(q0) * m, Mt, m, k_q, rcond, y, e);
+        cholesky_solve_kernel<<<nq, 256, ch_smem, stream>>>(G, c + int64_t(q0) * m, Mt, m, k_q, rcond, y, e);
         ANNCUR_LAUNCH_OK("cholesky_solve_kernel");
         int rc = sgemm_rowmajor(e, k_q, R_anc, ldr, S, n_items, nq, n_items, k_q, stream);
         if (rc != ANNCUR_OK) return rc;
