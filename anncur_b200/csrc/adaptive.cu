@@ -131,60 +131,95 @@ cholesky_solve_kernel(double* __restrict__ G, const float* __restrict__ c, const
     for (int j0 = 0; j0 < m; j0 += CH_NB) {
         const int nb = m - j0 < CH_NB ? m - j0 : CH_NB;
         const int rows = m + 1 - j0;                        // panel rows: matrix rows j0 .. m (row m = right-hand side)
-        // 1. panel -> shared memory
-        for (int r = ty; r < rows; r += 8)
-            if (tx < nb) P[r * CH_LD + tx] = (r >= tx || r >= nb) ? L[int64_t(j0 + r) * m + j0 + tx] : 0.0;
+        // 1. panel -> shared memory (8 independent loads per thread in flight)
+        for (int r0 = 0; r0 < rows; r0 += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + ty + 8 * u;
+                v[u] = (r < rows && tx < nb && (r >= tx || r >= nb)) ? __ldcg(L + int64_t(j0 + r) * m + j0 + tx) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + ty + 8 * u;
+                if (r < rows && tx < nb) P[r * CH_LD + tx] = v[u];
+            }
+        }
         __syncthreads();
-        // 2. factor the panel column by column (diagonal block and everything below it)
+        // 2a. the nb x nb diagonal block, column by column (two barriers per column; every thread derives the pivot itself)
         for (int jj = 0; jj < nb; ++jj) {
-            if (tid == 0) {
-                const double d = P[jj * CH_LD + jj];
-                s_piv = d > drop ? sqrt(d) : 0.0;
-                P[jj * CH_LD + jj] = s_piv;
-            }
+            const double d = P[jj * CH_LD + jj];
+            const double piv = d > drop ? sqrt(d) : 0.0;
+            const double inv = piv > 0.0 ? 1.0 / piv : 0.0;        // dropped pivot: the column becomes 0
+            __syncthreads();                                        // everyone has read d
+            if (tid == 0) P[jj * CH_LD + jj] = piv;
+            if (tid > jj && tid < nb) P[tid * CH_LD + jj] *= inv;
             __syncthreads();
-            const double piv = s_piv;
-            if (piv == 0.0) {
-                for (int r = jj + 1 + tid; r < rows; r += 256) P[r * CH_LD + jj] = 0.0;
-                __syncthreads();
-                continue;
-            }
-            const double inv = 1.0 / piv;
-            for (int r = jj + 1 + tid; r < rows; r += 256) P[r * CH_LD + jj] *= inv;
-            __syncthreads();
-            // P[r][t] -= P[r][jj] * P[t][jj] for jj < t < nb, r >= t
+            // P[r][t] -= P[r][jj] * P[t][jj] for jj < t <= r < nb
             const int t = jj + 1 + tx;
             if (t < nb) {
                 const double ptj = P[t * CH_LD + jj];
-                for (int r = t + ty; r < rows; r += 8) P[r * CH_LD + t] -= P[r * CH_LD + jj] * ptj;
+                for (int r = t + ty; r < nb; r += 8) P[r * CH_LD + t] -= P[r * CH_LD + jj] * ptj;
             }
-            __syncthreads();
         }
+        __syncthreads();
+        // 2b. the rows below it (incl. the right-hand side row): X L_d^T = P by forward substitution, one thread per row
+        for (int r = nb + tid; r < rows; r += 256) {
+            double* pr = P + r * CH_LD;
+            for (int jj = 0; jj < nb; ++jj) {
+                double acc = pr[jj];
+                for (int k = 0; k < jj; ++k) acc = fma(-pr[k], P[jj * CH_LD + k], acc);
+                const double piv = P[jj * CH_LD + jj];
+                pr[jj] = piv > 0.0 ? acc / piv : 0.0;
+            }
+        }
+        __syncthreads();
         // 3. panel back to global memory
         for (int r = ty; r < rows; r += 8)
-            if (tx < nb && (r >= tx || r >= nb)) L[int64_t(j0 + r) * m + j0 + tx] = P[r * CH_LD + tx];
-        // 4. trailing update: L[i][t] -= sum_k P[i][k] P[t][k] for j0 + nb <= t <= i <= m (t < m), 32 x 32 tiles
+            if (tx < nb && (r >= tx || r >= nb)) __stcg(L + int64_t(j0 + r) * m + j0 + tx, P[r * CH_LD + tx]);
+        // 4. trailing update: L[i][t] -= sum_k P[i][k] P[t][k] for j0 + nb <= t <= i <= m (t < m).  64 x 64 tiles, each thread a
+        //    4 x 4 block with rows / columns 16 apart (conflict-free panel reads at row stride 33): 8 LDS feed 16 DFMA per k.
         const int base = j0 + nb;
         const int n_tr = m + 1 - base;                      // trailing rows (incl. the right-hand side row)
         const int n_tc = m - base;                          // trailing columns
-        for (int ti = 0; ti < n_tr; ti += 32) {
-            for (int tt = 0; tt <= ti && tt < n_tc; tt += 32) {
-                const int tcol = tt + tx;                   // column (relative to base) of this thread
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                if (tcol < n_tc) {
-                    const double* pt = P + (nb + tcol) * CH_LD;
-                    for (int k = 0; k < nb; ++k) {
-                        const double v = pt[k];
+        const int sx = tid & 15, sy = tid >> 4;
+        for (int ti = 0; ti < n_tr; ti += 64) {
+            for (int tt = 0; tt <= ti && tt < n_tc; tt += 64) {
+                const double* pr[4];
+                const double* pc[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int ri = ti + ty + q * 8;
-                            if (ri < n_tr) acc[q] = fma(P[(nb + ri) * CH_LD + k], v, acc[q]);
-                        }
+                for (int q = 0; q < 4; ++q) {
+                    const int ri = ti + sy + 16 * q, ci = tt + sx + 16 * q;
+                    pr[q] = P + (nb + (ri < n_tr ? ri : 0)) * CH_LD;       // out-of-range rows / columns compute garbage that is never stored
+                    pc[q] = P + (nb + (ci < n_tc ? ci : 0)) * CH_LD;
+                }
+                // the 16 old values are fetched before the k loop (their latency hides behind it; as read-modify-writes in one
+                // statement each, the compiler has to serialise them: 16 L2 round trips per tile)
+                double acc[4][4], old[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int ri = ti + sy + 16 * r, ci = tt + sx + 16 * cc;
+                        acc[r][cc] = 0.0;
+                        old[r][cc] = (ri < n_tr && ci < n_tc && ci <= ri) ? __ldcg(L + int64_t(base + ri) * m + base + ci) : 0.0;
                     }
+                for (int k = 0; k < nb; ++k) {
+                    double a[4], bb[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int ri = ti + ty + q * 8;
-                        if (ri < n_tr && tcol <= ri) L[int64_t(base + ri) * m + base + tcol] -= acc[q];
+                    for (int q = 0; q < 4; ++q) { a[q] = pr[q][k]; bb[q] = pc[q][k]; }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fma(a[r], bb[cc], acc[r][cc]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int ri = ti + sy + 16 * r;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int ci = tt + sx + 16 * cc;
+                        if (ri < n_tr && ci < n_tc && ci <= ri) __stcg(L + int64_t(base + ri) * m + base + ci, old[r][cc] - acc[r][cc]);
                     }
                 }
             }
@@ -199,8 +234,19 @@ cholesky_solve_kernel(double* __restrict__ G, const float* __restrict__ c, const
         const int j0 = pi * CH_NB;
         const int nb = m - j0 < CH_NB ? m - j0 : CH_NB;
         const int rows = m + 1 - j0;
-        for (int r = ty; r < rows; r += 8)
-            if (tx < nb) P[r * CH_LD + tx] = (r >= tx || r >= nb) ? L[int64_t(j0 + r) * m + j0 + tx] : 0.0;
+        for (int r0 = 0; r0 < rows; r0 += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + ty + 8 * u;
+                v[u] = (r < rows && tx < nb && (r >= tx || r >= nb)) ? __ldcg(L + int64_t(j0 + r) * m + j0 + tx) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + ty + 8 * u;
+                if (r < rows && tx < nb) P[r * CH_LD + tx] = v[u];
+            }
+        }
         __syncthreads();
         // rhs_k = z_k - sum_{i >= j0 + nb} L[i][k] y_i : one warp per column k (stride 8), lanes over the rows
         for (int k = ty; k < nb; k += 8) {
