@@ -41,43 +41,49 @@ __global__ void gather_anchor_rows_kernel(const float* __restrict__ Rt, int k_q,
     for (int t = lane_id(); t < k_q; t += 32) dst[t] = src[t];
 }
 
-// G[b] = Mt[b] . Mt[b]^T  (m x m lower triangle, fp64 accumulate), 64 x 64 output tile per CTA, 4 x 4 per thread
-// (operands are converted to fp64 once, on their way into shared memory: the inner loop is 4 x LDS.128 + 16 DFMA).
+// G[b] = Mt[b] . Mt[b]^T  (m x m lower triangle, fp64), 64 x 64 output tile per CTA on the fp64 tensor cores
+// (mma.sync m8n8k4 f64: 256 FMAs per warp instruction; a warp owns a 32 x 16 block = 4 x 2 MMA tiles, so one 4-wide k step
+// is 6 shared-memory loads for 8 MMAs).  Operands are converted to fp64 once, on their way into shared memory; the row
+// stride of 20 doubles makes the fragment loads conflict-free per half warp.
 // G has row stride m and (m + 1) rows per query: row m is the right-hand side c of the solve (see below).
-constexpr int GR_T = 64, GR_K = 16;
+constexpr int GR_T = 64, GR_K = 16, GR_LD = GR_K + 4;
 __global__ void __launch_bounds__(256)
 gram_kernel(const float* __restrict__ Mt, int m, int k_q, double* __restrict__ G) {
-    __shared__ __align__(16) double As[GR_K][GR_T + 2], Bs[GR_K][GR_T + 2];
+    __shared__ __align__(16) double As[GR_T][GR_LD], Bs[GR_T][GR_LD];
     const int b = blockIdx.z;
     const int i0 = blockIdx.y * GR_T, j0 = blockIdx.x * GR_T;
     if (j0 > i0) return;                                   // lower triangle only
     const float* M = Mt + int64_t(b) * m * k_q;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, each a 4 x 4 block (rows ty*4.., cols tx*4..)
-    double acc[4][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16; // this warp's block inside the tile
+    const int fr = lane >> 2, fc = lane & 3;               // fragment row / k index (A), fragment column / k index (B)
+    double acc[4][2][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < 2; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
     for (int k0 = 0; k0 < k_q; k0 += GR_K) {
-        // 64 rows x 16 k of each operand: thread loads 4 elements of each (k fastest in global memory)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const int e = threadIdx.x + s * 256;           // 0 .. 1023
+            const int e = threadIdx.x + s * 256;           // 0 .. 1023: 64 rows x 16 k, k fastest (as in global memory)
             const int r = e >> 4, kk = e & 15;
-            As[kk][r] = (i0 + r < m && k0 + kk < k_q) ? double(M[int64_t(i0 + r) * k_q + k0 + kk]) : 0.0;
-            Bs[kk][r] = (j0 + r < m && k0 + kk < k_q) ? double(M[int64_t(j0 + r) * k_q + k0 + kk]) : 0.0;
+            As[r][kk] = (i0 + r < m && k0 + kk < k_q) ? double(M[int64_t(i0 + r) * k_q + k0 + kk]) : 0.0;
+            Bs[r][kk] = (j0 + r < m && k0 + kk < k_q) ? double(M[int64_t(j0 + r) * k_q + k0 + kk]) : 0.0;
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < GR_K; ++kk) {
-            const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]), a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]), b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-            const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int k4 = 0; k4 < GR_K; k4 += 4) {
+            double a[4], bb[2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = As[wr + r * 8 + fr][k4 + fc];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) bb[c] = Bs[wc + c * 8 + fr][k4 + fc];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], bb[c], acc[r][c]);
+                for (int c = 0; c < 2; ++c)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[r][c][0]), "+d"(acc[r][c][1]) : "d"(a[r]), "d"(bb[c]));
         }
         __syncthreads();
     }
@@ -85,10 +91,12 @@ gram_kernel(const float* __restrict__ Mt, int m, int k_q, double* __restrict__ G
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
-            if (i < m && j <= i) Gb[int64_t(i) * m + j] = acc[r][c];
-        }
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + wr + r * 8 + fr, j = j0 + wc + c * 8 + fc * 2 + h;
+                if (i < m && j <= i) Gb[int64_t(i) * m + j] = acc[r][c][h];
+            }
 }
 
 // One CTA per query: blocked right-looking Cholesky G = L L^T of the lower triangle (panels of 32 columns held in shared
