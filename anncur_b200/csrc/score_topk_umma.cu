@@ -760,7 +760,7 @@ pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int
 // num_kb + 1 are copies of that last k-block with the slot set to -1.05 ||q'|| 2^-5 and to 0 (see FusedParams::a_last_kb).
 template <int KIND>
 __global__ void __launch_bounds__(256)
-pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int k_dim, int num_kb,
+pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int plane_rows, int k_dim, int num_kb,
                     const float* __restrict__ e_scale, uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l,
                     float* __restrict__ row_inv_scale, uint32_t* __restrict__ thr_shared,
                     uint32_t* __restrict__ mtile_flags, const float* __restrict__ e_rowmax, float* __restrict__ row_delta) {
@@ -768,8 +768,16 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     constexpr bool X3 = KIND == ANNCUR_KIND_F32X3;
     constexpr bool R = KIND == ANNCUR_KIND_F32R;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_queries) return;
+    if (row >= plane_rows) return;
     const uint32_t lane = lane_id();
+    if (row >= n_queries) {                                // padding rows of the last query tile read as zero
+        const int n_blocks = num_kb + (R ? 2 : 0);
+        for (int kb = 0; kb < n_blocks; ++kb) {
+            plane_h[(int64_t(kb) * plane_rows + row) * 32 + lane] = 0;
+            if (!BF16) plane_l[(int64_t(kb) * plane_rows + row) * 32 + lane] = 0;
+        }
+        return;
+    }
     const float* q = Q + int64_t(row) * ldq;
     float scale = 1.f;
     float bound = 0.f, norm2 = 0.f;
@@ -792,7 +800,7 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
             if (u < num_kb) {
                 const int kidx = u * 32 + int(lane);
                 const float x = xr[u] * scale;
-                split_store<BF16>(x, plane_h, plane_l, (int64_t(u) * n_queries + row) * 32 + lane);
+                split_store<BF16>(x, plane_h, plane_l, (int64_t(u) * plane_rows + row) * 32 + lane);
                 if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
                 if (R) norm2 = fmaf(x, x, norm2);
             }
@@ -809,7 +817,7 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         for (int kb = 0; kb < num_kb; ++kb) {
             int kidx = kb * 32 + int(lane);
             float x = kidx < k_dim ? q[kidx] * scale : 0.f;
-            split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * n_queries + row) * 32 + lane);
+            split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * plane_rows + row) * 32 + lane);
             if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
             if (R) norm2 = fmaf(x, x, norm2);
         }
@@ -839,9 +847,9 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         const float x = kidx < k_dim ? q[kidx] * scale : 0.f;
         const uint16_t h = __half_as_ushort(__float2half_rn(x));
         const bool is_slot = int(lane) == l_s;
-        plane_h[(int64_t(kb_s) * n_queries + row) * 32 + lane] = is_slot ? slot_p : h;                       // +b: upper bounds
-        plane_h[(int64_t(num_kb) * n_queries + row) * 32 + lane] = is_slot ? uint16_t(slot_p | 0x8000u) : h; // -b: lower bounds
-        plane_h[(int64_t(num_kb + 1) * n_queries + row) * 32 + lane] = h;                                    //  0: plain scores
+        plane_h[(int64_t(kb_s) * plane_rows + row) * 32 + lane] = is_slot ? slot_p : h;                       // +b: upper bounds
+        plane_h[(int64_t(num_kb) * plane_rows + row) * 32 + lane] = is_slot ? uint16_t(slot_p | 0x8000u) : h; // -b: lower bounds
+        plane_h[(int64_t(num_kb + 1) * plane_rows + row) * 32 + lane] = h;                                    //  0: plain scores
     }
     if (lane == 0) {
         row_inv_scale[row] = 1.f / (scale * e_scale[0]);
@@ -1086,6 +1094,9 @@ static int planes_for(int kind) { return kind == ANNCUR_KIND_BF16 ? 1 : 2; }
 static size_t plane_bytes(int64_t rows, int num_kb) { return align_up(size_t(num_kb) * size_t(rows) * BLOCK_K * 2, 256); }
 // query planes: F32R keeps two more copies of the last k-block of the high plane (bound slot = -b and 0)
 static int q_plane_kb(int num_kb, int kind) { return num_kb + (kind == ANNCUR_KIND_F32R ? 2 : 0); }
+// Query planes are allocated with whole 128-row tiles (rows past n_queries zeroed): the TMA box of a query tile then never
+// leaves the tensor.  Measured at N = 1M: with the box hanging out of a 1-row tensor MAIN took 0.267 ms, at 64 rows 0.172 ms.
+static int q_plane_rows(int n_queries) { return (n_queries + BLOCK_M - 1) / BLOCK_M * BLOCK_M; }
 static int et_ld(int k_dim) { return (k_dim + 3) & ~3; }                 // row stride (floats) of the item-major fp32 copy
 static bool valid_kind(int kind) { return kind == ANNCUR_KIND_F32X3 || kind == ANNCUR_KIND_BF16 || kind == ANNCUR_KIND_F32R; }
 
@@ -1197,7 +1208,7 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     pl.cap = pow2_at_least(want);
     if (pl.cap > 2048u) pl.cap = 2048u;
     size_t off = 0;
-    pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(n_queries, q_plane_kb(pl.num_kb, kind));
+    pl.off_qplanes = off; off += size_t(planes_for(kind)) * plane_bytes(q_plane_rows(n_queries), q_plane_kb(pl.num_kb, kind));
     pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
@@ -1398,7 +1409,8 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     const bool sampled = pl.sample_stride != 0;
     char* ws = reinterpret_cast<char*>(workspace);
     const int q_kb = q_plane_kb(pl.num_kb, kind);
-    const size_t qpb = plane_bytes(n_queries, q_kb);
+    const int q_rows = q_plane_rows(n_queries);
+    const size_t qpb = plane_bytes(q_rows, q_kb);
     uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
     uint16_t* q_l = bf16 ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
     float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
@@ -1411,24 +1423,24 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     float* smax = reinterpret_cast<float*>(ws + pl.off_smax);
     int* err = reinterpret_cast<int*>(ws + pl.off_err);
 
-    const int qgrid = (n_queries + 7) / 8;
+    const int qgrid = (q_rows + 7) / 8;                    // the kernel also zeroes the padding rows of the last query tile
     const PackedLayout L = packed_layout(n_items, k_dim, kind);
     const char* items = reinterpret_cast<const char*>(packed_items);
     const float* e_rowmax = reinterpret_cast<const float*>(items + L.off_rowmax);
-    if (bf16) pack_queries_kernel<ANNCUR_KIND_BF16><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
-    else if (refine) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
-    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    if (bf16) pack_queries_kernel<ANNCUR_KIND_BF16><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, q_rows, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else if (refine) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, q_rows, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, q_rows, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
     ANNCUR_LAUNCH_OK("pack_queries_kernel");
 
     const int cg = cta_group_for(pl.m_tiles);
     const int b_box = BLOCK_N / cg;                       // a CTA of a pair stages half of each item tile
     CUtensorMap a0, a1, b0, b1;
     int rc;
-    if ((rc = make_plane_map(&a0, q_h, n_queries, q_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&a0, q_h, q_rows, q_kb, BLOCK_M, bf16)) != ANNCUR_OK) return rc;
     if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, b_box, bf16)) != ANNCUR_OK) return rc;
     if (bf16) { a1 = a0; b1 = b0; }
     else {
-        if ((rc = make_plane_map(&a1, q_l, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+        if ((rc = make_plane_map(&a1, q_l, q_rows, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
         if ((rc = make_plane_map(&b1, items + L.plane, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
     }
     // the full-precision launch: 3 passes (fp32-grade kinds) or the single bf16 pass
@@ -1515,7 +1527,7 @@ static DensePlan make_dense_plan(int n_queries, int64_t n_items, int k_dim, int 
     const int units = sm_count() / cg > 0 ? sm_count() / cg : 1;
     pl.n_chunks = choose_chunks((pl.m_tiles + cg - 1) / cg, pl.n_tiles > 0 ? pl.n_tiles : 1, units, 0.0);
     size_t off = 0;
-    pl.off_qplanes = off; off += 2 * plane_bytes(n_queries, q_plane_kb(pl.num_kb, kind));
+    pl.off_qplanes = off; off += 2 * plane_bytes(q_plane_rows(n_queries), q_plane_kb(pl.num_kb, kind));
     pl.off_inv_scale = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_delta = off; off += align_up(sizeof(float) * size_t(n_queries), 256);
     pl.off_thr = off; off += align_up(sizeof(uint32_t) * size_t(n_queries), 256);
@@ -1546,7 +1558,8 @@ static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_que
     }
     char* ws = reinterpret_cast<char*>(workspace);
     const int q_kb = q_plane_kb(pl.num_kb, kind);
-    const size_t qpb = plane_bytes(n_queries, q_kb);
+    const int q_rows = q_plane_rows(n_queries);
+    const size_t qpb = plane_bytes(q_rows, q_kb);
     uint16_t* q_h = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes);
     uint16_t* q_l = reinterpret_cast<uint16_t*>(ws + pl.off_qplanes + qpb);
     float* inv_scale = reinterpret_cast<float*>(ws + pl.off_inv_scale);
@@ -1557,9 +1570,9 @@ static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_que
     const PackedLayout L = packed_layout(n_items, k_dim, kind);
     const char* items = reinterpret_cast<const char*>(packed_items);
     const float* e_rowmax = reinterpret_cast<const float*>(items + L.off_rowmax);
-    const int qgrid = (n_queries + 7) / 8;
-    if (kind == ANNCUR_KIND_F32R) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
-    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    const int qgrid = (q_rows + 7) / 8;                    // the kernel also zeroes the padding rows of the last query tile
+    if (kind == ANNCUR_KIND_F32R) pack_queries_kernel<ANNCUR_KIND_F32R><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, q_rows, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
+    else pack_queries_kernel<ANNCUR_KIND_F32X3><<<qgrid, 256, 0, stream>>>(Q, ldq, n_queries, q_rows, k_dim, pl.num_kb, e_scale, q_h, q_l, inv_scale, thr, flags, e_rowmax, delta);
     ANNCUR_LAUNCH_OK("pack_queries_kernel");
     if (epi == EPI_ERR) {
         ANNCUR_CUDA_OK(cudaMemsetAsync(err2, 0, sizeof(double) * size_t(n_queries), stream));
@@ -1569,8 +1582,8 @@ static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_que
     const int b_box = BLOCK_N / cg;
     CUtensorMap a0, a1, b0, b1;
     int rc;
-    if ((rc = make_plane_map(&a0, q_h, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
-    if ((rc = make_plane_map(&a1, q_l, n_queries, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&a0, q_h, q_rows, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
+    if ((rc = make_plane_map(&a1, q_l, q_rows, q_kb, BLOCK_M, false)) != ANNCUR_OK) return rc;
     if ((rc = make_plane_map(&b0, items, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
     if ((rc = make_plane_map(&b1, items + L.plane, n_items, pl.num_kb, b_box, false)) != ANNCUR_OK) return rc;
     FusedParams fp{};
