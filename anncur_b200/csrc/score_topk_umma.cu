@@ -1094,9 +1094,10 @@ static int planes_for(int kind) { return kind == ANNCUR_KIND_BF16 ? 1 : 2; }
 static size_t plane_bytes(int64_t rows, int num_kb) { return align_up(size_t(num_kb) * size_t(rows) * BLOCK_K * 2, 256); }
 // query planes: F32R keeps two more copies of the last k-block of the high plane (bound slot = -b and 0)
 static int q_plane_kb(int num_kb, int kind) { return num_kb + (kind == ANNCUR_KIND_F32R ? 2 : 0); }
-// Query planes are allocated with whole 128-row tiles (rows past n_queries zeroed): the TMA box of a query tile then never
+// Query planes are allocated in whole 256-row units (rows past n_queries zeroed): the TMA box of a query tile then never
 // leaves the tensor.  Measured at N = 1M: with the box hanging out of a 1-row tensor MAIN took 0.267 ms, at 64 rows 0.172 ms.
-static int q_plane_rows(int n_queries) { return (n_queries + BLOCK_M - 1) / BLOCK_M * BLOCK_M; }
+// (256 = the two query tiles of a CTA pair: the second CTA of the last pair may own a tile past the batch)
+static int q_plane_rows(int n_queries) { return (n_queries + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2 * BLOCK_M); }
 static int et_ld(int k_dim) { return (k_dim + 3) & ~3; }                 // row stride (floats) of the item-major fp32 copy
 static bool valid_kind(int kind) { return kind == ANNCUR_KIND_F32X3 || kind == ANNCUR_KIND_BF16 || kind == ANNCUR_KIND_F32R; }
 
