@@ -153,4 +153,4 @@ def cpu_adaptive():
 
 emit("A8", f"adaptive round: {Bq} queries x (pinv of {k_q}x{m} + re-score over {N} + top-125)  [not in the reference]", t,
      cpu_s(cpu_adaptive, reps=1) * (Bq / 4), "4 of 256 queries, numpy pinv per query (oracle restatement of SURVEY 8a-A8)",
-     bound="fp64 Gram + Cholesky per query (latency / fp64 pipe)")
+     bound="fp64 Gram on the fp64 tensor cores + blocked fp64 Cholesky per query")
