@@ -246,7 +246,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "queries/sec (ANNCUR score+top-100)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world, "cpu"),
+        # same config object as the GPU arm prints for these flags (the arm itself runs on the host threads of rank 0)
+        "config": workload_config(args, world, args.shard or ("items" if args.workload == "c4" else "queries")),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
