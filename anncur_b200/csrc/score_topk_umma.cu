@@ -22,8 +22,8 @@
 //           3-pass kind on the same planes.
 //
 // Layout in HBM (built once per index by pack_items, per batch for Q by pack_queries):
-//   plane[kb][row][32]  16-bit elements, kb = k / 32; a TMA box {32, rows, 1} is one contiguous
-//   rows*64-byte span and lands in shared memory in the canonical K-major SWIZZLE_64B layout.
+//   plane[kb][row][64]  16-bit elements, kb = k / 64; a TMA box {64, rows, 1} is one contiguous
+//   rows*128-byte span and lands in shared memory in the canonical K-major SWIZZLE_128B layout.
 //
 // Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
 //   warp 0      TMA producer  (ring of 6 stages x 1 k-block, fp32-grade; 3 stages x 4 k-blocks, one-pass kinds)
@@ -68,10 +68,16 @@ namespace anncur {
 // ------------------------------------------------------------------------------------------------
 constexpr int BLOCK_M = 128;           // queries per tile (TMEM lanes)
 constexpr int BLOCK_N = 256;           // items per tile (TMEM columns per accumulator buffer)
-constexpr int BLOCK_K = 32;            // 16-bit elements per k-block = 64 bytes = one SWIZZLE_64B row
+constexpr int BLOCK_K = 64;            // 16-bit elements per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int K32_PER_KB = BLOCK_K / 32;   // the packing kernels work in 32-wide chunks (one element per lane)
 constexpr int UMMA_K = 16;
-constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 8 KB
-constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB
+constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+
+// element (anchor index kidx, row) of a plane[kb][row][BLOCK_K] with `rows` rows per k-block
+__host__ __device__ __forceinline__ int64_t plane_off(int kidx, int64_t row, int64_t rows) {
+    return (int64_t(kidx / BLOCK_K) * rows + row) * BLOCK_K + kidx % BLOCK_K;
+}
 constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, each takes half of a tile's columns
 constexpr int EPI_HALVES = NUM_EPI_WARPS / 4;
 constexpr int FUSED_THREADS = 32 * (2 + NUM_EPI_WARPS);
@@ -87,9 +93,9 @@ template <int PASSES, int CG> struct StageCfg {
     // barrier wait + commit per stage then costs as much as the tensor work it feeds (measured: tensor pipe 69 % busy).
     // Four k-blocks per stage (8 MMAs per wait) took bf16 MAIN from 0.357 to 0.277 ms at C2; six per stage with two
     // stages is slower again (3.29 vs 2.81 ms at N = 1M), and the fp32-grade kind (6 MMAs per k-block) gains nothing.
-    static constexpr int kKbPerStage = PASSES == 3 ? 1 : 4;
+    static constexpr int kKbPerStage = PASSES == 3 ? 1 : 2;      // (in 64-wide k-blocks: 12 / 8 MMAs per stage)
     static constexpr int kStageBytes = kKbPerStage * kSubBytes;
-    static constexpr int kStages = PASSES == 3 ? (CG == 2 ? 6 : 4) : (CG == 2 ? 3 : 2);
+    static constexpr int kStages = CG == 2 ? 3 : 2;
 };
 
 enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
@@ -203,14 +209,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major, SWIZZLE_64B canonical layout: rows of 64 bytes, 8-row groups 512 bytes apart.
+// K-major, SWIZZLE_128B canonical layout: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
     uint64_t d = 0;
     d |= uint64_t((saddr >> 4) & 0x3fffu);        // start address
     d |= uint64_t(1) << 16;                       // leading byte offset (unused for swizzled K-major)
-    d |= uint64_t(512 >> 4) << 32;                // stride byte offset: 8 rows x 64 B
+    d |= uint64_t(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
     d |= uint64_t(1) << 46;                       // descriptor version (sm_100)
-    d |= uint64_t(4) << 61;                       // layout type SWIZZLE_64B
+    d |= uint64_t(2) << 61;                       // layout type SWIZZLE_128B
     return d;
 }
 // tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane: issue only (asynchronous) ...
@@ -739,7 +745,7 @@ pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int
                   uint16_t* __restrict__ plane_h, uint16_t* __restrict__ plane_l) {
     __shared__ float tile[32][65];
     const float scale = scale_p[0];
-    const int kb = blockIdx.y;
+    const int kb = blockIdx.y;                              // 32-wide chunk of anchors
     const int64_t n0 = int64_t(blockIdx.x) * 64;
     for (int e = threadIdx.x; e < 32 * 64; e += 256) {
         int kk = e / 64, j = e % 64;
@@ -751,7 +757,7 @@ pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int
     for (int e = threadIdx.x; e < 64 * 32; e += 256) {
         int j = e / 32, kk = e % 32;
         int64_t n = n0 + j;
-        if (n < n_items) split_store<BF16>(tile[kk][j], plane_h, plane_l, (int64_t(kb) * n_items + n) * 32 + kk);
+        if (n < n_items) split_store<BF16>(tile[kk][j], plane_h, plane_l, plane_off(kb * 32 + kk, n, n_items));
     }
 }
 
@@ -771,10 +777,10 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     if (row >= plane_rows) return;
     const uint32_t lane = lane_id();
     if (row >= n_queries) {                                // padding rows of the last query tile read as zero
-        const int n_blocks = num_kb + (R ? 2 : 0);
-        for (int kb = 0; kb < n_blocks; ++kb) {
-            plane_h[(int64_t(kb) * plane_rows + row) * 32 + lane] = 0;
-            if (!BF16) plane_l[(int64_t(kb) * plane_rows + row) * 32 + lane] = 0;
+        const int n_chunks = (num_kb + (R ? 2 : 0)) * K32_PER_KB;
+        for (int u = 0; u < n_chunks; ++u) {
+            plane_h[plane_off(u * 32 + int(lane), row, plane_rows)] = 0;
+            if (!BF16) plane_l[plane_off(u * 32 + int(lane), row, plane_rows)] = 0;
         }
         return;
     }
@@ -782,12 +788,13 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
     float scale = 1.f;
     float bound = 0.f, norm2 = 0.f;
     constexpr int RC = 16;                       // rows of up to 512 anchors are read once and kept in registers
-    if (num_kb <= RC) {
+    const int n32 = num_kb * K32_PER_KB;         // 32-wide chunks (one element per lane)
+    if (n32 <= RC) {
         float xr[RC];
 #pragma unroll
         for (int u = 0; u < RC; ++u) {
             const int kidx = u * 32 + int(lane);
-            xr[u] = (u < num_kb && kidx < k_dim) ? q[kidx] : 0.f;
+            xr[u] = (u < n32 && kidx < k_dim) ? q[kidx] : 0.f;
         }
         if (!BF16) {
             float m = 0.f;
@@ -797,10 +804,10 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         }
 #pragma unroll
         for (int u = 0; u < RC; ++u) {
-            if (u < num_kb) {
+            if (u < n32) {
                 const int kidx = u * 32 + int(lane);
                 const float x = xr[u] * scale;
-                split_store<BF16>(x, plane_h, plane_l, (int64_t(u) * plane_rows + row) * 32 + lane);
+                split_store<BF16>(x, plane_h, plane_l, plane_off(kidx, row, plane_rows));
                 if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
                 if (R) norm2 = fmaf(x, x, norm2);
             }
@@ -814,10 +821,10 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
             }
             scale = pow2_scale_for(warp_max_f(m));
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < n32; ++kb) {
             int kidx = kb * 32 + int(lane);
             float x = kidx < k_dim ? q[kidx] * scale : 0.f;
-            split_store<BF16>(x, plane_h, plane_l, (int64_t(kb) * plane_rows + row) * 32 + lane);
+            split_store<BF16>(x, plane_h, plane_l, plane_off(kidx, row, plane_rows));
             if (X3 && kidx < k_dim) { const float t = x * e_rowmax[kidx]; bound = fmaf(t, t, bound); }
             if (R) norm2 = fmaf(x, x, norm2);
         }
@@ -842,14 +849,17 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         norm2 = warp_sum(norm2);
         const float slot = sqrtf(norm2 + float(k_dim) * 0x1p-28f) * (1.05f * 1.001f * 0x1p-5f);
         const uint16_t slot_p = __half_as_ushort(__float2half_ru(slot));
-        const int kb_s = num_kb - 1, l_s = k_dim & 31;                       // the slot lives at anchor index k_dim
-        const int kidx = kb_s * 32 + int(lane);
-        const float x = kidx < k_dim ? q[kidx] * scale : 0.f;
-        const uint16_t h = __half_as_ushort(__float2half_rn(x));
-        const bool is_slot = int(lane) == l_s;
-        plane_h[(int64_t(kb_s) * plane_rows + row) * 32 + lane] = is_slot ? slot_p : h;                       // +b: upper bounds
-        plane_h[(int64_t(num_kb) * plane_rows + row) * 32 + lane] = is_slot ? uint16_t(slot_p | 0x8000u) : h; // -b: lower bounds
-        plane_h[(int64_t(num_kb + 1) * plane_rows + row) * 32 + lane] = h;                                    //  0: plain scores
+        const int kb_s = num_kb - 1;                                         // the slot lives at anchor index k_dim, in the last k-block
+#pragma unroll
+        for (int u = 0; u < K32_PER_KB; ++u) {
+            const int kidx = kb_s * BLOCK_K + u * 32 + int(lane);
+            const float x = kidx < k_dim ? q[kidx] * scale : 0.f;
+            const uint16_t h = __half_as_ushort(__float2half_rn(x));
+            const bool is_slot = kidx == k_dim;
+            plane_h[plane_off(kidx, row, plane_rows)] = is_slot ? slot_p : h;                                  // +b: upper bounds
+            plane_h[plane_off(kidx + BLOCK_K, row, plane_rows)] = is_slot ? uint16_t(slot_p | 0x8000u) : h;    // -b: lower bounds
+            plane_h[plane_off(kidx + 2 * BLOCK_K, row, plane_rows)] = h;                                       //  0: plain scores
+        }
     }
     if (lane == 0) {
         row_inv_scale[row] = 1.f / (scale * e_scale[0]);
@@ -868,7 +878,7 @@ item_bound_slot_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items
         float s = 0.f;
         for (int i = 0; i < k_dim; ++i) { const float x = E[int64_t(i) * lde + n] * scale; s = fmaf(x, x, s); }
         const float ne = sqrtf(s + float(k_dim) * 0x1p-28f) * (1.001f * 0x1p-5f);
-        plane_h[(int64_t(k_dim >> 5) * n_items + n) * 32 + (k_dim & 31)] = __half_as_ushort(__float2half_ru(ne));
+        plane_h[plane_off(k_dim, n, n_items)] = __half_as_ushort(__float2half_ru(ne));
     }
 }
 
@@ -1083,7 +1093,7 @@ static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int 
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld kb=%d)", int(r), (long long)rows, num_kb); return ANNCUR_E_CUDA; }
     return ANNCUR_OK;
 }
@@ -1255,7 +1265,7 @@ int pack_items(const float* E, int64_t lde, int64_t n_items, int k_dim, int kind
     float* rowmax = reinterpret_cast<float*>(base + L.off_rowmax);
     row_absmax_kernel<<<L.num_kb * BLOCK_K, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, rowmax);
     ANNCUR_LAUNCH_OK("row_absmax_kernel");
-    dim3 grid(unsigned((n_items + 63) / 64), unsigned(L.num_kb));
+    dim3 grid(unsigned((n_items + 63) / 64), unsigned(L.num_kb * K32_PER_KB));
     if (bf16) pack_items_kernel<true><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
     else pack_items_kernel<false><<<grid, 256, 0, stream>>>(E, lde, n_items, k_dim, e_scale_out, plane_h, plane_l);
     ANNCUR_LAUNCH_OK("pack_items_kernel");
