@@ -423,7 +423,7 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of the MAIN kernel, one `ncu --set full` capture per (workload, kind)
     # (profiles/r1_ncu_fused_c2_f32x3_v8_details.txt); null where no capture was taken
-    # and profiles/r1_ncu_fused_c2_f32r_v13_details.txt
+    # and profiles/r1_ncu_fused_c2_f32r_v16_details.txt
     NCU_TRAFFIC = {("c2", "f32x3"): 238.13e6 + 16.71e6, ("c2", "f32r"): 110.78e6 + 12.60e6}
     roofline = {
         "kernel": "fused_score_topk_kernel (tcgen05 score GEMM + streaming top-k)",
