@@ -25,8 +25,8 @@
 //   plane[kb][row][64]  16-bit elements, kb = k / 64; a TMA box {64, rows, 1} is one contiguous
 //   rows*128-byte span and lands in shared memory in the canonical K-major SWIZZLE_128B layout.
 //
-// Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
-//   warp 0      TMA producer  (ring of 6 stages x 1 k-block, fp32-grade; 3 stages x 4 k-blocks, one-pass kinds)
+// Kernel: persistent, one CTA pair per SM pair (cta_group::2; single CTAs for one query tile), 320 threads, warp-specialised
+//   warp 0      TMA producer  (ring of 3 stages x 1 k-block of 64, 3-pass kind; 3 stages x 2 k-blocks, one-pass kinds)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator 128 x 256 fp32,
 //               double-buffered in the 512 TMEM columns
 //   warps 2-9   epilogue: thread = one query row x one half of the tile's columns (two warps per TMEM
@@ -36,7 +36,8 @@
 //               push the rare survivors as 64-bit keys to the row's candidate list (L2-resident);
 //               if a list fills up the warp radix-selects it back to k entries and tightens the
 //               threshold (streaming fallback -- stays correct for adversarial inputs).
-// Work item = (chunk of item tiles, 128-query tile), ordered chunk-major so that co-resident CTAs
+// The same pipeline also serves the dense products (EPI_DENSE: store the scores; EPI_ERR: squared reconstruction error).
+// Work item = (chunk of item tiles, 128-query tile or pair of them), ordered chunk-major so that co-resident CTAs
 // stream the same slice of E and it is read from HBM once.
 //
 // Thresholds.  Pushing is only cheap when the threshold is tight from the first tile on, so a call
@@ -210,7 +211,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, SWIZZLE_128B canonical layout: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= uint64_t((saddr >> 4) & 0x3fffu);        // start address
     d |= uint64_t(1) << 16;                       // leading byte offset (unused for swizzled K-major)
@@ -453,16 +454,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                                 const uint32_t koff = uint32_t(ks) * UMMA_K * 2;          // bytes inside the 64 B row
                                 const uint32_t accum = (kb0 | u | ks) != 0 ? 1u : 0u;
                                 if (PASSES == 3) {
-                                    const uint64_t a_h = make_smem_desc_sw64(sb + koff);
-                                    const uint64_t a_l = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
-                                    const uint64_t b_h = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + koff);
-                                    const uint64_t b_l = make_smem_desc_sw64(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
+                                    const uint64_t a_h = make_smem_desc_sw128(sb + koff);
+                                    const uint64_t a_l = make_smem_desc_sw128(sb + A_PLANE_BYTES + koff);
+                                    const uint64_t b_h = make_smem_desc_sw128(sb + 2 * A_PLANE_BYTES + koff);
+                                    const uint64_t b_l = make_smem_desc_sw128(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
                                     mma(d_tmem, a_h, b_h, accum);
                                     mma(d_tmem, a_h, b_l, 1u);
                                     mma(d_tmem, a_l, b_h, 1u);
                                 } else {
-                                    const uint64_t a = make_smem_desc_sw64(sb + koff);
-                                    const uint64_t b = make_smem_desc_sw64(sb + A_PLANE_BYTES + koff);
+                                    const uint64_t a = make_smem_desc_sw128(sb + koff);
+                                    const uint64_t b = make_smem_desc_sw128(sb + A_PLANE_BYTES + koff);
                                     mma(d_tmem, a, b, accum);
                                 }
                             }
