@@ -94,9 +94,11 @@ template <int PASSES, int CG> struct StageCfg {
     // barrier wait + commit per stage then costs as much as the tensor work it feeds (measured: tensor pipe 69 % busy).
     // Four k-blocks per stage (8 MMAs per wait) took bf16 MAIN from 0.357 to 0.277 ms at C2; six per stage with two
     // stages is slower again (3.29 vs 2.81 ms at N = 1M), and the fp32-grade kind (6 MMAs per k-block) gains nothing.
-    static constexpr int kKbPerStage = PASSES == 3 ? 1 : 2;      // (in 64-wide k-blocks: 12 / 8 MMAs per stage)
+    // With 64-wide k-blocks: pairs 2 k-blocks x 3 stages (1 x 6: 0.295 ms, 3 x 2: 0.292 ms against 0.265 ms at C2); single CTAs
+    // (one query tile, HBM-bound) 1 x 4 (0.159 against 0.163 ms at N = 1M, B = 64).
+    static constexpr int kKbPerStage = PASSES == 3 ? 1 : (CG == 2 ? 2 : 1);
     static constexpr int kStageBytes = kKbPerStage * kSubBytes;
-    static constexpr int kStages = CG == 2 ? 3 : 2;
+    static constexpr int kStages = PASSES == 3 ? (CG == 2 ? 3 : 2) : (CG == 2 ? 3 : 4);
 };
 
 enum : int { MODE_MAIN = 0, MODE_SAMPLE = 1 };
@@ -198,6 +200,13 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (the same one every time): the surrounding code stays warp-uniform, so the operands of the
+// instruction it guards live in uniform registers
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -219,6 +228,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     d |= uint64_t(1) << 46;                       // descriptor version (sm_100)
     d |= uint64_t(2) << 61;                       // layout type SWIZZLE_128B
     return d;
+}
+// The same descriptor split into its address word and its constant word: inside a pipeline stage the operands differ only by
+// multiples of 16 bytes, so the issuer derives each descriptor from the stage's address word with ONE add (the sum stays
+// inside the 14-bit field: shared-memory offsets are below 256 KB).
+constexpr uint32_t SMEM_DESC_HI = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc_at(uint32_t lo, uint32_t byte_offset) {
+    return (uint64_t(SMEM_DESC_HI) << 32) | uint64_t(lo + (byte_offset >> 4));
 }
 // tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane: issue only (asynchronous) ...
 __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -424,14 +441,20 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0 && leader) {
+        // The whole warp of the leader CTA walks the loops (warp-uniform control flow and addresses: descriptors are
+        // built with uniform-datapath instructions); one elected lane issues each tcgen05.mma / commit.  With the loops
+        // inside `if (lane == 0)` every MMA cost ~21 instructions of descriptor arithmetic and register -> uniform-register
+        // moves in a divergent branch, and the single issuing thread was what the tensor pipe waited for.
+        if (leader) {
             // instruction descriptor: D fp32, A/B f16 or bf16, both K-major, N = 256, M = 128 per CTA
             const uint32_t fmt = BF16 ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((BLOCK_M * CG) >> 4) << 24);
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-                if (CG == 2) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+                if (elect_one_sync()) { if (CG == 2) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc); }
             };
-            auto commit = [&](uint32_t bar) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); };
+            auto commit = [&](uint32_t bar) {
+                if (elect_one_sync()) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); }
+            };
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t acc_phase = 0;
             for (int w = unit; w < total_items; w += n_units) {
@@ -447,24 +470,25 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                         const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
                         mbar_wait(full_bar(stage), phase, p.error_flag);
                         tcgen05_fence_after();
-                        for (int u = 0; u < n_sub; ++u) {
-                            const uint32_t sb = smem_base + uint32_t(stage) * Cfg::kStageBytes + uint32_t(u) * Cfg::kSubBytes;
+                        const uint32_t lo0 = smem_desc_lo(smem_base + uint32_t(stage) * Cfg::kStageBytes);
 #pragma unroll
-                            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-                                const uint32_t koff = uint32_t(ks) * UMMA_K * 2;          // bytes inside the 64 B row
-                                const uint32_t accum = (kb0 | u | ks) != 0 ? 1u : 0u;
-                                if (PASSES == 3) {
-                                    const uint64_t a_h = make_smem_desc_sw128(sb + koff);
-                                    const uint64_t a_l = make_smem_desc_sw128(sb + A_PLANE_BYTES + koff);
-                                    const uint64_t b_h = make_smem_desc_sw128(sb + 2 * A_PLANE_BYTES + koff);
-                                    const uint64_t b_l = make_smem_desc_sw128(sb + 2 * A_PLANE_BYTES + Cfg::kBBytes + koff);
-                                    mma(d_tmem, a_h, b_h, accum);
-                                    mma(d_tmem, a_h, b_l, 1u);
-                                    mma(d_tmem, a_l, b_h, 1u);
-                                } else {
-                                    const uint64_t a = make_smem_desc_sw128(sb + koff);
-                                    const uint64_t b = make_smem_desc_sw128(sb + A_PLANE_BYTES + koff);
-                                    mma(d_tmem, a, b, accum);
+                        for (int u = 0; u < Cfg::kKbPerStage; ++u) {
+                            if (u < n_sub) {
+#pragma unroll
+                                for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                                    const uint32_t off = uint32_t(u) * Cfg::kSubBytes + uint32_t(ks) * UMMA_K * 2;   // sub-block + bytes inside the 128 B row
+                                    const uint32_t accum = (kb0 | u | ks) != 0 ? 1u : 0u;
+                                    if (PASSES == 3) {
+                                        const uint64_t a_h = smem_desc_at(lo0, off);
+                                        const uint64_t a_l = smem_desc_at(lo0, off + A_PLANE_BYTES);
+                                        const uint64_t b_h = smem_desc_at(lo0, off + 2 * A_PLANE_BYTES);
+                                        const uint64_t b_l = smem_desc_at(lo0, off + 2 * A_PLANE_BYTES + Cfg::kBBytes);
+                                        mma(d_tmem, a_h, b_h, accum);
+                                        mma(d_tmem, a_h, b_l, 1u);
+                                        mma(d_tmem, a_l, b_h, 1u);
+                                    } else {
+                                        mma(d_tmem, smem_desc_at(lo0, off), smem_desc_at(lo0, off + A_PLANE_BYTES), accum);
+                                    }
                                 }
                             }
                         }
