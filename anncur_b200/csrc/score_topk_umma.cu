@@ -200,13 +200,6 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// one lane of a converged warp (the same one every time): the surrounding code stays warp-uniform, so the operands of the
-// instruction it guards live in uniform registers
-__device__ __forceinline__ bool elect_one_sync() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -441,19 +434,18 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        // The whole warp of the leader CTA walks the loops (warp-uniform control flow and addresses: descriptors are
-        // built with uniform-datapath instructions); one elected lane issues each tcgen05.mma / commit.  With the loops
-        // inside `if (lane == 0)` every MMA cost ~21 instructions of descriptor arithmetic and register -> uniform-register
-        // moves in a divergent branch, and the single issuing thread was what the tensor pipe waited for.
-        if (leader) {
+        // One thread of the leader CTA.  (A warp-uniform variant -- all 32 lanes walk the loops, an elected lane issues, as
+        // CUTLASS does -- was measured: 14 instead of 21 instructions per MMA and the same kernel time, so the issuing thread
+        // is not what the tensor pipe waits for at 8 MMAs per barrier; the simpler form stayed.)
+        if (lane == 0 && leader) {
             // instruction descriptor: D fp32, A/B f16 or bf16, both K-major, N = 256, M = 128 per CTA
             const uint32_t fmt = BF16 ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((BLOCK_M * CG) >> 4) << 24);
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-                if (elect_one_sync()) { if (CG == 2) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc); }
+                if (CG == 2) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
             };
             auto commit = [&](uint32_t bar) {
-                if (elect_one_sync()) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); }
+                if (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
             };
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t acc_phase = 0;
