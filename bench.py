@@ -364,7 +364,7 @@ def main():
     # Rotating streams, each with its own workspace and pinned result buffers, so that the H2D copy of one batch and the
     # D2H copy of another overlap the kernels of a third (the calls are asynchronous; every step still moves its
     # own query batch in and its own result out inside the timed region).
-    N_SLOTS = 2          # measured (tools/e2e_probe.py): 2 rotating streams 0.506 ms/step at C2, 3 streams 0.525, 1 stream 0.785
+    N_SLOTS = 3          # measured with the current kernels (tools/e2e_probe.py, 200 steps at C2): 1 stream 0.712 ms/step, 2: 0.525, 3: 0.478, 4: 0.492
     Qh = [b.cpu().pin_memory() for b in batches]
     vh = [torch.empty((B, k), dtype=torch.float32).pin_memory() for _ in range(N_SLOTS)]
     ih = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(N_SLOTS)]
@@ -399,6 +399,20 @@ def main():
     e2e_qps = B * e2e_steps * (world if shard == "queries" else 1) / t_e2e
     h2d = B * k_i * 4
     d2h = B * k * (4 + 8)
+    # what the box's host link gives a pinned copy of one step's input / output on its own (CUDA events, best of 5): the e2e
+    # figure cannot exceed B / (h2d / h2d_gbs) when the copy engine is the slowest stage of the pipeline
+    def copy_gbs(dst, src):
+        best = 0.0
+        for _ in range(5):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            dst.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            best = max(best, src.numel() * src.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        return best
+    h2d_gbs = copy_gbs(q_stage[0], Qh[0])
+    d2h_gbs = copy_gbs(ih[0], out_i)
 
     # the host-buffer path must give what the device-resident path gives
     chk_v, chk_i = engine.score_topk(batches[(e2e_steps - 1) % N_BATCHES], packed, k, idx_offset=lo) if index is None \
@@ -453,7 +467,8 @@ def main():
         "data": "synthetic", "config": workload_config(args, world, shard),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "anncur_search_host (C ABI, pinned host buffers)" if index is None else "ShardedIndex.search + pinned copies",
-                "passes_s": e2e_times},
+                "passes_s": e2e_times, "h2d_gbs_alone": h2d_gbs, "d2h_gbs_alone": d2h_gbs,
+                "copy_bound_queries_per_s": B / max(h2d / (h2d_gbs * 1e9), d2h / (d2h_gbs * 1e9)) * (world if shard == "queries" else 1)},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
         "index_build_s": {"pinv": wl["build_s"]["pinv"], "U@R": wl["build_s"]["gemm"], "pack": t_pack},
     }
