@@ -169,6 +169,28 @@ def test_adaptive_round_matches_oracle_restatement(eng):
         assert np.allclose(val[q].cpu().numpy(), s[got], atol=10 * tau)
 
 
+def test_adaptive_multi_round_matches_oracle_restatement(eng):
+    """The whole multi-round procedure (anncur_b200.adaptive_anncur: T - 1 K8 calls, exact-score gathers, K9 at the end)
+    against oracle.cur_oracle.adaptive_anncur.  Picks of a round may differ from the oracle's only among near-ties of the
+    approximate scores, so the comparison is on what the procedure is for: the final exact scores and the overlap of the
+    anchor sets."""
+    from anncur_b200 import adaptive_anncur
+    rng = np.random.default_rng(5)
+    k_q, N, B, T, kpr, top_k = 60, 3000, 24, 4, 12, 10
+    A = O.synthetic_scores(k_q + B, N, rank=10, noise=0.05, seed=7)
+    R, X = A[:k_q], A[k_q:]
+    first = np.sort(rng.choice(N, kpr, replace=False))
+    want_anc, want_idx, want_val, _ = O.adaptive_anncur(R, X, first, T, kpr, top_k, rcond=1e-15)
+    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k)
+    anc, idx, val = anc.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
+    assert anc.shape == (B, T * kpr) and (anc[:, :kpr] == first[None, :]).all()
+    assert all(len(set(r.tolist())) == T * kpr for r in anc)                 # anchors are never re-picked
+    overlap = np.mean([len(set(anc[q].tolist()) & set(want_anc[q].tolist())) / (T * kpr) for q in range(B)])
+    assert overlap > 0.97, overlap
+    assert (val == np.take_along_axis(X, idx, 1)).all()                      # returned values are the exact scores of the returned items
+    assert np.allclose(val, want_val, atol=2e-3 * np.abs(X).max())
+
+
 def test_singular_values_and_matrix_rank(eng):
     """eval/compute_m2e_matrix_ranks.py:44-53: np.linalg.matrix_rank of a score matrix."""
     rng = np.random.default_rng(0)
