@@ -40,6 +40,10 @@ def test_abi_version_and_size_queries(lib):
     assert lib.anncur_packed_items_bytes(100000, 500, 0) >= 2 * 16 * 100000 * 64
     assert lib.anncur_packed_items_bytes(100000, 500, 1) >= 16 * 100000 * 64
     assert lib.anncur_packed_items_bytes(0, 500, 0) == 256
+    # kind F32R: both planes (k_i + 1 bound slot, padded to 64) plus the item-major fp32 copy: >= 8 bytes per element
+    assert lib.anncur_packed_items_bytes(100000, 500, 2) >= 8 * 500 * 100000
+    assert lib.anncur_packed_items_bytes(100000, 512, 2) > lib.anncur_packed_items_bytes(100000, 511, 2)   # the slot opens a k-block
+    assert lib.anncur_score_dense_workspace_bytes(4096, 100000, 500, 2) >= 2 * 2 * 4096 * 512
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):
@@ -49,6 +53,17 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     rc = lib.anncur_topk_rows_f32(None, 0, 3, 10, 5000, 0, None, None, None)
     assert rc == _lib.E_INVALID
     assert lib.anncur_gemm_f32(None, 0, None, 0, None, 0, 0, 5, 3, None) == 0      # empty problem is a no-op
+    # the kind checks of the packed index come before any device work (pointers below are never dereferenced on the host)
+    import ctypes as C
+    p = C.c_void_p(256)
+    rc = lib.anncur_pack_items(p, 100, 100, 16, 7, p, p, None)
+    assert rc == _lib.E_INVALID and b"kind" in lib.anncur_last_error()
+    rc = lib.anncur_pack_items(p, 100, 100, 9000, 2, p, p, None)
+    assert rc == _lib.E_UNSUPPORTED and b"k_dim" in lib.anncur_last_error()
+    rc = lib.anncur_score_topk(p, 16, 4, p, p, 100, 16, 0, 5000, 0, p, p, p, 1 << 20, None)
+    assert rc == _lib.E_INVALID and b"k = 5000" in lib.anncur_last_error()
+    rc = lib.anncur_score_dense(p, 16, 4, p, p, 100, 16, 1, p, 100, p, 1 << 20, None)                 # bf16 has no fp32-grade planes
+    assert rc == _lib.E_INVALID and b"kind" in lib.anncur_last_error()
 
 
 def test_built_for_sm100a_with_tcgen05_and_tma():
