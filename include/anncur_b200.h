@@ -7,7 +7,7 @@
  *   models/nearest_nbr.py          (build_flat_or_ivff_index(...).search, :24-55)
  *   eval/run_retrieval_eval_wrt_exact_crossenc*.py (per-query retrieve/rerank/overlap loops)
  * Each entry point below names the reference lines whose arithmetic it replaces.  The host-side
- * mirror of those Python surfaces lives in anncur_b200/*.py and binds this ABI with ctypes
+ * mirror of those Python surfaces lives in the anncur_b200 package (its .py files) and binds this ABI with ctypes
  * (INTEGRATION.md shows the binding).
  *
  * Conventions

@@ -66,6 +66,26 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert rc == _lib.E_INVALID and b"kind" in lib.anncur_last_error()
 
 
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++-isms, no torch types) and a C program links and calls it."""
+    from anncur_b200 import _lib
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include "anncur_b200.h"\n#include <stdio.h>\n'
+        'int main(void) {\n'
+        '    size_t b = anncur_packed_items_bytes(1000, 500, ANNCUR_KIND_F32R);\n'
+        '    int rc = anncur_merge_topk(NULL, NULL, 4, 8, 0, NULL, NULL, NULL);\n'
+        '    printf("%d %zu %d %s\\n", anncur_abi_version(), b, rc, anncur_last_error());\n'
+        '    return (anncur_abi_version() == ANNCUR_ABI_VERSION && rc == ANNCUR_E_INVALID) ? 0 : 1;\n}\n')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lanncur_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split()[0] == "1" and int(r.stdout.split()[1]) >= 8 * 500 * 1000
+
+
 def test_built_for_sm100a_with_tcgen05_and_tma():
     from anncur_b200 import _lib
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
