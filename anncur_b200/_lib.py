@@ -20,6 +20,7 @@ PROTOTYPES = {
     "anncur_pinv_workspace_bytes": (_sz, [_i, _i]),
     "anncur_pinv_f32": (_i, [_vp, _i, _i, _i, _d, _vp, _i, _vp, _vp, _sz, _vp]),
     "anncur_singular_values_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "anncur_jacobi_status": (_i, [_vp, _vp, _vp]),
     "anncur_gemm_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "anncur_packed_items_bytes": (_sz, [_i64, _i, _i]),
     "anncur_pack_items": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
@@ -39,6 +40,15 @@ PROTOTYPES = {
     "anncur_topk_to_keys": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "anncur_merge_topk_keys_workspace_bytes": (_sz, [_i]),
     "anncur_merge_topk_keys": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_peer_channel_bytes": (_sz, [_i, _i, _i]),
+    "anncur_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "anncur_peer_free": (_i, [_vp]),
+    "anncur_peer_export": (_i, [_vp, _vp]),
+    "anncur_peer_open": (_i, [_vp, C.POINTER(_vp)]),
+    "anncur_peer_close": (_i, [_vp]),
+    "anncur_peer_scatter_keys": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.c_uint32, C.POINTER(_vp), _vp]),
+    "anncur_peer_merge_owned": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_peer_error": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_int), _vp]),
     "anncur_rerank_overlap": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp, _i, C.POINTER(C.c_int), _i, _vp, _vp, _vp, _vp]),
     "anncur_overlap_counts": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "anncur_recon_error_f32": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),

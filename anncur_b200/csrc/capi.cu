@@ -71,6 +71,11 @@ int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* si
     return singular_values_f32(A, m, n, lda, sigma_out, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+int anncur_jacobi_status(const void* workspace, double* status4_out, void* stream) {
+    ANNCUR_REQUIRE(workspace && status4_out, "jacobi_status: null pointer");
+    return jacobi_status(workspace, status4_out, cudaStream_t(stream));
+}
+
 int anncur_gemm_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int m, int n, int k,
                     void* stream) {
     ANNCUR_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative shape");
@@ -259,6 +264,41 @@ int anncur_merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k
     if (workspace_bytes < anncur_merge_topk_keys_workspace_bytes(n_rows)) { set_error("merge_topk_keys workspace too small"); return ANNCUR_E_WORKSPACE; }
     return merge_topk_keys(keys, n_shards, n_rows, k_in, k_out, out_vals, out_idx, reinterpret_cast<uint32_t*>(workspace),
                            cudaStream_t(stream));
+}
+
+size_t anncur_peer_channel_bytes(int world, int rows_cap, int k_cap) { return peer_channel_bytes(world, rows_cap, k_cap); }
+int anncur_peer_alloc(size_t bytes, void** base_out) {
+    ANNCUR_REQUIRE(base_out && bytes > 0, "peer_alloc: null pointer or zero size");
+    return peer_alloc(bytes, base_out);
+}
+int anncur_peer_free(void* base) { return peer_free(base); }
+int anncur_peer_export(const void* base, void* handle64_out) {
+    ANNCUR_REQUIRE(base && handle64_out, "peer_export: null pointer");
+    return peer_export(base, handle64_out);
+}
+int anncur_peer_open(const void* handle64, void** mapped_out) {
+    ANNCUR_REQUIRE(handle64 && mapped_out, "peer_open: null pointer");
+    return peer_open(handle64, mapped_out);
+}
+int anncur_peer_close(void* mapped) { return peer_close(mapped); }
+int anncur_peer_scatter_keys(const float* vals, const int64_t* idx, int n_rows, int k, int rank, int world, int rows_cap,
+                             int k_cap, uint32_t epoch, void* const* peer_bases, void* stream) {
+    ANNCUR_REQUIRE(peer_bases && (n_rows == 0 || (vals && idx)), "peer_scatter_keys: null pointer");
+    ANNCUR_REQUIRE(rows_cap >= 1 && k_cap >= 1, "peer_scatter_keys: bad capacities");
+    return peer_scatter_keys(vals, idx, n_rows, k, rank, world, rows_cap, k_cap, epoch, peer_bases, cudaStream_t(stream));
+}
+int anncur_peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int rows_cap, int k_cap, int k_out,
+                            uint32_t epoch, float* out_vals, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    ANNCUR_REQUIRE(local_base && workspace && (rows_owned == 0 || (out_vals && out_idx)), "peer_merge_owned: null pointer");
+    ANNCUR_REQUIRE(k_out >= 1 && k_out <= 1024, "peer_merge_owned: k_out = %d outside [1, 1024]", k_out);
+    if (workspace_bytes < anncur_merge_topk_keys_workspace_bytes(rows_owned)) { set_error("peer_merge_owned workspace too small"); return ANNCUR_E_WORKSPACE; }
+    return peer_merge_owned(local_base, rank, world, rows_owned, rows_cap, k_cap, k_out, epoch, out_vals, out_idx,
+                            reinterpret_cast<uint32_t*>(workspace), cudaStream_t(stream));
+}
+int anncur_peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, void* stream) {
+    ANNCUR_REQUIRE(local_base && err_host, "peer_error: null pointer");
+    return peer_error(local_base, world, rows_cap, k_cap, err_host, cudaStream_t(stream));
 }
 
 int anncur_rerank_overlap(const float* exact, int64_t lds, int n_rows, int64_t n_cols, const int64_t* retr_idx,

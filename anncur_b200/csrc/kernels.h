@@ -16,6 +16,8 @@ int select_topk_keylists(const uint64_t* keys, const uint32_t* counts, int n_lis
 int topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint64_t* keys, cudaStream_t stream);
 int merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out, float* out_vals, int64_t* out_idx,
                     uint32_t* scratch_rows, cudaStream_t stream);
+int merge_topk_keys_strided(const uint64_t* keys, int n_shards, int n_rows, int k_in, int64_t shard_stride, int k_out,
+                            float* out_vals, int64_t* out_idx, uint32_t* scratch_rows, cudaStream_t stream);
 int select_topk_pairs(const float* vals, const int64_t* idx, int n_rows, int n_cand, int k, float* out_vals,
                       int64_t* out_idx, cudaStream_t stream);
 
@@ -35,6 +37,7 @@ int recon_error(const float* Q, int64_t ldq, const float* E, int64_t lde, const 
 size_t pinv_workspace_bytes(int m, int n);
 int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int jacobi_status(const void* workspace, double* status4_out, cudaStream_t stream);
 int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace, size_t workspace_bytes,
                         cudaStream_t stream);
 
@@ -63,6 +66,19 @@ int recon_error_packed(const float* Q, int ldq, int n_queries, const void* packe
                        size_t workspace_bytes, cudaStream_t stream);
 int score_topk_redo_rows(const void* workspace, int n_queries, int64_t n_items, int k_dim, int k, int kind, int* redo_rows_host,
                          cudaStream_t stream);
+
+// peer_exchange.cu (candidate exchange of the item-sharded search over NVLink peer memory)
+size_t peer_channel_bytes(int world, int rows_cap, int k_cap);
+int peer_alloc(size_t bytes, void** out);
+int peer_free(void* p);
+int peer_export(const void* base, void* handle64);
+int peer_open(const void* handle64, void** out);
+int peer_close(void* mapped);
+int peer_scatter_keys(const float* vals, const int64_t* idx, int n_rows, int k, int rank, int world, int rows_cap, int k_cap,
+                      uint32_t epoch, void* const* peer_bases, cudaStream_t stream);
+int peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int rows_cap, int k_cap, int k_out, uint32_t epoch,
+                     float* out_vals, int64_t* out_idx, uint32_t* scratch_rows, cudaStream_t stream);
+int peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, cudaStream_t stream);
 
 // smallest j with P[Binomial(n, p) >= j] <= eps (rank used by the sampled thresholds)
 int binomial_tail_rank(int n, double p, double eps);

@@ -152,7 +152,7 @@ jacobi_coop_kernel(double* __restrict__ G, double* __restrict__ V, int len, int 
 
 // sigma_j^2 -> weights 1/sigma_j^2 with numpy's cutoff; one CTA, p threads strided
 __global__ void __launch_bounds__(JAC_THREADS)
-jacobi_weights_kernel(const double* __restrict__ G, int len, int p, double rcond, double* __restrict__ w,
+jacobi_weights_kernel(const double* __restrict__ G, int len, int p, double rcond, double tol, double* __restrict__ w,
                       JacobiState* st) {
     __shared__ double red[JAC_THREADS / 32];
     __shared__ double smax;
@@ -168,7 +168,10 @@ jacobi_weights_kernel(const double* __restrict__ G, int len, int p, double rcond
     }
     if (threadIdx.x == 0) smax = sqrt(local_max);
     __syncthreads();
-    const double cutoff = rcond * smax;
+    // numpy's cutoff is rcond * s_max on singular values that LAPACK computed in fp32.  Ours are fp64 Jacobi values: a
+    // column that is an exact combination of others comes out at ~1e-16 s_max (not ~1e-7 as in fp32) and would be inverted
+    // to 1e32 under rcond = 1e-15.  Floor the cutoff at the level the sweeps resolve (8 x the orthogonality tolerance).
+    const double cutoff = fmax(rcond, 8.0 * tol) * smax;
     double min_kept = smax;
     for (int j = threadIdx.x; j < p; j += JAC_THREADS) {
         double sig = sqrt(w[j]);
@@ -240,6 +243,20 @@ __global__ void pinv_export_cond_kernel(const JacobiState* st, double* cond_out)
     cond_out[1] = st->s_min_kept;
 }
 
+// column-orthogonality tolerance of the sweeps: |g_i . g_j| <= tol |g_i| |g_j|
+static double jacobi_tol(int len) { return fmax(1e-15, 4.0 * sqrt(double(len)) * 1.1102230246251565e-16); }
+
+__global__ void jacobi_export_status_kernel(const JacobiState* st, double* out) {
+    out[0] = st->s_max; out[1] = st->s_min_kept; out[2] = double(st->converged); out[3] = double(st->sweeps_done);
+}
+
+// {s_max, s_min_kept (pinv only), converged (0 / 1), sweeps done} of the last factorisation run on `workspace`
+int jacobi_status(const void* workspace, double* status4_out, cudaStream_t stream) {
+    jacobi_export_status_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const JacobiState*>(workspace), status4_out);
+    ANNCUR_LAUNCH_OK("jacobi_export_status_kernel");
+    return ANNCUR_OK;
+}
+
 size_t pinv_workspace_bytes(int m, int n) {
     if (m <= 0 || n <= 0) return 256;
     size_t len = size_t(m > n ? m : n), p = size_t(m > n ? n : m);
@@ -259,8 +276,12 @@ static int jacobi_factor(const float* A, int m, int n, int lda, void* workspace,
 
     jacobi_init_kernel<<<sm_count() * 4, 256, 0, stream>>>(A, m, n, lda, len, p, tall, G, V, st);
     ANNCUR_LAUNCH_OK("jacobi_init_kernel");
-    const double tol = fmax(1e-15, 4.0 * sqrt(double(len)) * 1.1102230246251565e-16);
+    const double tol = jacobi_tol(len);
     bool coop_done = false;
+    if (p <= 1) {                                       // a single column is its own factorisation
+        jacobi_sweep_end_kernel<<<1, 1, 0, stream>>>(st, tol);
+        ANNCUR_LAUNCH_OK("jacobi_sweep_end_kernel");
+    }
     if (p > 1) {
         const int p_even = (p + 1) & ~1;
         int dev = 0, coop = 0, per_sm = 0;
@@ -302,7 +323,7 @@ int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, in
     double* G = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
     double* V = G + size_t(len) * p;
     double* w = V + size_t(p) * p;
-    jacobi_weights_kernel<<<1, JAC_THREADS, 0, stream>>>(G, len, p, rcond, w, st);
+    jacobi_weights_kernel<<<1, JAC_THREADS, 0, stream>>>(G, len, p, rcond, jacobi_tol(len), w, st);
     ANNCUR_LAUNCH_OK("jacobi_weights_kernel");
     dim3 grid((len + PT - 1) / PT, (p + PT - 1) / PT);
     // tall: pinv(A) = P (n x m = p x len);  wide: pinv(A) = P^T (n x m = len x p)

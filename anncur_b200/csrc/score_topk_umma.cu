@@ -12,7 +12,8 @@
 //   BF16  : single bf16 pass.
 //   F32R  : fp32 results at the one-pass rate ("filter and refine").  MAIN is ONE f16 pass on the high halves, but
 //           the contraction carries one extra anchor slot: the item side holds ||e_n|| 2^-5, the query side
-//           +-1.05 ||q|| 2^-5, so the accumulator is A_n +- b_n with b_n = 1.05 2^-10 ||q|| ||e_n|| >= |S_n - A_n|
+//           +-f(K) ||q|| 2^-5, so the accumulator is A_n +- b_n with b_n = f(K) 2^-10 ||q|| ||e_n|| >= |S_n - A_n|, f(K) =
+//           1.04 + K-proportional terms for the fp32 accumulation of the tensor pipe and of the re-scoring (f32r_slot_factor)
 //           (Cauchy-Schwarz over the per-element fp16 rounding errors; S_n = the fp32 score).  SAMPLE runs with
 //           the minus sign (lower bounds -> threshold T <= k-th best S), MAIN with the plus sign (upper bounds:
 //           every item that can be in the top-k is pushed), and refine_topk_keylists (refine_topk.cu) re-scores
@@ -778,9 +779,15 @@ pack_items_kernel(const float* __restrict__ E, int64_t lde, int64_t n_items, int
     }
 }
 
+// F32R: factor on the query-side bound slot, see pack_queries_kernel.  Relative to the fp16-rounding bound 2^-10 |q'| |e'|:
+// tensor-pipe accumulation (K/16 + 1) 2^-22 / 2^-10, re-scoring accumulation (K/32 + 8) 2^-24 / 2^-10, and a flat 4 %.
+__host__ __device__ __forceinline__ float f32r_slot_factor(int k_dim) {
+    return 1.04f + (float(k_dim) * (1.0f / 16.0f) + 1.0f) * 0x1p-12f + (float(k_dim) * (1.0f / 32.0f) + 8.0f) * 0x1p-14f;
+}
+
 // Q (B x k_dim, k contiguous) -> plane[kb][b][32], one warp per query row, per-row power-of-two scale.
-// F32R: slot k_dim of the last k-block of the high plane holds +1.05 ||q'|| 2^-5 (rounded up); k-blocks num_kb and
-// num_kb + 1 are copies of that last k-block with the slot set to -1.05 ||q'|| 2^-5 and to 0 (see FusedParams::a_last_kb).
+// F32R: slot k_dim of the last k-block of the high plane holds +f(K) ||q'|| 2^-5 (rounded up); k-blocks num_kb and
+// num_kb + 1 are copies of that last k-block with the slot set to -f(K) ||q'|| 2^-5 and to 0 (see FusedParams::a_last_kb).
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int plane_rows, int k_dim, int num_kb,
@@ -861,10 +868,13 @@ pack_queries_kernel(const float* __restrict__ Q, int64_t ldq, int n_queries, int
         // Error bound of the one-pass score A = sum_i h(q'_i) h(e'_i) against S = sum_i q'_i e'_i (scaled operands):
         // |x - h(x)| <= 2^-11 |x| + 2^-25 (fp16 rounding, subnormals included), so by Cauchy-Schwarz
         //   |S - A| <= (2^-10 + 2^-22) sqrt(|q'|^2 + K 2^-28) sqrt(|e'_n|^2 + K 2^-28).
-        // The slot product is 1.05 x that (rounded up on both sides): the 5 % cover the fp32 accumulation order of
-        // the tensor pipe and of the re-scoring kernel (each < 2^-17 sum_i |q'_i e'_i|) and the rounding of the norms.
+        // The slot product is f(K) x that (rounded up on both sides), f(K) = f32r_slot_factor(k_dim): a reserve that GROWS
+        // with K for what is not fp16 operand rounding -- the fp32 accumulation of the tensor pipe (K / 16 + 1 additions into
+        // the TMEM accumulator, each allowed a full 2 ulp = 2^-22 of sum_i |q'_i e'_i| <= |q'| |e'_n|: truncating adders,
+        // coherent signs), the accumulation of the re-scoring kernel (K / 32 + 8 roundings of 2^-24 per lane chain and
+        // shuffle tree) and 4 % for the fp32 rounding of the norms and the slot product.  f(500) = 1.049, f(8192) = 1.181.
         norm2 = warp_sum(norm2);
-        const float slot = sqrtf(norm2 + float(k_dim) * 0x1p-28f) * (1.05f * 1.001f * 0x1p-5f);
+        const float slot = sqrtf(norm2 + float(k_dim) * 0x1p-28f) * (f32r_slot_factor(k_dim) * 1.001f * 0x1p-5f);
         const uint16_t slot_p = __half_as_ushort(__float2half_ru(slot));
         const int kb_s = num_kb - 1;                                         // the slot lives at anchor index k_dim, in the last k-block
 #pragma unroll
@@ -1210,17 +1220,24 @@ static FusedPlan make_plan(int n_queries, int64_t n_items, int k_dim, int k, int
     // sampling stride G: the coarsest of 16 / 8 / 4 that still leaves >= 4 j group maxima per row.  (Coarser strides
     // were tried for large item sets: G = 64 makes SAMPLE 4x cheaper but leaves ~800 instead of ~460 survivors per
     // row at k = 100, which costs more in the select than it saves -- measured slower at N = 1M for B = 64 and 4096.)
-    for (int G : {16, 8, 4}) {
-        const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-6);
-        const int64_t s_items = (n_items + G - 1) / G;
-        const int64_t n_smax = (s_items + 31) / 32;
-        if (n_smax >= 4ll * j && s_items >= 4 * BLOCK_N) {
-            pl.sample_stride = G; pl.sample_rank = j; pl.s_items = int(s_items);
-            pl.s_tiles = int((s_items + BLOCK_N - 1) / BLOCK_N);
-            pl.n_smax = pl.s_tiles * (BLOCK_N / 32);
-            pl.s_chunks = choose_chunks(m_groups, pl.s_tiles, units, 0.25);
-            break;
+    // Second round, only when no stride gives 4 j maxima: settle for 2 j.  The j-th largest of n group maxima then sits
+    // at up to the median of the maxima (~1.4 j G survivors per row instead of ~1.25 j G) -- still a one-pass threshold
+    // where the call would otherwise stream from -inf: k = 1000 at N = 100k (the reference's largest k_r,
+    // ..._w_fixed_train_test_splits.py:238-247) took 17 ms per 4096 queries unsampled.
+    for (int need : {4, 2}) {
+        for (int G : {16, 8, 4}) {
+            const int j = binomial_tail_rank(k - 1, 1.0 / G, 1e-6);
+            const int64_t s_items = (n_items + G - 1) / G;
+            const int64_t n_smax = (s_items + 31) / 32;
+            if (n_smax >= int64_t(need) * j && s_items >= 4 * BLOCK_N) {
+                pl.sample_stride = G; pl.sample_rank = j; pl.s_items = int(s_items);
+                pl.s_tiles = int((s_items + BLOCK_N - 1) / BLOCK_N);
+                pl.n_smax = pl.s_tiles * (BLOCK_N / 32);
+                pl.s_chunks = choose_chunks(m_groups, pl.s_tiles, units, 0.25);
+                break;
+            }
         }
+        if (pl.sample_stride != 0) break;
     }
     const bool sampled = pl.sample_stride != 0;
     // with sampled thresholds a row keeps ~1.25 j G survivors: enough chunks that one list holds twice its share

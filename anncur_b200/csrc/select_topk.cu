@@ -547,9 +547,16 @@ int topk_to_keys(const float* vals, const int64_t* idx, int n_rows, int k, uint6
 // Best k_out of n_shards sorted key lists per row, keys laid out [shard][row][k_in] (the all-gather's output as is).
 int merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out, float* out_vals, int64_t* out_idx,
                     uint32_t* scratch_rows, cudaStream_t stream) {
+    return merge_topk_keys_strided(keys, n_shards, n_rows, k_in, int64_t(n_rows) * k_in, k_out, out_vals, out_idx, scratch_rows, stream);
+}
+
+// The same with an explicit distance (in keys) between the lists of consecutive shards: the receive buffer of the peer
+// exchange is [shard][rows_cap][k_in] with rows_cap >= n_rows (peer_exchange.cu).
+int merge_topk_keys_strided(const uint64_t* keys, int n_shards, int n_rows, int k_in, int64_t shard_stride, int k_out,
+                            float* out_vals, int64_t* out_idx, uint32_t* scratch_rows, cudaStream_t stream) {
     if (n_rows == 0) return ANNCUR_OK;
     if (n_shards > kMaxLists) { set_error("merge_topk_keys: %d shards > %d", n_shards, kMaxLists); return ANNCUR_E_UNSUPPORTED; }
-    KeyLists src{keys, nullptr, n_shards, k_in, 0, nullptr, nullptr, 0, 0, nullptr, int64_t(n_rows) * k_in, int64_t(k_in), 0};
+    KeyLists src{keys, nullptr, n_shards, k_in, 0, nullptr, nullptr, 0, 0, nullptr, shard_stride, int64_t(k_in), 0};
     SelectOut o{out_vals, out_idx, 0, nullptr, k_out, next_pow2(k_out < 2 ? 2 : k_out)};
     ANNCUR_CUDA_OK(cudaMemsetAsync(scratch_rows, 0, sizeof(uint32_t), stream));
     const size_t smem = size_t(kWarpSelWarps) * (kWarpSelCap * sizeof(uint64_t) + (256 + size_t(n_shards) + 1) * sizeof(uint32_t));

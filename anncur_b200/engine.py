@@ -100,7 +100,19 @@ def pinv(A, rcond=1e-15, return_cond=False):
         with torch.cuda.device(A.device):
             _lib.check(lib.anncur_pinv_f32(_ptr(A), m, n, _ld(A), float(rcond), _ptr(out), max(m, 1), _ptr(cond),
                                            _ptr(ws), ws.numel(), _stream()))
+            _require_converged(lib, ws, "pinv", (m, n))
     return (out, cond) if return_cond else out
+
+
+def _require_converged(lib, ws, what, shape):
+    """The Jacobi sweeps stop at a sweep limit; a factorisation that did not converge must not pass silently (the index
+    build is a one-off, so the host read-back of the status is affordable)."""
+    status = torch.zeros(4, dtype=torch.float64, device=ws.device)
+    _lib.check(lib.anncur_jacobi_status(_ptr(ws), _ptr(status), _stream()))
+    s_max, _, converged, sweeps = status.tolist()
+    if converged != 1.0:
+        raise RuntimeError(f"anncur_b200.{what}: Jacobi SVD of a {shape[0]} x {shape[1]} matrix did not converge in "
+                           f"{int(sweeps)} sweeps (s_max = {s_max:.3g}); the result is not usable")
 
 
 def singular_values(A):
@@ -115,6 +127,7 @@ def singular_values(A):
         ws = WORKSPACE.get("pinv", nbytes, A.device)
         with torch.cuda.device(A.device):
             _lib.check(lib.anncur_singular_values_f32(_ptr(A), m, n, _ld(A), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+            _require_converged(lib, ws, "singular_values", (m, n))
     return torch.sort(out, descending=True).values
 
 

@@ -2,30 +2,37 @@
 """Benchmark of the ANNCUR test-time search path (score + top-100) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|n1m|c4] [--precision f32r|f32x3|bf16] [--shard queries|items]
+                    [--workload n1m|c2|c4] [--precision f32r|f32x3|bf16]
+                    [--shard items|queries] [--exchange p2p|nccl|allgather]
 
 One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch of B queries:
 ``CURApprox.topk_in_row`` = ``torch.topk(Q @ E, k, dim=1)`` (eval/matrix_approx_zeshel.py:109-126 of the
-reference).  Workloads (BASELINE.json ``configs``):
+reference).  Workloads (BASELINE.json):
 
-  c2   N = 100 000 items, k_i = 500, B = 4096, top-100            <- default, configs[1]
-  n1m  N = 1 000 000 items, k_i = 500, B = 4096, top-100          (north_star headline size)
-  c4   N = 10 000 000 items, k_i = 500, B = 4096, top-100         (configs[3], item-sharded)
+  n1m  N = 1 000 000 items, k_i = 500, B = 4096, top-100   <- default: the size north_star quotes its target on
+  c2   N = 100 000 items,   k_i = 500, B = 4096, top-100      (configs[1]; carried as an extra key of the default run at N = 1)
+  c4   N = 10 000 000 items, k_i = 500, B = 4096, top-100     (configs[3]; carried as an extra key of every default run)
 
-``value``  : device-resident throughput (queries already in HBM), CUDA events, max over ranks.
-``e2e``    : the same through the host-buffer C-ABI entry (anncur_search_host): pinned host Q -> H2D ->
-             kernels -> D2H of (values, indices) every step.
-``roofline``: dominant kernel (fused tcgen05 score + top-k), per-launch CUDA events recorded inside the
-             library on the launching stream; algorithmic flops 2*B*k_i*N (counted once, also for the 3-pass
-             kind), peak = MEASURED_PEAKS.json.  Default precision f32r: fp32 results from ONE f16 tensor pass
-             of rigorous score upper bounds + fp32 re-scoring of the ~k candidates per row.
-``cpu_baseline`` / ``--impl reference``: the oracle's CPU restatement of the reference path
-             (torch.matmul + torch.topk on all host threads) -- the only place bench executes oracle/.
+N = 1: the whole index on one GPU.  N > 1 (torchrun, one rank per GPU): **items sharded** -- rank p holds E[:, lo_p:hi_p],
+every rank scores the same batch against its slice, then ONE exchange step: each row's P candidate lists travel to the rank
+that owns the row (contiguous row blocks) and are merged there.  ``--exchange p2p`` (default): keys are stored straight into
+the owner's buffer over NVLink peer memory by our own kernel (csrc/peer_exchange.cu); ``nccl``: all_to_all_single;
+``allgather``: all-gather + merge of every row on every rank (the form north_star words).  The exchange is inside both timed
+regions; total work is fixed as N grows (``scaling: "strong"``).  In every multi-GPU run rank 0 also builds the whole index
+and asserts that the sharded answer equals the single-GPU answer on a row sample.  ``--shard queries`` = replicas of the
+index, no collective (weak scaling; kept for comparison).
 
-Multi-GPU (torchrun, one rank per GPU): ``--shard queries`` (default for c2/n1m) replicates E and gives
-every rank its own query batches -- no data-path collective, weak scaling; ``--shard items`` (default
-for c4) splits the items, every rank scores the same batch against its slice and the candidates are
-merged after one NCCL all-gather (strong scaling in N).
+``value``  : device-resident throughput (queries already in HBM), CUDA events, max over ranks, one stream, in order.
+``e2e``    : the same through the host-facing call: N = 1 ``anncur_search_host`` (C ABI: pinned host Q -> H2D -> kernels ->
+             D2H of values + indices every step); N > 1 ``ShardedIndex.search_owned``: every rank uploads ITS block of the
+             batch, the blocks are all-gathered over NVLink, and every rank downloads the merged rows it owns.
+``roofline``: dominant kernel (fused tcgen05 score + top-k = MAIN), per-launch CUDA events recorded inside the library on
+             the launching stream; algorithmic flops 2*B*k_i*N_local counted once; peak = MEASURED_PEAKS.json (burst figure
+             when the timed loop is shorter than 1 s, sustained otherwise; both fractions are printed).  ``step_frac`` is
+             the same ratio for the whole step (all kernels + exchange).
+``cpu_baseline`` / ``--impl reference``: the reference's OWN ``CURApprox.topk_in_row`` from oracle/_ref (a verbatim copy of
+             eval/matrix_approx_zeshel.py made by oracle/build_ref.py; kind "reference") on all host threads, or the oracle
+             port when oracle/_ref is absent (kind "port") -- the only places bench executes oracle/.
 """
 import argparse
 import json
@@ -46,8 +53,10 @@ WORKLOADS = {
     "n1m": (1_000_000, 500, 2000, 4096, 100),
     "c4": (10_000_000, 500, 2000, 4096, 100),
 }
+DEFAULT_STEPS = {"c2": 200, "n1m": 200, "c4": 30}
 RANK_LOW, NOISE = 64, 0.05
 N_BATCHES = 4            # distinct query batches rotated through the steps
+CHECK_ROWS = 256         # rows of the sharded == single-GPU assertion
 
 
 def log(*a):
@@ -128,85 +137,113 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# synthetic workload: A = X.Y^T/sqrt(r) + noise*G; only R = A_train and Q = A_test[:, anchors]
-# are ever formed.  Built with the engine's own K1/K2 (pinv + U.R) outside the timed region.
+# synthetic workload: A = X.Y^T/sqrt(r) + noise*G; only R = A_train (its anchor columns C) and
+# Q = A_test[:, anchors] are ever formed.  Plain torch on `device` (cuda or cpu), chunk-keyed seeds, so that any item range
+# of the same workload can be regenerated anywhere (a shard on its rank, the whole index on rank 0, the reference arm).
 # ---------------------------------------------------------------------------------------------------
-def build_workload(name, device, lo, hi, seed, n_batches, batch_seed_offset=0):
-    """Item-embedding slice E[:, lo:hi] (k_i x (hi-lo) fp32 on `device`) of the N-item index + query batches."""
-    import numpy as np
+CHUNK = 250_000
+
+
+class Synthetic:
+    def __init__(self, name, device, seed=0):
+        import numpy as np
+        import torch
+        self.torch = torch
+        self.name, self.device, self.seed = name, device, seed
+        self.N, self.k_i, self.n_train, self.B, self.k = WORKLOADS[name]
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        self.X_train = torch.randn((self.n_train, RANK_LOW), generator=g, device=device)
+        self.anc = torch.as_tensor(np.sort(np.random.default_rng(seed).choice(self.N, size=self.k_i, replace=False)), device=device)
+        self.chunks = [(a, min(a + CHUNK, self.N)) for a in range(0, self.N, CHUNK)]
+        # anchor-item factors / columns: taken from the chunk they live in, so that C == R[:, anchors] exactly
+        self.C = torch.empty((self.n_train, self.k_i), device=device)
+        self.Y_anc = torch.empty((self.k_i, RANK_LOW), device=device)
+        for a, b in self.chunks:
+            sel = (self.anc >= a) & (self.anc < b)
+            if not bool(sel.any()):
+                continue
+            Y = self._item_factors(a, b)
+            Rc = self._rows_chunk(Y, a, b)
+            self.C[:, sel] = Rc[:, self.anc[sel] - a]
+            self.Y_anc[sel] = Y[self.anc[sel] - a]
+            del Rc, Y
+
+    def _item_factors(self, a, b):
+        gy = self.torch.Generator(device=self.device)
+        gy.manual_seed(self.seed * 1_000_003 + a)
+        return self.torch.randn((b - a, RANK_LOW), generator=gy, device=self.device)
+
+    def _rows_chunk(self, Y, a, b):
+        gn = self.torch.Generator(device=self.device)
+        gn.manual_seed(self.seed * 7_000_003 + a * 31 + 1)
+        return self.X_train @ Y.t() / math.sqrt(RANK_LOW) + self.torch.randn((self.n_train, b - a), generator=gn, device=self.device) * NOISE
+
+    def anchor_rows(self, lo, hi):
+        """R[:, lo:hi] = the anchor queries' exact scores of items lo..hi, chunk by chunk: yields (a2, b2, R_chunk)."""
+        for a, b in self.chunks:
+            a2, b2 = max(a, lo), min(b, hi)
+            if a2 >= b2:
+                continue
+            Rc = self._rows_chunk(self._item_factors(a, b), a, b)[:, a2 - a:b2 - a].contiguous()
+            yield a2, b2, Rc
+
+    def query_batch(self, j, salt=0):
+        gq = self.torch.Generator(device=self.device)
+        gq.manual_seed(self.seed * 13 + 1000 + j + salt)
+        Xq = self.torch.randn((self.B, RANK_LOW), generator=gq, device=self.device)
+        Q = Xq @ self.Y_anc.t() / math.sqrt(RANK_LOW) + self.torch.randn((self.B, self.k_i), generator=gq, device=self.device) * NOISE
+        return Q.contiguous()
+
+
+def build_index(syn, lo, hi):
+    """E[:, lo:hi] with the engine's own K1 (pinv) and K2 (U . R) -- outside every timed region."""
     import torch
     from anncur_b200 import engine
-
-    N, k_i, n_train, B, k = WORKLOADS[name]
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    r = RANK_LOW
-    X_train = torch.randn((n_train, r), generator=g, device=device)
-    anc = np.sort(np.random.default_rng(seed).choice(N, size=k_i, replace=False))
-    anc_t = torch.as_tensor(anc, device=device)
-
-    def item_factors(a, b):                       # Y[a:b] regenerated per chunk from a chunk-keyed seed
-        gy = torch.Generator(device=device)
-        gy.manual_seed(seed * 1_000_003 + a)
-        return torch.randn((b - a, r), generator=gy, device=device)
-
-    def noise(rows, a, b, salt):
-        gn = torch.Generator(device=device)
-        gn.manual_seed(seed * 7_000_003 + a * 31 + salt)
-        return torch.randn((rows, b - a), generator=gn, device=device) * NOISE
-
-    CH = 250_000
-    chunks = [(a, min(a + CH, N)) for a in range(0, N, CH)]
-    # anchor-item factors/noise: take them from the chunk they live in so that C == R[:, anc] exactly
-    C = torch.empty((n_train, k_i), device=device)
-    Y_anc = torch.empty((k_i, r), device=device)
-    for a, b in chunks:
-        sel = (anc_t >= a) & (anc_t < b)
-        if not bool(sel.any()):
-            continue
-        Y = item_factors(a, b)
-        Rc = X_train @ Y.t() / math.sqrt(r) + noise(n_train, a, b, 1)
-        C[:, sel] = Rc[:, anc_t[sel] - a]
-        Y_anc[sel] = Y[anc_t[sel] - a]
-        del Rc, Y
+    dev = syn.device
     t0 = time.perf_counter()
-    U = engine.pinv(C)                                                   # K1: k_i x n_train
-    torch.cuda.synchronize(device)
+    U = engine.pinv(syn.C)                                                   # K1: k_i x n_train
+    torch.cuda.synchronize(dev)
     t_pinv = time.perf_counter() - t0
-    E = torch.empty((k_i, hi - lo), device=device)
+    E = torch.empty((syn.k_i, hi - lo), device=dev)
     t_gemm = 0.0
-    for a, b in chunks:
-        a2, b2 = max(a, lo), min(b, hi)
-        if a2 >= b2:
-            continue
-        Y = item_factors(a, b)
-        Rc = (X_train @ Y.t() / math.sqrt(r) + noise(n_train, a, b, 1))[:, a2 - a:b2 - a].contiguous()
-        torch.cuda.synchronize(device)
+    for a2, b2, Rc in syn.anchor_rows(lo, hi):
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        E[:, a2 - lo:b2 - lo] = engine.gemm(U, Rc)                        # K2: E = U . R
-        torch.cuda.synchronize(device)
+        E[:, a2 - lo:b2 - lo] = engine.gemm(U, Rc)                            # K2: E = U . R
+        torch.cuda.synchronize(dev)
         t_gemm += time.perf_counter() - t0
-        del Rc, Y
-    batches = []
-    for j in range(n_batches):
-        gq = torch.Generator(device=device)
-        gq.manual_seed(seed * 13 + 1000 + j + batch_seed_offset)
-        Xq = torch.randn((B, r), generator=gq, device=device)
-        Q = Xq @ Y_anc.t() / math.sqrt(r) + torch.randn((B, k_i), generator=gq, device=device) * NOISE
-        batches.append(Q.contiguous())
-    return {"E": E, "batches": batches, "N": N, "k_i": k_i, "B": B, "k": k, "n_train": n_train,
-            "build_s": {"pinv": t_pinv, "gemm": t_gemm}}
+        del Rc
+    return E, {"pinv": t_pinv, "U@R": t_gemm}
 
 
-def cpu_topk_throughput(E_host, Q_host, k, repeats, warmup=1):
-    """The oracle's CPU restatement of CURApprox.topk_in_row on all host threads; returns (q/s, seconds list)."""
+def cpu_sample_rows(N, B):
+    """Bounded CPU sample: rows of one batch such that one pass is ~1e12 flop (seconds on a host's cores)."""
+    return int(max(64, min(B, 1_000_000_000 // N)))
+
+
+def reference_topk_fn():
+    """(callable(Q, E, k) -> topk, kind): the reference's own CURApprox.topk_in_row when oracle/_ref is there, else the port."""
+    from oracle.ref_shim import load_reference_curapprox
+    CUR = load_reference_curapprox()
+    if CUR is None:
+        from oracle import cur_oracle as O
+        return O.score_topk, "port"
+
+    def run(Q, E, k):
+        ap = CUR.__new__(CUR)                  # E was built outside: attach it as the constructor would (:63-65)
+        ap.latent_cols, ap.approx_preference = E, "rows"
+        return ap.topk_in_row(Q, k)            # eval/matrix_approx_zeshel.py:121-126, verbatim
+    return run, "reference"
+
+
+def cpu_topk_throughput(fn, E_host, Q_host, k, repeats, warmup=1):
     import torch
-    from oracle import cur_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     times = []
     for it in range(warmup + repeats):
         t0 = time.perf_counter()
-        O.score_topk(Q_host, E_host, k)
+        fn(Q_host, E_host, k)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -214,41 +251,64 @@ def cpu_topk_throughput(E_host, Q_host, k, repeats, warmup=1):
     return Q_host.shape[0] / med, times
 
 
-def cpu_sample_rows(N, B):
-    """Bounded CPU sample: rows of one batch such that one pass is ~1-3 s on a few cores."""
-    rows = int(max(64, min(B, 4.0e8 // N * 1)))          # 100k -> 4000, 1M -> 400, 10M -> 64
-    return min(B, rows)
-
-
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only).
+
+    Same synthetic workload as the GPU arm (same generator code and seeds; generated with torch on the GPU when one is
+    visible -- plain torch ops, none of our kernels -- else on the CPU).  The index is built the reference's way: its own
+    constructor (np.linalg.pinv + U @ R, eval/matrix_approx_zeshel.py:21-69) when R fits in host memory, its formulas chunk by
+    chunk otherwise.  Timed: CURApprox.topk_in_row on a bounded row sample of one batch."""
     if rank != 0:
         return
+    import numpy as np
     import torch
     N, k_i, n_train, B, k = WORKLOADS[args.workload]
-    torch.manual_seed(0)
-    rows = cpu_sample_rows(N, B)
-    # same distribution as the GPU arm; E is formed directly (its build is outside the timed region anyway)
-    E = torch.randn((k_i, RANK_LOW)) @ torch.randn((RANK_LOW, N)) / math.sqrt(RANK_LOW) / math.sqrt(k_i)
-    Q = torch.randn((rows, k_i))
-    from oracle import cur_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
+    fn, kind = reference_topk_fn()
+    gen_dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    syn = Synthetic(args.workload, gen_dev, seed=0)
+    rows = cpu_sample_rows(N, B)
+    t0 = time.perf_counter()
+    from oracle.ref_shim import load_reference_curapprox
+    CUR = load_reference_curapprox()
+    C_host = syn.C.cpu()
+    if CUR is not None and N <= 2_000_000:
+        R_host = torch.empty((n_train, N))
+        for a2, b2, Rc in syn.anchor_rows(0, N):
+            R_host[:, a2:b2] = Rc.cpu()
+        ap = CUR(rows=R_host, cols=C_host, row_idxs=list(range(n_train)), col_idxs=syn.anc.cpu().tolist(), approx_preference="rows")
+        E = ap.latent_cols
+        built = "reference constructor (np.linalg.pinv + U @ R)"
+        del R_host
+    else:
+        U = torch.from_numpy(np.linalg.pinv(C_host.numpy()))                    # :49
+        E = torch.empty((k_i, N))
+        for a2, b2, Rc in syn.anchor_rows(0, N):
+            E[:, a2:b2] = U @ Rc.cpu()                                          # :65
+        built = "np.linalg.pinv + U @ R chunk by chunk (the reference's formulas :49, :65)"
+    t_build = time.perf_counter() - t0
+    Q = syn.query_batch(0)[:rows].cpu()
+    del syn
     for _ in range(args.warmup):
-        O.score_topk(Q, E, k)
+        fn(Q, E, k)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.score_topk(Q, E, k)
+        fn(Q, E, k)
     dt = time.perf_counter() - t0
     qps = rows * args.steps / dt
-    sample = f"{rows} of the {B} queries of a batch per step, all {N} items, k_i={k_i}, top-{k}; torch.matmul+torch.topk fp32"
+    sample = (f"{rows} of the {B} queries of a batch per step, all {N} items, k_i={k_i}, top-{k}; "
+              f"{'the reference CURApprox.topk_in_row (oracle/_ref)' if kind == 'reference' else 'oracle port'}: torch.matmul + torch.topk fp32; "
+              f"index built by {built} in {t_build:.1f} s (untimed)")
+    shard = args.shard or "items"
     line = {
         "impl": "reference", "metric": "queries/sec (ANNCUR score+top-100)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if shard == "items" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         # same config object as the GPU arm prints for these flags (the arm itself runs on the host threads of rank 0)
-        "config": workload_config(args, world, args.shard or ("items" if args.workload == "c4" else "queries")),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": workload_config(args, world, shard),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -257,13 +317,137 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world, shard):
     N, k_i, n_train, B, k = WORKLOADS[args.workload]
+    if world == 1:
+        par = "1 GPU: the whole index on one device"
+    elif shard == "items":
+        how = {"p2p": "candidate keys stored into the row owner's buffer over NVLink peer memory (own kernel) + merge of owned rows",
+               "nccl": "NCCL all_to_all_single of candidate keys by row block + merge of owned rows",
+               "allgather": "NCCL all-gather of candidate keys + merge of every row on every rank"}[args.exchange]
+        par = f"items sharded over {world} ranks (E[:, N/{world}] per GPU), same batch on every rank; exchange: {how}"
+    else:
+        par = f"dp{world}: E replicated, queries sharded, no collective"
     return {"workload": f"{args.workload}: ANNCUR score+top-{k}, N={N} items, k_i={k_i}, batch {B} queries/step",
-            "n_items": N, "k_i": k_i, "batch": B, "top_k": k, "precision": args.precision,
-            "parallelism": {"queries": f"dp{world}: E replicated, queries sharded, no collective",
-                            "items": f"items sharded over {world} ranks, NCCL all-gather + merge",
-                            "cpu": "host threads"}[shard],
-            "l2": "inputs larger than L2: packed E is streamed every step (>=205 MB at N=100k fp32-grade) and "
-                  f"{N_BATCHES} distinct query batches rotate"}
+            "n_items": N, "k_i": k_i, "batch": B, "top_k": k, "precision": args.precision, "parallelism": par,
+            "l2": f"inputs larger than L2: the packed index is streamed every step ({2 * k_i * N / world / 1e6:.0f} MB per rank "
+                  f"for the one-pass kinds) and {N_BATCHES} distinct query batches rotate"}
+
+
+# ---------------------------------------------------------------------------------------------------
+class Harness:
+    """One workload on this rank: index (whole or item slice), query batches, the step functions."""
+
+    def __init__(self, args, name, rank, local_rank, world, shard):
+        import torch
+        import torch.distributed as dist
+        from anncur_b200 import engine
+        from anncur_b200.sharded import ShardedIndex, shard_bounds
+        self.torch, self.dist, self.engine = torch, dist, engine
+        self.args, self.name, self.rank, self.world, self.shard = args, name, rank, world, shard
+        self.device = torch.device("cuda", local_rank)
+        self.N, self.k_i, self.n_train, self.B, self.k = WORKLOADS[name]
+        self.sharded = shard == "items" and world > 1
+        self.syn = Synthetic(name, self.device, seed=0)
+        self.lo, self.hi = shard_bounds(self.N, world)[rank] if self.sharded else (0, self.N)
+        self.E, self.build_s = build_index(self.syn, self.lo, self.hi)
+        t0 = time.perf_counter()
+        self.packed = engine.PackedItems(self.E, args.precision)
+        torch.cuda.synchronize()
+        self.build_s["pack"] = time.perf_counter() - t0
+        salt = 0 if (self.sharded or world == 1) else 97 * rank                       # replicas: every rank its own queries
+        self.batches = [self.syn.query_batch(j, salt) for j in range(N_BATCHES)]
+        self.index = None
+        if self.sharded:
+            self.index = ShardedIndex(self.E, self.lo, self.N, precision=args.precision, packed=self.packed,
+                                      exchange="nccl" if args.exchange == "allgather" else args.exchange)
+            self.row_lo, self.row_hi = self.index.row_block(self.B)
+        self.out_v = torch.empty((self.B, self.k), dtype=torch.float32, device=self.device)
+        self.out_i = torch.empty((self.B, self.k), dtype=torch.int64, device=self.device)
+
+    # one step with the batch already in HBM
+    def step_device(self, j):
+        Q = self.batches[j % N_BATCHES]
+        if self.index is None:
+            return self.engine.score_topk(Q, self.packed, self.k, idx_offset=self.lo, out=(self.out_v, self.out_i))
+        if self.args.exchange == "allgather":
+            return self.index.search(Q, self.k)
+        return self.index.search_rowblock(Q, self.k)
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def units_per_step(self):
+        return self.B * (self.world if (self.world > 1 and not self.sharded) else 1)
+
+    def time_device(self, steps, warmup, streams=1, sample_clocks=False, local_rank=0):
+        """(ms_total max over ranks, clocks summary | None, MAIN ms sum, MAIN launches, launches counted)."""
+        torch, engine = self.torch, self.engine
+        pool = [torch.cuda.current_stream(self.device)] if streams == 1 else [torch.cuda.Stream(device=self.device) for _ in range(streams)]
+
+        def issue(j):
+            if streams == 1:
+                self.step_device(j)
+            else:
+                with torch.cuda.stream(pool[j % streams]):
+                    self.step_device(j)
+        for j in range(max(warmup, 2 * streams)):
+            issue(j)
+        self.sync_all()
+        engine.profile_enable(True)
+        engine.profile_read()
+        engine.reset_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        self.sync_all()
+        ev0.record()
+        if streams > 1:
+            for s in pool:
+                s.wait_event(ev0)
+        for j in range(steps):
+            issue(j)
+        if streams > 1:
+            for s in pool:
+                torch.cuda.current_stream(self.device).wait_stream(s)
+        ev1.record()
+        self.sync_all()
+        if sampler:
+            sampler.__exit__()
+        ms_total = self.max_over_ranks(ev0.elapsed_time(ev1))
+        launches = engine.launch_count()
+        fused_ms, fused_n = engine.profile_read()
+        engine.profile_enable(False)
+        return ms_total, (sampler.summary() if sampler else None), fused_ms, fused_n, launches
+
+    def close(self):
+        if self.index is not None:
+            self.index.close()
+        self.engine.WORKSPACE.clear()
+        for name in ("E", "packed", "batches", "index", "syn", "out_v", "out_i"):
+            setattr(self, name, None)
+        self.torch.cuda.empty_cache()
+
+
+def quick_extra(args, name, rank, local_rank, world, shard, steps):
+    """Device-resident figure of another BASELINE config inside the same run (no e2e / CPU legs)."""
+    h = Harness(args, name, rank, local_rank, world, shard)
+    ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3)
+    out = {"workload": workload_config(argparse.Namespace(**{**vars(args), "workload": name}), world, shard)["workload"],
+           "value": h.units_per_step() * steps / (ms_total * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
+           "ms_per_step": ms_total / steps, "main_kernel_ms": fused_ms / max(fused_n, 1),
+           "parallelism": workload_config(argparse.Namespace(**{**vars(args), "workload": name}), world, shard)["parallelism"],
+           "index_build_s": h.build_s}
+    h.close()
+    return out
 
 
 def main():
@@ -272,10 +456,12 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="n1m", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f32r", choices=["f32r", "f32x3", "bf16"])
     ap.add_argument("--shard", default=None, choices=["queries", "items"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the bf16 / recall side measurements")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "allgather"])
+    ap.add_argument("--extras", default=None, help="comma list of other workloads measured in the same run (default: c2,c4 at N=1, c4 at N>1; 'none')")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other-precision / recall / pipelined side measurements and the extras")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -287,14 +473,13 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args, rank, world)
         return
-    args.steps = args.steps if args.steps is not None else 200
+    args.steps = args.steps if args.steps is not None else DEFAULT_STEPS[args.workload]
     args.warmup = max(3, args.warmup if args.warmup is not None else 10)
-    shard = args.shard or ("items" if args.workload == "c4" else "queries")
+    shard = args.shard or "items"
 
     import torch
     import torch.distributed as dist
     from anncur_b200 import engine
-    from anncur_b200.sharded import ShardedIndex, shard_bounds
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
@@ -304,103 +489,61 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     N, k_i, n_train, B, k = WORKLOADS[args.workload]
 
-    # ---- index + queries ---------------------------------------------------------------------------
-    if shard == "items" and world > 1:
-        lo, hi = shard_bounds(N, world)[rank]
-        wl = build_workload(args.workload, device, lo, hi, seed=0, n_batches=N_BATCHES)          # same Q on all ranks
-    else:
-        lo, hi = 0, N
-        wl = build_workload(args.workload, device, 0, N, seed=0, n_batches=N_BATCHES, batch_seed_offset=97 * rank)
-    t0 = time.perf_counter()
-    packed = engine.PackedItems(wl["E"], args.precision)
-    torch.cuda.synchronize()
-    t_pack = time.perf_counter() - t0
-    batches = wl["batches"]
-    index = ShardedIndex(wl["E"], lo, N, precision=args.precision, packed=packed) if (shard == "items" and world > 1) else None
+    h = Harness(args, args.workload, rank, local_rank, world, shard)
+    packed, batches, index = h.packed, h.batches, h.index
+    lo = h.lo
 
-    out_v = torch.empty((B, k), dtype=torch.float32, device=device)
-    out_i = torch.empty((B, k), dtype=torch.int64, device=device)
+    # ---- device-resident timing (one stream, in order) -------------------------------------------------
+    ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, sample_clocks=True, local_rank=local_rank)
+    qps = h.units_per_step() * args.steps / (ms_total * 1e-3)
 
-    def step_device(j):
-        if index is not None:
-            return index.search(batches[j % N_BATCHES], k)
-        return engine.score_topk(batches[j % N_BATCHES], packed, k, idx_offset=lo, out=(out_v, out_i))
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timing ----------------------------------------------------------------------
-    for j in range(args.warmup):
-        step_device(j)
-    sync_all()
-    engine.profile_enable(True)
-    engine.profile_read()
-    engine.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        sync_all()
-        ev0.record()
-        for j in range(args.steps):
-            step_device(j)
-        ev1.record()
-        sync_all()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = engine.launch_count()
-    fused_ms, fused_n = engine.profile_read()
-    engine.profile_enable(False)
-    units = B * args.steps * (world if (shard == "queries") else 1)
-    qps = units / (ms_total * 1e-3)
-
-    # ---- end-to-end through the host-buffer C-ABI entry ----------------------------------------------
-    # Rotating streams, each with its own workspace and pinned result buffers, so that the H2D copy of one batch and the
-    # D2H copy of another overlap the kernels of a third (the calls are asynchronous; every step still moves its
-    # own query batch in and its own result out inside the timed region).
-    N_SLOTS = 3          # measured with the current kernels (tools/e2e_probe.py, 200 steps at C2): 1 stream 0.712 ms/step, 2: 0.525, 3: 0.478, 4: 0.492
-    Qh = [b.cpu().pin_memory() for b in batches]
-    vh = [torch.empty((B, k), dtype=torch.float32).pin_memory() for _ in range(N_SLOTS)]
-    ih = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(N_SLOTS)]
+    # ---- end-to-end through the host-facing call ---------------------------------------------------------
+    # Rotating streams, each with its own workspace / exchange channel and pinned result buffers, so that the H2D copy of one
+    # batch and the D2H copy of another overlap the kernels of a third (the calls are asynchronous; every step still moves
+    # its own query rows in and its own result rows out inside the timed region).
+    N_SLOTS = 3          # measured (tools/e2e_probe.py, 200 steps at C2): 1 stream 0.712 ms/step, 2: 0.525, 3: 0.478, 4: 0.492
+    rows_lo, rows_hi = (h.row_lo, h.row_hi) if (index is not None and args.exchange != "allgather") else (0, B)
+    n_own = rows_hi - rows_lo
+    Qh = [b[rows_lo:rows_hi].cpu().pin_memory() for b in batches]
+    vh = [torch.empty((n_own, k), dtype=torch.float32).pin_memory() for _ in range(N_SLOTS)]
+    ih = [torch.empty((n_own, k), dtype=torch.int64).pin_memory() for _ in range(N_SLOTS)]
     streams = [torch.cuda.Stream(device=device) for _ in range(N_SLOTS)]
-    q_stage = [torch.empty_like(batches[0]) for _ in range(N_SLOTS)]
+    q_stage = [torch.empty((n_own, k_i), dtype=torch.float32, device=device) for _ in range(N_SLOTS)]
 
     def step_e2e(j):
         s = j % N_SLOTS
         with torch.cuda.stream(streams[s]):
-            if index is not None:
-                # item-sharded: H2D of the (replicated) batch, collective search, D2H of the merged result on every rank
-                q_stage[s].copy_(Qh[j % N_BATCHES], non_blocking=True)
-                v, i = index.search(q_stage[s], k)
-                vh[s].copy_(v, non_blocking=True)
-                ih[s].copy_(i, non_blocking=True)
-            else:
+            if index is None:
                 engine.search_host(Qh[j % N_BATCHES], packed, k, vh[s], ih[s], idx_offset=lo, ws_key=f"search_host{s}")
+                return
+            q_stage[s].copy_(Qh[j % N_BATCHES], non_blocking=True)
+            if args.exchange == "allgather":        # replicated batch in, full answer out on every rank
+                v, i = index.search(q_stage[s], k)
+            else:                                   # own block of rows in, NVLink all-gather of the blocks, own rows out
+                v, i = index.search_owned(q_stage[s], B, k)
+            vh[s].copy_(v, non_blocking=True)
+            ih[s].copy_(i, non_blocking=True)
 
     e2e_steps = args.steps
     for j in range(2 * N_SLOTS):
         step_e2e(j)
-    sync_all()
+    h.sync_all()
     e2e_times = []
     for _ in range(3):                     # host-timed (the copies are part of it): median of three passes of `steps` steps
         t0 = time.perf_counter()
         for j in range(e2e_steps):
             step_e2e(j)
         torch.cuda.synchronize()
-        e2e_times.append(max_over_ranks(time.perf_counter() - t0))
-        sync_all()
+        e2e_times.append(h.max_over_ranks(time.perf_counter() - t0))
+        h.sync_all()
     t_e2e = statistics.median(e2e_times)
-    e2e_qps = B * e2e_steps * (world if shard == "queries" else 1) / t_e2e
-    h2d = B * k_i * 4
-    d2h = B * k * (4 + 8)
-    # what the box's host link gives a pinned copy of one step's input / output on its own (CUDA events, best of 5): the e2e
-    # figure cannot exceed B / (h2d / h2d_gbs) when the copy engine is the slowest stage of the pipeline
+    e2e_qps = h.units_per_step() * e2e_steps / t_e2e
+    replicated_io = index is not None and args.exchange == "allgather"
+    io_ranks = world if (replicated_io or (world > 1 and index is None)) else 1
+    h2d = B * k_i * 4 * io_ranks           # bytes over all ranks per step (item-sharded row-block form: each rank moves B/P rows)
+    d2h = B * k * (4 + 8) * io_ranks
+
+    # what the box's host link gives a pinned copy of this rank's share of one step's input / output on its own
     def copy_gbs(dst, src):
         best = 0.0
         for _ in range(5):
@@ -412,23 +555,46 @@ def main():
             best = max(best, src.numel() * src.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
         return best
     h2d_gbs = copy_gbs(q_stage[0], Qh[0])
-    d2h_gbs = copy_gbs(ih[0], out_i)
+    d2h_gbs = copy_gbs(ih[0], h.out_i[:n_own])
 
-    # the host-buffer path must give what the device-resident path gives
-    chk_v, chk_i = engine.score_topk(batches[(e2e_steps - 1) % N_BATCHES], packed, k, idx_offset=lo) if index is None \
-        else index.search(batches[(e2e_steps - 1) % N_BATCHES], k)
+    # the host-facing path must give what the device-resident path gives
+    last = e2e_steps - 1
+    chk_v, chk_i = h.step_device(last)
     torch.cuda.synchronize()
-    assert torch.equal(chk_i.cpu(), ih[(e2e_steps - 1) % N_SLOTS]) and torch.equal(chk_v.cpu(), vh[(e2e_steps - 1) % N_SLOTS]), \
+    assert torch.equal(chk_i.cpu(), ih[last % N_SLOTS]) and torch.equal(chk_v.cpu(), vh[last % N_SLOTS]), \
         "host-buffer result differs from the device-resident result"
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    # ---- multi-GPU: the sharded answer must equal the single-GPU answer (rank 0 builds the whole index) ----
+    sharded_check = None
+    if index is not None:
+        got_v, got_i = index.search_rowblock(batches[0], k) if args.exchange != "allgather" else index.search(batches[0], k)
+        peer_err = [ch.error() for ch in index._channels.values()]
+        if rank == 0:
+            if N <= 2_000_000:
+                E_full, _ = build_index(h.syn, 0, N)
+                packed_full = engine.PackedItems(E_full, args.precision)
+                rows = min(CHECK_ROWS, got_v.shape[0])
+                ref_v, ref_i = engine.score_topk(batches[0][:rows].contiguous(), packed_full, k)
+                same_i = bool(torch.equal(ref_i, got_i[:rows]))
+                max_dv = float((ref_v - got_v[:rows]).abs().max().item())
+                sharded_check = {"rows": rows, "reference": "single-GPU engine.score_topk on the whole index, same precision kind",
+                                 "indices_equal": same_i, "max_abs_value_diff": max_dv, "peer_wait_errors": peer_err}
+                del E_full, packed_full
+                assert same_i and max_dv <= 1e-5 * float(ref_v.abs().max().item()), f"sharded != single-GPU: {sharded_check}"
+            else:
+                sharded_check = {"rows": 0, "note": "whole index not rebuilt at this size; see the n1m run and tests/test_gpu_sharded_nccl.py",
+                                 "peer_wait_errors": peer_err}
+            assert not any(peer_err), f"peer exchange wait timed out: {peer_err}"
+        h.sync_all()
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_src = "measured (MEASURED_PEAKS.json, sustained: the kernel is timed inside a long step loop)"
+        peak_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
         peak_src = "fallback (B200_PROFILING.md)"
-    n_local = hi - lo
+    n_local = h.hi - h.lo
     fused_ms_avg = fused_ms / max(fused_n, 1)
     flops = 2.0 * B * k_i * n_local
     # bytes of E the MAIN kernel streams per launch: both fp16 planes (f32x3), or one 16-bit plane (bf16; f32r streams
@@ -437,23 +603,33 @@ def main():
     alg_bytes = e_bytes + 4 * B * k_i + 12 * B * k
     passes = 3 if args.precision == "f32x3" else 1
     tf = flops / (fused_ms_avg * 1e-3) / 1e12 if fused_n else None
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    # dram__bytes_read.sum + dram__bytes_write.sum of the MAIN kernel, one `ncu --set full` capture per (workload, kind)
-    # (profiles/r1_ncu_fused_c2_f32x3_v8_details.txt); null where no capture was taken
-    # and profiles/r1_ncu_fused_c2_f32r_v16_details.txt
-    NCU_TRAFFIC = {("c2", "f32x3"): 238.13e6 + 16.71e6, ("c2", "f32r"): 110.78e6 + 12.60e6}
+    peak_burst = float(peaks.get("bf16_tflops", 1640.0))
+    peak_sust = float(peaks.get("bf16_tflops_sustained", 1380.0))
+    burst = ms_total < 1000.0                      # a timed loop shorter than 1 s runs at burst clocks / power
+    peak_tf = peak_burst if burst else peak_sust
+    step_tf = flops / (ms_total / args.steps * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    try:                                           # dram bytes of the MAIN kernel from an `ncu --set full` capture of this revision
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.workload}/{args.precision}/{world}")
+        if t:
+            traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+    except Exception:
+        pass
     roofline = {
-        "kernel": "fused_score_topk_kernel (tcgen05 score GEMM + streaming top-k)",
+        "kernel": "fused_score_topk_kernel (tcgen05 score GEMM + streaming top-k), MAIN launch",
         "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (tf / peak_tf) if tf else None,
-        "traffic": NCU_TRAFFIC.get((args.workload, args.precision)) if world == 1 else None, "peak_source": peak_src,
+        "peak_kind": ("burst" if burst else "sustained") + f" (timed loop {ms_total:.0f} ms)", "peak_source": peak_src,
+        "frac_of_burst": (tf / peak_burst) if tf else None, "frac_of_sustained": (tf / peak_sust) if tf else None,
+        "step_achieved": step_tf, "step_frac": step_tf / peak_tf, "step_frac_of_burst": step_tf / peak_burst,
+        "step_frac_of_sustained": step_tf / peak_sust,
+        "traffic": traffic, "traffic_source": traffic_src,
         "launch_ms": fused_ms_avg, "launches_timed": fused_n, "share_of_step": fused_ms / ms_total if ms_total else None,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
         "tensor_passes": passes,
         "tensor_pipe_tflops": (tf * passes) if tf else None,
-        "tensor_pipe_frac": (tf * passes / peak_tf) if tf else None,
-        "note": "achieved/frac count the algorithmic flops 2*B*k_i*N once; kind f32x3 issues 3 f16 tensor passes per product "
-                "(h.h + h.l + l.h), so its tensor pipe runs at tensor_pipe_tflops; kind f32r issues one pass (upper bounds of "
-                "the scores) and re-scores ~k candidates per row in fp32 in a separate kernel (not part of launch_ms)",
+        "note": "achieved / step_achieved count the algorithmic flops 2*B*k_i*N_local of THIS rank once (per-GPU figures); kind f32x3 "
+                "issues 3 f16 tensor passes per product, kind f32r one pass (score upper bounds) + fp32 re-scoring of ~k "
+                "candidates per row in refine_topk_kernel (inside the step, not inside launch_ms)",
         "hbm_gbs_achieved": alg_bytes / (fused_ms_avg * 1e-3) / 1e9 if fused_n else None,
         "hbm_gbs_peak": peaks.get("hbm_gbs"),
     }
@@ -461,35 +637,45 @@ def main():
     line = {
         "metric": "queries/sec (ANNCUR score+top-100)", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak" if shard == "queries" else "strong", "vs_baseline": None,
+        "scaling": "strong" if (shard == "items") else "weak", "vs_baseline": None,
         "dtype": {"f32x3": "f32 (2xfp16 split operands, 3 tcgen05 passes, fp32 accumulate)", "bf16": "bf16",
                   "f32r": "f32 (one f16 tcgen05 pass of rigorous score upper bounds, fp32 FFMA re-scoring of the candidates)"}[args.precision],
         "data": "synthetic", "config": workload_config(args, world, shard),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "anncur_search_host (C ABI, pinned host buffers)" if index is None else "ShardedIndex.search + pinned copies",
-                "passes_s": e2e_times, "h2d_gbs_alone": h2d_gbs, "d2h_gbs_alone": d2h_gbs,
-                "copy_bound_queries_per_s": B / max(h2d / (h2d_gbs * 1e9), d2h / (d2h_gbs * 1e9)) * (world if shard == "queries" else 1)},
-        "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-        "index_build_s": {"pinv": wl["build_s"]["pinv"], "U@R": wl["build_s"]["gemm"], "pack": t_pack},
+                "api": "anncur_search_host (C ABI, pinned host buffers)" if index is None else
+                       ("ShardedIndex.search + pinned copies of the whole batch / answer on every rank" if replicated_io else
+                        "ShardedIndex.search_owned: every rank uploads its B/P rows, NVLink all-gather of the rows, search, "
+                        "exchange, download of the B/P merged rows it owns"),
+                "passes_s": e2e_times, "h2d_gbs_alone_this_rank": h2d_gbs, "d2h_gbs_alone_this_rank": d2h_gbs,
+                "streams": N_SLOTS},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "index_build_s": h.build_s,
     }
+    if sharded_check is not None:
+        line["sharded_equals_single_gpu"] = sharded_check
     if index is None:
         # rows of the last device-resident batch that needed the fallback pass (0 = the fast path served the whole batch)
-        engine.score_topk(batches[0], packed, k, idx_offset=lo, out=(out_v, out_i))
+        engine.score_topk(batches[0], packed, k, idx_offset=lo, out=(h.out_v, h.out_i))
         line["redo_rows_last_batch"] = engine.last_redo_rows(B, packed, k)
 
-    # ---- side measurements (rank 0, single GPU): other precision + recall, CPU baseline -----------------
+    # ---- side measurements ---------------------------------------------------------------------------------
+    if not args.no_extra:
+        # the same in-order work issued over two rotating streams (exchange / tail of batch j under the kernels of batch j+1)
+        ms2, _, _, _, _ = h.time_device(args.steps, 4, streams=2)
+        line["pipelined_2_streams"] = {"value": h.units_per_step() * args.steps / (ms2 * 1e-3), "unit": "queries/s",
+                                       "ms_per_step": ms2 / args.steps}
     if world == 1 and not args.no_extra:
         line["other_precision"] = []
         v_a, i_a = engine.score_topk(batches[0], packed, k)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for other in [p for p in ("f32r", "f32x3", "bf16") if p != args.precision]:
-            packed_o = engine.PackedItems(wl["E"], other)
+            packed_o = engine.PackedItems(h.E, other)
             for j in range(3):
-                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
+                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(h.out_v, h.out_i))
             torch.cuda.synchronize()
             n_o = max(10, args.steps // 4)
             ev0.record()
             for j in range(n_o):
-                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(out_v, out_i))
+                engine.score_topk(batches[j % N_BATCHES], packed_o, k, out=(h.out_v, h.out_i))
             ev1.record()
             torch.cuda.synchronize()
             qps_o = B * n_o / (ev0.elapsed_time(ev1) * 1e-3)
@@ -500,20 +686,39 @@ def main():
             del packed_o
     if world == 1 and rank == 0 and not args.no_cpu:
         rows = cpu_sample_rows(N, B)
-        E_host = wl["E"].cpu()
+        fn, kind = reference_topk_fn()
+        E_host = h.E.cpu()
         Q_host = batches[0][:rows].cpu()
-        cpu_qps, times = cpu_topk_throughput(E_host, Q_host, k, repeats=3)
+        cpu_qps, times = cpu_topk_throughput(fn, E_host, Q_host, k, repeats=3)
         # while the CPU result is at hand: the GPU answer for the same rows must be the reference's answer
-        from oracle import cur_oracle as O
-        ref = O.score_topk(Q_host, E_host, k)
+        ref = fn(Q_host, E_host, k)
         got_v, got_i = engine.score_topk(batches[0][:rows].contiguous(), packed, k)
         dense_scale = ref.values.abs().max(dim=1, keepdim=True).values
         same = (got_i.cpu() == ref.indices).float().mean().item()
         rel = ((got_v.cpu() - ref.values).abs() / dense_scale).max().item()
-        line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{rows} of the {B} queries of one batch x all {N} items, median of 3 after 1 warm-up "
-                                          f"({statistics.median(times):.2f} s each); torch.matmul + torch.topk fp32",
+        line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"{rows} of the {B} queries of one batch x all {N} items (same E and Q as the GPU arm), median of 3 "
+                                          f"after 1 warm-up ({statistics.median(times):.2f} s each); "
+                                          + ("the reference's CURApprox.topk_in_row (oracle/_ref)" if kind == "reference" else "oracle port")
+                                          + ": torch.matmul + torch.topk fp32",
                                 "gpu_vs_cpu_check": {"index_agreement": same, "max_rel_score_err_sorted_lists": rel}}
+        del E_host
+    h.close()
+
+    # ---- the other BASELINE configs, device-resident figure only ---------------------------------------------
+    if args.extras is None:
+        extras = [] if (args.no_extra or args.workload != "n1m") else (["c2", "c4"] if world == 1 else ["c4"])
+    else:
+        extras = [e for e in args.extras.split(",") if e and e != "none"]
+    if extras:
+        line["extras"] = {}
+        for name in extras:
+            try:
+                line["extras"][name] = quick_extra(args, name, rank, local_rank, world, shard, steps=min(args.steps, 100 if name == "c2" else 20))
+            except Exception as exc:                                     # an extra never takes the headline line down
+                line["extras"][name] = {"error": f"{type(exc).__name__}: {exc}"}
+                if world > 1:
+                    raise
 
     if rank == 0:
         emit(line)

@@ -65,7 +65,8 @@ ANNCUR_API const char* anncur_last_error(void);
 /* ---- K1: pseudo-inverse -------------------------------------------------------------------
  * Replaces np.linalg.pinv at eval/matrix_approx_zeshel.py:47,49 (U = pinv(C[row_idxs,:])).
  * A is m x n fp32 (lda), out is n x m fp32 (ldo).  One-sided Jacobi SVD in fp64; singular values
- * <= rcond * s_max are dropped (numpy's rule; the reference uses numpy's default rcond = 1e-15).
+ * <= max(rcond, 8 tol) * s_max are dropped (numpy's rule with a floor at what fp64 sweeps resolve, see
+ * anncur_jacobi_status; the reference uses numpy's default rcond = 1e-15).
  * cond_out (optional, device double[2]) receives {s_max, s_min_kept}. */
 ANNCUR_API size_t anncur_pinv_workspace_bytes(int m, int n);
 ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo,
@@ -76,6 +77,13 @@ ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rco
  * (rank = #{sigma > max(m, n) * eps_fp32 * sigma_max}, counted by the caller).  Workspace: anncur_pinv_workspace_bytes. */
 ANNCUR_API int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out,
                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Outcome of the last anncur_pinv_f32 / anncur_singular_values_f32 that ran on `workspace` (enqueued on `stream`):
+ * status4_out (device double[4]) = {s_max, s_min_kept (pinv only), converged (1 = every column pair orthogonal to the
+ * tolerance within the sweep limit, 0 = the factorisation stopped at the limit and the result must not be trusted),
+ * sweeps done}.  A rank-deficient input is not an error: singular values below max(rcond, 8 tol) * s_max are dropped,
+ * tol = the sweeps' orthogonality tolerance (~4 sqrt(len) eps_fp64) -- fp64 noise values are never inverted. */
+ANNCUR_API int anncur_jacobi_status(const void* workspace, double* status4_out, void* stream);
 
 /* ---- K2 / dense products -------------------------------------------------------------------
  * C[m x n] = A[m x k] . B[k x n], fp32 FFMA accumulate.  Replaces `U @ R`
@@ -179,6 +187,31 @@ ANNCUR_API int anncur_topk_to_keys(const float* vals, const int64_t* idx, int n_
 ANNCUR_API size_t anncur_merge_topk_keys_workspace_bytes(int n_rows);
 ANNCUR_API int anncur_merge_topk_keys(const uint64_t* keys, int n_shards, int n_rows, int k_in, int k_out,
                            float* out_vals, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- candidate exchange of the item-sharded search over NVLink peer memory (north_star: "candidates are
+ * merged after ... over NVLink"; no counterpart in the reference, which is single-process) -------------------------------
+ * Query rows are owned in contiguous blocks (owner o merges rows [o*B/P, (o+1)*B/P)).  anncur_peer_scatter_keys turns this
+ * rank's local top-k (values + global indices) into 64-bit keys and stores every row straight into its OWNER's receive
+ * buffer through the peer mapping, then publishes an epoch flag in every owner; anncur_peer_merge_owned waits for the P
+ * flags of `epoch` and writes the best k_out of the P lists of each owned row.  One "channel" = one buffer of
+ * anncur_peer_channel_bytes per rank, allocated with anncur_peer_alloc (plain cudaMalloc -- the one place the library
+ * allocates: CUDA IPC can only export such memory), exported with anncur_peer_export (64-byte handle, exchanged by the
+ * host, e.g. torch.distributed.all_gather_object) and mapped with anncur_peer_open.  peer_bases[p] = base of rank p's
+ * buffer as mapped in THIS process (own rank: the local pointer).  Calls on one channel must be stream-ordered on every
+ * rank, epochs 1, 2, 3, ...; all ranks pass the same n_rows / k / rows_cap / k_cap. */
+ANNCUR_API size_t anncur_peer_channel_bytes(int world, int rows_cap, int k_cap);
+ANNCUR_API int anncur_peer_alloc(size_t bytes, void** base_out);
+ANNCUR_API int anncur_peer_free(void* base);
+ANNCUR_API int anncur_peer_export(const void* base, void* handle64_out);
+ANNCUR_API int anncur_peer_open(const void* handle64, void** mapped_out);
+ANNCUR_API int anncur_peer_close(void* mapped);
+ANNCUR_API int anncur_peer_scatter_keys(const float* vals, const int64_t* idx, int n_rows, int k, int rank, int world,
+                             int rows_cap, int k_cap, uint32_t epoch, void* const* peer_bases, void* stream);
+ANNCUR_API int anncur_peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int rows_cap, int k_cap,
+                            int k_out, uint32_t epoch, float* out_vals, int64_t* out_idx, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* 0 = every wait so far was served; 1 + s = the wait for sender s timed out (~10 s) and the merged rows are invalid. */
+ANNCUR_API int anncur_peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, void* stream);
 
 /* ---- K5+K6: rerank the retrieved items by exact score, then overlap with the exact top-k -----
  * Replaces the per-query loop body at eval/run_retrieval_eval_wrt_exact_crossenc.py:108-113 /

@@ -21,6 +21,9 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("ANNCUR_REFERENCE_ROOT", "/root/reference")
+# verbatim copy of the ONE reference file the timed path lives in, made by oracle/build_ref.py (git-ignored, travels to
+# the GPU box with the snapshot like a built .so) -- what `bench.py --impl reference` and its cpu_baseline leg execute
+LOCAL_REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def reference_available():
@@ -164,3 +167,28 @@ def load_reference():
         eval_approx_score_mat=split.eval_approx_score_mat,
         modules=types.SimpleNamespace(mat=mat, utils=utils, sweep=sweep, split=split),
     )
+
+
+def local_reference_available():
+    return os.path.isfile(os.path.join(LOCAL_REF_ROOT, "eval", "matrix_approx_zeshel.py"))
+
+
+def load_reference_curapprox():
+    """The reference's own ``CURApprox`` class (eval/matrix_approx_zeshel.py:20-126) from oracle/_ref, executed verbatim with
+    asserts stripped (see the module docstring), or None when oracle/_ref has not been built.  Loaded under a private module
+    name so that it never collides with the in-container reference import above."""
+    if not local_reference_available():
+        return None
+    _stand_in("IPython", embed=lambda *a, **k: None)
+    plt = _stand_in("matplotlib.pyplot")
+    _stand_in("matplotlib", pyplot=plt)
+    name = "_anncur_ref_matrix_approx_zeshel"
+    if name in sys.modules:
+        return sys.modules[name].CURApprox
+    path = os.path.join(LOCAL_REF_ROOT, "eval", "matrix_approx_zeshel.py")
+    loader = _StripAssertsLoader(name, path)
+    spec = importlib.util.spec_from_loader(name, loader, origin=path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    loader.exec_module(mod)
+    return mod.CURApprox

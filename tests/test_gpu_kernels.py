@@ -108,6 +108,46 @@ def test_pinv_drops_null_directions(eng):
     assert np.linalg.norm(P - ref) / np.linalg.norm(ref) < 1e-4
 
 
+def test_pinv_rank_deficient_anchor_columns(eng):
+    """Duplicated anchor columns (exactly dependent in fp32) and a column that is an fp32-rounded sum of two others.
+    With the default rcond = 1e-15 the fp64 Jacobi values of the null directions (~1e-16 s_max) must be DROPPED, not
+    inverted to 1e32: the result is the minimum-norm pseudo-inverse (the cutoff is floored at what the sweeps
+    resolve).  numpy's fp32 LAPACK path keeps its ~1e-7 noise values in this case, so the comparison is with the fp64
+    pinv at a cutoff between the noise and the data."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((120, 40)).astype(np.float32)
+    A[:, 7] = A[:, 3]                                   # exact duplicate
+    A[:, 21] = A[:, 3]                                  # and again
+    A[:, 30] = 2.0 * A[:, 11]                           # exact multiple (power of two: no rounding)
+    P = eng.pinv(torch.from_numpy(A).cuda()).cpu().numpy().astype(np.float64)
+    A64 = A.astype(np.float64)
+    ref = np.linalg.pinv(A64, rcond=1e-10)
+    assert np.abs(P).max() < 1e3 * np.abs(ref).max()    # nothing was inverted as 1 / noise
+    assert np.linalg.norm(P - ref) / np.linalg.norm(ref) < 1e-5
+    # Moore-Penrose identities
+    assert np.linalg.norm(A64 @ P @ A64 - A64) < 1e-5 * np.linalg.norm(A64)
+    assert np.linalg.norm(P @ A64 @ P - P) < 1e-5 * np.linalg.norm(P)
+    # the same through the wide orientation (k_q < k_i)
+    Pw = eng.pinv(torch.from_numpy(np.ascontiguousarray(A.T)).cuda()).cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(Pw - ref.T) / np.linalg.norm(ref) < 1e-5
+    # all-zero input: every singular value is dropped
+    assert float(eng.pinv(torch.zeros(9, 4).cuda()).abs().max()) == 0.0
+
+
+def test_jacobi_status_reports_convergence(eng):
+    import ctypes as C
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    A = torch.from_numpy(O.synthetic_scores(300, 64, rank=32, seed=2)).cuda()
+    eng.pinv(A)                                         # raises if the sweeps had not converged
+    ws = eng.WORKSPACE.get("pinv", lib.anncur_pinv_workspace_bytes(300, 64), A.device)
+    st = torch.zeros(4, dtype=torch.float64, device="cuda")
+    _lib.check(lib.anncur_jacobi_status(C.c_void_p(ws.data_ptr()), C.c_void_p(st.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    s_max, s_min, conv, sweeps = st.tolist()
+    s = np.linalg.svd(A.cpu().numpy().astype(np.float64), compute_uv=False)
+    assert conv == 1.0 and 1 <= sweeps <= 30 and abs(s_max - s[0]) < 1e-6 * s[0] and abs(s_min - s[-1]) < 1e-4 * s[-1] + 1e-9 * s[0]
+
+
 # ---------------------------------------------------------------------------------------------- FFMA score + top-k
 @pytest.mark.parametrize("B,K,N,k", [(1, 50, 10000, 100), (200, 500, 20000, 100), (37, 7, 300, 300), (9, 64, 5000, 1500)])
 def test_score_topk_f32_matches_oracle(eng, B, K, N, k):

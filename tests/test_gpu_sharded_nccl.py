@@ -28,10 +28,23 @@ def _worker(rank, world, port, ret):
         E = torch.from_numpy(rng.standard_normal((96, 150_001), dtype=np.float32)).cuda()
         Q = torch.from_numpy(rng.standard_normal((300, 96), dtype=np.float32)).cuda()
         ok = 1
+        full = engine.PackedItems(E)
         for k in (10, 100):
-            v, i = ShardedIndex.from_full(E).search(Q, k)
-            rv, ri = engine.score_topk(Q, engine.PackedItems(E), k)
+            rv, ri = engine.score_topk(Q, full, k)
+            index = ShardedIndex.from_full(E)                          # all-gather form: the full answer on every rank
+            v, i = index.search(Q, k)
             ok &= int(torch.equal(i, ri) and torch.allclose(v, rv, rtol=1e-5, atol=1e-5))
+            r0, r1 = index.row_block(Q.shape[0])
+            for exchange in ("nccl", "p2p"):                           # row-block forms: all_to_all_single / NVLink peer stores
+                ix = ShardedIndex.from_full(E, exchange=exchange)
+                for _ in range(3):                                     # both parity buffers of the peer channel
+                    v, i = ix.search_rowblock(Q, k)
+                    ok &= int(torch.equal(i, ri[r0:r1]) and torch.allclose(v, rv[r0:r1], rtol=1e-5, atol=1e-5))
+                v, i = ix.search_owned(Q[r0:r1].contiguous(), Q.shape[0], k)
+                ok &= int(torch.equal(i, ri[r0:r1]) and torch.allclose(v, rv[r0:r1], rtol=1e-5, atol=1e-5))
+                if exchange == "p2p":
+                    ok &= int(all(ch.error() == 0 for ch in ix._channels.values()))
+                ix.close()
         out = torch.tensor([ok], device="cuda")
         dist.all_reduce(out, op=dist.ReduceOp.MIN)
         if rank == 0:

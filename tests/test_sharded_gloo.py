@@ -44,6 +44,13 @@ def _worker(rank, world, port, k, ret):
         v, i = index.search(Q, k)
         ref = O.score_topk(Q, E, k)
         ok = torch.equal(i, ref.indices) and torch.allclose(v, ref.values)
+        # row-block form: every rank ends with the rows it owns (all-to-all by row block), from a replicated batch ...
+        r0, r1 = index.row_block(Q.shape[0])
+        v2, i2 = index.search_rowblock(Q, k)
+        ok = ok and torch.equal(i2, ref.indices[r0:r1]) and torch.allclose(v2, ref.values[r0:r1])
+        # ... and from a batch that arrives distributed (each rank passes its own rows; ragged blocks: 9 rows over 2 / 3 ranks)
+        v3, i3 = index.search_owned(Q[r0:r1].contiguous(), Q.shape[0], k)
+        ok = ok and torch.equal(i3, ref.indices[r0:r1]) and torch.allclose(v3, ref.values[r0:r1])
         out = torch.tensor([1 if ok else 0])
         dist.all_reduce(out, op=dist.ReduceOp.MIN)
         if rank == 0:
