@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libanncur_b200.so")
 
 ABI_VERSION = 1
 KIND_F32X3, KIND_BF16, KIND_F32R = 0, 1, 2
-MAX_K, MAX_K_FUSED = 2048, 1024
+MAX_K, MAX_K_FUSED, MAX_K_DIM_F32R = 2048, 1024, 8192
 E_INVALID, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
 
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double

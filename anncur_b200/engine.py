@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import KIND_BF16, KIND_F32R, KIND_F32X3, MAX_K, MAX_K_FUSED  # noqa: F401
+from ._lib import KIND_BF16, KIND_F32R, KIND_F32X3, MAX_K, MAX_K_DIM_F32R, MAX_K_FUSED  # noqa: F401
 
 KINDS = {"f32r": KIND_F32R, "f32x3": KIND_F32X3, "bf16": KIND_BF16}
 

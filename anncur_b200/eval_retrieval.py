@@ -187,3 +187,77 @@ def fixed_split_cur_eval(train_scores, test_scores, n_ent_anchors_vals, top_k_va
             for k, metrics in res.items():
                 out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_m={n_train}_anc_n_e={k_i}"] = metrics
     return out
+
+
+def _grid_eval(test, v, i, top_k_vals, top_k_retvr_vals, n_ents):
+    """{k_r: {k: metrics}} for every retrieved-list length from ONE retrieval (v, i) at the largest k_r: top-k_r lists are
+    prefixes of it."""
+    out = {}
+    for k_r in top_k_retvr_vals:
+        if k_r > n_ents or k_r <= 0:
+            continue
+        out[k_r] = eval_approx_score_mat_for_all_topk(test, None, top_k_vals, k_r,
+                                                      approx_topk=(v[:, :k_r].contiguous(), i[:, :k_r].contiguous()))
+    return out
+
+
+def fixed_split_embed_eval(test_scores, query_embeds, item_embeds, n_train, n_ent_anchors_vals, top_k_vals, top_k_retvr_vals,
+                           *, precision="f32r"):
+    """The ``bienc`` / ``tfidf`` / ``fixed_anc_ent`` methods of run_eval_method
+    (..._w_fixed_train_test_splits.py:257-284, :305-325, :360-385 + :403-429): the approximate score matrix is
+    ``query_embeds @ item_embeds.T`` (:283, :324, :383) whatever the anchor count, so it is evaluated once per k_r and the
+    result is entered under every ``anc_n_e`` key, as the reference does (:411-417).  Same fused tcgen05 score + top-k
+    kernel as ANNCUR, with K = the embedding dimension; the (n_test x N) approximate matrix is never formed."""
+    engine.require_cuda()
+    test = engine._f32(test_scores)
+    Q = engine._f32(query_embeds, device=test.device)
+    Et = engine._f32(item_embeds, device=test.device)                   # N x d, as the reference holds them
+    n_ents = test.shape[1]
+    assert Et.shape[0] == n_ents and Q.shape[0] == test.shape[0] and Q.shape[1] == Et.shape[1], (test.shape, Q.shape, Et.shape)
+    max_kr = max([kr for kr in top_k_retvr_vals if kr <= n_ents] + [0])
+    out = {}
+    if max_kr == 0:
+        return out
+    d = int(Et.shape[1])
+    if precision == "f32" or max_kr > engine.MAX_K_FUSED or (precision == "f32r" and d > engine.MAX_K_DIM_F32R):
+        v, i = engine.score_topk_f32(Q, Et.t().contiguous(), max_kr)
+    else:
+        v, i = engine.score_topk(Q, engine.PackedItems(Et.t().contiguous(), precision), max_kr)
+    for k_r, res in _grid_eval(test, v, i, top_k_vals, top_k_retvr_vals, n_ents).items():
+        for k, metrics in res.items():
+            for k_i in n_ent_anchors_vals:
+                out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_m={n_train}_anc_n_e={k_i}"] = metrics
+    return out
+
+
+def fixed_split_fixed_anc_cur_eval(test_scores, ent_to_fixed_anchor_scores, n_train, n_ent_anchors_vals, top_k_vals,
+                                   top_k_retvr_vals, *, seed=0, precision="f32r", only_k_i=None):
+    """The ``fixed_anc_ent_cur`` method (..._w_fixed_train_test_splits.py:327-358): CUR with the entity-to-fixed-anchor
+    score matrix in the role of the anchor-query rows, R = ent_to_fixed_anchor_scores.T (n_fixed x N); per anchor count one
+    generator draw (seed 0, ONE generator across the grid :341-346), U = pinv(R[:, anchors]) (:349), E = U @ R (:350) and the
+    test scores against the anchors as queries (:353-356)."""
+    engine.require_cuda()
+    test = engine._f32(test_scores)
+    R = engine._f32(ent_to_fixed_anchor_scores, device=test.device).t().contiguous()       # n_fixed x N
+    n_fixed, n_ents = R.shape
+    assert test.shape[1] == n_ents
+    rng = np.random.default_rng(seed=seed)
+    max_kr = max([kr for kr in top_k_retvr_vals if kr <= n_ents] + [0])
+    out = {}
+    for k_i in n_ent_anchors_vals:
+        anc = sorted(rng.choice(n_ents, size=k_i, replace=False))
+        if (only_k_i is not None and k_i not in only_k_i) or max_kr == 0:
+            continue
+        n_test = test.shape[0]
+        if k_i == 0:                                    # empty anchor set: all approximate scores are 0 (see fixed_split_cur_eval)
+            i = torch.arange(max_kr, device=test.device, dtype=torch.int64).repeat(n_test, 1)
+            v = torch.zeros((n_test, max_kr), device=test.device)
+        else:
+            anc_t = torch.as_tensor(np.asarray(anc, dtype=np.int64), device=test.device)
+            cur = CURApprox(row_idxs=np.arange(n_fixed), col_idxs=anc, rows=R, cols=R[:, anc_t], approx_preference="rows",
+                            precision=precision)
+            v, i = cur.topk_in_row(test[:, anc_t], max_kr)
+        for k_r, res in _grid_eval(test, v, i, top_k_vals, top_k_retvr_vals, n_ents).items():
+            for k, metrics in res.items():
+                out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_m={n_train}_anc_n_e={k_i}"] = metrics
+    return out
