@@ -20,6 +20,7 @@ PROTOTYPES = {
     "anncur_pinv_workspace_bytes": (_sz, [_i, _i]),
     "anncur_pinv_f32": (_i, [_vp, _i, _i, _i, _d, _vp, _i, _vp, _vp, _sz, _vp]),
     "anncur_singular_values_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "anncur_orthonormalize_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "anncur_jacobi_status": (_i, [_vp, _vp, _vp]),
     "anncur_gemm_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "anncur_packed_items_bytes": (_sz, [_i64, _i, _i]),

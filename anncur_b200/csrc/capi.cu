@@ -71,6 +71,15 @@ int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* si
     return singular_values_f32(A, m, n, lda, sigma_out, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+int anncur_orthonormalize_f32(const float* A, int m, int n, int lda, float* Q, int ldq, double* sigma_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(m >= 0 && n >= 0, "orthonormalize: negative shape %d x %d", m, n);
+    if (m == 0 || n == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(A && Q && workspace, "orthonormalize: null pointer");
+    ANNCUR_REQUIRE(lda >= n && ldq >= n, "orthonormalize: lda %d or ldq %d < n %d", lda, ldq, n);
+    return orthonormalize_f32(A, m, n, lda, Q, ldq, sigma_out, workspace, workspace_bytes, cudaStream_t(stream));
+}
+
 int anncur_jacobi_status(const void* workspace, double* status4_out, void* stream) {
     ANNCUR_REQUIRE(workspace && status4_out, "jacobi_status: null pointer");
     return jacobi_status(workspace, status4_out, cudaStream_t(stream));

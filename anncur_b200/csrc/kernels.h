@@ -37,6 +37,8 @@ int recon_error(const float* Q, int64_t ldq, const float* E, int64_t lde, const 
 size_t pinv_workspace_bytes(int m, int n);
 int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo, double* cond_out,
              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int orthonormalize_f32(const float* A, int m, int n, int lda, float* Q, int ldq, double* sigma_out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 int jacobi_status(const void* workspace, double* status4_out, cudaStream_t stream);
 int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace, size_t workspace_bytes,
                         cudaStream_t stream);

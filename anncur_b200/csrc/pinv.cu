@@ -336,6 +336,53 @@ int pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, in
     return ANNCUR_OK;
 }
 
+__global__ void jacobi_sigma_kernel(const double* __restrict__ G, int len, int p, double* __restrict__ sigma);
+
+// Q[r][j] = G[j][r] / |g_j| (0 for columns below the cutoff): after the sweeps the columns of G = T V are mutually
+// orthogonal, so these are the left singular vectors of T -- an orthonormal basis of its column space.  sigma[j] = |g_j|
+// was written by jacobi_sigma_kernel; columns below cutoff_rel * max_j sigma[j] (null directions) come out as zero.
+__global__ void __launch_bounds__(256)
+orth_export_kernel(const double* __restrict__ G, int len, int p, double cutoff_rel, const double* __restrict__ sigma,
+                   float* __restrict__ Q, int ldq) {
+    __shared__ double red[8];
+    __shared__ double s_max;
+    double m = 0.0;
+    for (int t = threadIdx.x; t < p; t += blockDim.x) m = fmax(m, sigma[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+        s_max = m;
+    }
+    __syncthreads();
+    const int j = blockIdx.x;
+    const double* g = G + int64_t(j) * len;
+    const double nrm = sigma[j];
+    const double inv = (nrm > cutoff_rel * s_max && nrm > 0.0) ? 1.0 / nrm : 0.0;
+    for (int r = threadIdx.x; r < len; r += blockDim.x) Q[int64_t(r) * ldq + j] = float(g[r] * inv);
+}
+
+// Orthonormal basis of the column space of a TALL matrix A (m x n, m >= n): Q (m x n fp32, ldq), columns = left singular
+// vectors (unsorted), zero columns for singular values below ~1e-12 of the largest; sigma_out (optional, n fp64).  The
+// range-finder step of the randomised rank analysis (eval/compute_m2e_matrix_ranks.py:44-53 at sizes where a full SVD is
+// out of reach).
+int orthonormalize_f32(const float* A, int m, int n, int lda, float* Q, int ldq, double* sigma_out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return ANNCUR_OK;
+    if (m < n) { set_error("orthonormalize: matrix must be tall (m = %d < n = %d)", m, n); return ANNCUR_E_INVALID; }
+    int rc = jacobi_factor(A, m, n, lda, workspace, workspace_bytes, stream);
+    if (rc != ANNCUR_OK) return rc;
+    double* G = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+    double* sig = sigma_out ? sigma_out : G + size_t(m) * n + size_t(n) * n;          // the weights slot of the workspace
+    jacobi_sigma_kernel<<<(n + 7) / 8, 256, 0, stream>>>(G, m, n, sig);
+    ANNCUR_LAUNCH_OK("jacobi_sigma_kernel");
+    orth_export_kernel<<<n, 256, 0, stream>>>(G, m, n, 8.0 * jacobi_tol(m), sig, Q, ldq);
+    ANNCUR_LAUNCH_OK("orth_export_kernel");
+    return ANNCUR_OK;
+}
+
 // Singular values of A (m x n fp32) in fp64, unsorted: the same Jacobi factorisation without the inverse.
 // Replaces the SVD inside np.linalg.matrix_rank (eval/compute_m2e_matrix_ranks.py:44-53).
 int singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out, void* workspace, size_t workspace_bytes,

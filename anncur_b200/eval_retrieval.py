@@ -261,3 +261,53 @@ def fixed_split_fixed_anc_cur_eval(test_scores, ent_to_fixed_anchor_scores, n_tr
             for k, metrics in res.items():
                 out.setdefault(f"top_k={k}", {}).setdefault(f"k_retvr={k_r}", {})[f"anc_n_m={n_train}_anc_n_e={k_i}"] = metrics
     return out
+
+
+def run_approx_eval(approx_method, all_ment_to_ent_scores, precomp_approx_ment_to_ent_scores, n_ment_anchors, n_ent_anchors,
+                    top_k, top_k_retvr, n_seeds, *, precision="f32r"):
+    """eval/run_retrieval_eval_wrt_exact_crossenc.py:162-201: seeds 0..n_seeds-1, metric-wise mean."""
+    acc = {}
+    for seed in range(n_seeds):
+        res = run_approx_eval_w_seed(approx_method, all_ment_to_ent_scores, n_ment_anchors, n_ent_anchors, top_k, top_k_retvr,
+                                     seed, precomp_approx_ment_to_ent_scores, precision=precision)
+        for ment_type, res_dict in res.items():
+            for metric, val in res_dict.items():
+                acc.setdefault(ment_type, {}).setdefault(metric, []).append(float(val))
+    return {mt: {m: float(np.mean(v)) for m, v in d.items()} for mt, d in acc.items()}
+
+
+def sweep_grids(total_n_ment, total_n_ent):
+    """The anchor grids of the random-anchor sweep (eval/run_retrieval_eval_wrt_exact_crossenc.py:227-233)."""
+    n_ment_anchors_vals = [v for v in [50, 100, 200, 500, 1000, 2000, 5000] if v <= total_n_ment]
+    n_ent_anchors_vals = [v for v in [50, 100, 200, 500, 1000, 2000] if v < total_n_ent] + [total_n_ent]
+    return n_ment_anchors_vals, n_ent_anchors_vals
+
+
+def run_sweep(all_ment_to_ent_scores, n_seeds=1, eval_methods=("cur", "cur_oracle"), top_k_vals=(10,), top_k_retr_vals=(500,),
+              n_ment_anchors_vals=None, n_ent_anchors_vals=None, *, precision="f32r", progress=None):
+    """The grid loop of the sweep driver's ``run`` (eval/run_retrieval_eval_wrt_exact_crossenc.py:204-371) for the CUR
+    methods: eval_res[method]["top_k=k"]["k_retvr=k_r"]["anc_n_m=k_q~anc_n_e=k_i"] = seed-averaged metrics incl.
+    ``approx_error`` / ``approx_error_relative`` for anchor / non_anchor / all rows, + ``other_args`` (:373-376 layout)."""
+    A = engine._f32(all_ment_to_ent_scores)
+    total_n_ment, total_n_ent = A.shape
+    g_m, g_e = sweep_grids(total_n_ment, total_n_ent)
+    n_ment_anchors_vals = list(n_ment_anchors_vals) if n_ment_anchors_vals is not None else g_m
+    n_ent_anchors_vals = list(n_ent_anchors_vals) if n_ent_anchors_vals is not None else g_e
+    eval_res = {}
+    for method in eval_methods:
+        if method not in ("cur", "cur_oracle"):
+            raise NotImplementedError(f"Method = {method} not supported")
+        for top_k in top_k_vals:
+            for k_r in top_k_retr_vals:
+                if k_r < top_k or k_r > total_n_ent:                                   # :347-348
+                    continue
+                for k_q in n_ment_anchors_vals:
+                    for k_i in n_ent_anchors_vals:
+                        ans = run_approx_eval(method, A, None, k_q, k_i, int(top_k), int(k_r), n_seeds, precision=precision)
+                        eval_res.setdefault(method, {}).setdefault(f"top_k={top_k}", {}).setdefault(f"k_retvr={k_r}", {})[
+                            f"anc_n_m={k_q}~anc_n_e={k_i}"] = ans
+                        if progress is not None:
+                            progress(method, top_k, k_r, k_q, k_i, ans)
+    eval_res["other_args"] = {"top_k_vals": list(top_k_vals), "top_k_retr_vals": list(top_k_retr_vals),
+                              "n_ent_anchors_vals": n_ent_anchors_vals, "n_ment_anchors_vals": n_ment_anchors_vals}
+    return eval_res

@@ -554,15 +554,14 @@ def main():
             torch.cuda.synchronize()
             best = max(best, src.numel() * src.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
         return best
-    h2d_gbs = copy_gbs(q_stage[0], Qh[0])
-    d2h_gbs = copy_gbs(ih[0], h.out_i[:n_own])
-
     # the host-facing path must give what the device-resident path gives
     last = e2e_steps - 1
     chk_v, chk_i = h.step_device(last)
     torch.cuda.synchronize()
     assert torch.equal(chk_i.cpu(), ih[last % N_SLOTS]) and torch.equal(chk_v.cpu(), vh[last % N_SLOTS]), \
         "host-buffer result differs from the device-resident result"
+    h2d_gbs = copy_gbs(q_stage[0], Qh[0])
+    d2h_gbs = copy_gbs(ih[0], h.out_i[:n_own])             # (the result buffers are not needed any more)
 
     # ---- multi-GPU: the sharded answer must equal the single-GPU answer (rank 0 builds the whole index) ----
     sharded_check = None

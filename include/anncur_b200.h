@@ -78,6 +78,14 @@ ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rco
 ANNCUR_API int anncur_singular_values_f32(const float* A, int m, int n, int lda, double* sigma_out,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Orthonormal basis of the column space of a TALL matrix A (m x n fp32, m >= n): Q (m x n fp32, ldq) = its left singular
+ * vectors (unsorted; zero columns where A is rank-deficient), sigma_out (optional, device double[n]) the matching
+ * singular values.  The range-finder step of the randomised rank analysis that replaces np.linalg.matrix_rank
+ * (eval/compute_m2e_matrix_ranks.py:44-53) where a full SVD is out of reach (BASELINE configs[4]: 10k x 1M).
+ * Workspace: anncur_pinv_workspace_bytes(m, n). */
+ANNCUR_API int anncur_orthonormalize_f32(const float* A, int m, int n, int lda, float* Q, int ldq, double* sigma_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Outcome of the last anncur_pinv_f32 / anncur_singular_values_f32 that ran on `workspace` (enqueued on `stream`):
  * status4_out (device double[4]) = {s_max, s_min_kept (pinv only), converged (1 = every column pair orthogonal to the
  * tolerance within the sweep limit, 0 = the factorisation stopped at the limit and the result must not be trusted),

@@ -306,6 +306,34 @@ def fixed_split_cur_scores(train_scores, test_scores, n_ent_anchors_vals, seed):
     return out
 
 
+def fixed_anc_ent_scores(test_scores, ent_to_ent_scores, topk_ents_row0, n_fixed_anc_ent):
+    """..._w_fixed_train_test_splits.py:321-324 (method ``fixed_anc_ent``; ``bienc`` :283 and ``tfidf`` :383 are the same
+    product with model embeddings): entities are embedded by their scores against the first n fixed anchor entities,
+    mentions by their exact scores against the same anchors; approx = mention_embeds @ ent_embeds.T."""
+    test_scores = torch.as_tensor(test_scores)
+    anchor_ent_idxs = _as_index(np.asarray(topk_ents_row0)[:n_fixed_anc_ent])          # :321
+    ent_embeds = torch.as_tensor(ent_to_ent_scores)[:, :n_fixed_anc_ent]                # :322
+    mention_embeds = test_scores[:, anchor_ent_idxs]                                    # :323
+    return mention_embeds @ ent_embeds.T                                                # :324
+
+
+def fixed_anc_ent_cur_scores(test_scores, ent_to_ent_scores, n_fixed_anc_ent, n_ent_anchors_vals, seed=0):
+    """..._w_fixed_train_test_splits.py:340-358 (method ``fixed_anc_ent_cur``): R = the dump transposed (n_fixed x N); ONE
+    generator (seed 0) across the anchor-count grid; U = pinv(R[:, anchors]) (numpy, fp32), approx = test[:, anchors] @ (U @ R).
+    Returns {n_anc_ent: approx test scores}."""
+    test_scores = torch.as_tensor(test_scores)
+    R = torch.as_tensor(ent_to_ent_scores)[:, :n_fixed_anc_ent].T                       # :340
+    n_ents = R.shape[1]
+    rng = np.random.default_rng(seed=seed)                                              # :342
+    out = {}
+    for n_anc_ent in n_ent_anchors_vals:
+        anc = sorted(rng.choice(n_ents, size=n_anc_ent, replace=False))                 # :347
+        idx = _as_index(anc)
+        U = torch.tensor(np.linalg.pinv(R[:, idx]))                                     # :349-350
+        out[n_anc_ent] = test_scores[:, idx] @ (U @ R)                                  # :351-357
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # sharded search (SURVEY.md section 8e) -- restated on CPU so the merge can be checked
 # --------------------------------------------------------------------------------------------

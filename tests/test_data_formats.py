@@ -131,3 +131,148 @@ def test_cli_end_to_end_writes_reference_layout(tmp_path, gold, dump):
     want = c["eval_res_common_frac_mean_std"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"][0]
     got = d["seed=0"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"]["exact_vs_reranked_approx_retvr~common_frac_mean"]
     assert abs(got - want) <= 0.03
+
+
+# ---- the other approximators of the fixed-split eval and the e2e dump they read (8f-2) ----------------------
+@pytest.fixture(scope="module")
+def methods_gold():
+    golden_dir = GOLD
+    with open(os.path.join(golden_dir, "methods.json")) as f:
+        g = json.load(f)
+    z = np.load(os.path.join(golden_dir, "methods_inputs.npz"))
+    g["ent_to_ent_scores"], g["topk_ents"] = z["ent_to_ent_scores"], z["topk_ents"]
+    return g
+
+
+def test_e2e_pickle_roundtrip_and_schema(tmp_path, methods_gold):
+    g = methods_gold
+    path = str(tmp_path / "e2e" / "ent_to_ent.pkl")
+    F.save_e2e_pickle(path, F.make_e2e_dict(g["ent_to_ent_scores"], g["topk_ents"]))
+    import pickle
+    raw = pickle.load(open(path, "rb"))
+    assert sorted(raw) == ["ent_to_ent_scores", "topk_ents"]               # what the reference reads (:313-319)
+    assert torch.is_tensor(raw["ent_to_ent_scores"]) and np.asarray(raw["topk_ents"]).shape == (1, 40)
+    emb, anc = F.load_e2e_pickle(path, 25)
+    assert emb.shape == (1100, 25) and emb.dtype == torch.float32 and anc.shape == (25,) and anc.dtype == np.int64
+    assert np.array_equal(emb.numpy(), g["ent_to_ent_scores"][:, :25]) and np.array_equal(anc, g["topk_ents"][0][:25])
+    assert F.load_e2e_pickle(path)[0].shape == (1100, 40)
+    # a 1-D anchor list is promoted to the (1 x n) layout; a score dump is refused
+    assert F.make_e2e_dict(g["ent_to_ent_scores"], g["topk_ents"][0])["topk_ents"].shape == (1, 40)
+    F.save_m2e_pickle(str(tmp_path / "m2e.pkl"), F.make_m2e_dict(np.zeros((2, 3), np.float32), [{}, {}], [[1], [2]]))
+    with pytest.raises(KeyError):
+        F.load_e2e_pickle(str(tmp_path / "m2e.pkl"))
+
+
+def test_oracle_other_methods_match_the_reference_golden(methods_gold, gold, dump):
+    """Pins the oracle's restatement of fixed_anc_ent / fixed_anc_ent_cur to the reference's run_eval_method output
+    (oracle/make_golden_methods.py) on a sample of grid points -- CPU only."""
+    from oracle import cur_oracle as O
+    g = methods_gold
+    a = g["split_args"]
+    idx = [i for n, s, i in F.split_indices(64, a["num_train_ment_vals"], a["num_splits"], a["seed"], a["dev_frac"]) if n == 30 and s == 0][0]
+    test = dump["ment_to_ent_scores"][idx["test"], :]
+    n_fixed = g["n_fixed_anc_ent"]
+    top_k_vals = [1, 10, 50, 100]
+    approx = O.fixed_anc_ent_scores(test, g["ent_to_ent_scores"], g["topk_ents"][0], n_fixed)
+    want = g["fixed_anc_ent"]["eval_res_common_frac_mean_std"]
+    for k_r in (10, 100, 450, 1000):
+        res = O.eval_approx_score_mat_for_all_topk(test, approx, top_k_vals, k_r)
+        for k, m in res.items():
+            for an in ("anc_n_m=30_anc_n_e=0", "anc_n_m=30_anc_n_e=500"):           # one evaluation entered under every key (:411-417)
+                mean, std = want[f"top_k={k}"][f"k_retvr={k_r}"][an]
+                assert abs(m["exact_vs_reranked_approx_retvr~common_frac_mean"] - mean) < 1e-6
+                assert abs(m["exact_vs_reranked_approx_retvr~common_frac_std"] - std) < 1e-6
+    ki_all = g["fixed_anc_ent_cur"]["retrieval_params"]["n_ent_anchors_vals"]
+    approx_by_ki = O.fixed_anc_ent_cur_scores(test, g["ent_to_ent_scores"], n_fixed, ki_all, seed=0)
+    want = g["fixed_anc_ent_cur"]["eval_res_common_frac_mean_std"]
+    for k_i in (10, 25, 90, 500, 1100):
+        for k_r in (50, 500):
+            res = O.eval_approx_score_mat_for_all_topk(test, approx_by_ki[k_i], top_k_vals, k_r)
+            for k, m in res.items():
+                mean, std = want[f"top_k={k}"][f"k_retvr={k_r}"][f"anc_n_m=30_anc_n_e={k_i}"]
+                assert abs(m["exact_vs_reranked_approx_retvr~common_frac_mean"] - mean) < 1e-6, (k_i, k_r, k)
+
+
+def _compare_grid(res, want, skip_ki=(0,), tol_frac=0.02, only_ki=None):
+    n_cmp, n_bad, worst = 0, 0, 0.0
+    for tk, v in want.items():
+        for kr, v2 in v.items():
+            for an, (mean, std) in v2.items():
+                k_i = int(an.split("anc_n_e=")[1])
+                if k_i in skip_ki or (only_ki is not None and k_i not in only_ki):
+                    continue
+                got = res[tk][kr][an]["exact_vs_reranked_approx_retvr~common_frac_mean"]
+                n_cmp += 1
+                worst = max(worst, abs(got - mean))
+                n_bad += abs(got - mean) > 1e-3
+    return n_cmp, n_bad, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["fixed_anc_ent", "fixed_anc_ent_cur"])
+def test_other_methods_on_split_files_match_reference_results(tmp_path, gold, dump, methods_gold, method):
+    """run_eval_method(<method>) of the reference on its own split files + e2e dump vs ours through the fused kernel (GPU)."""
+    g = methods_gold
+    a = gold["splits"]["args"]
+    F.write_splits(dump, a["num_train_ment_vals"], a["num_splits"], a["seed"], a["dev_frac"], str(tmp_path))
+    e2e = str(tmp_path / "e2e.pkl")
+    F.save_e2e_pickle(e2e, F.make_e2e_dict(g["ent_to_ent_scores"], g["topk_ents"]))
+    only = None if method == "fixed_anc_ent" else [10, 20, 25, 45, 100, 500, 700, 1000, 1100]
+    res, params = F.run_eval_method(method, str(tmp_path / g["test"]), str(tmp_path / g["train"]),
+                                    fixed_anc_ent_args={"e2e_fname": e2e, "n_fixed_anc_ent": g["n_fixed_anc_ent"]},
+                                    cur_args={"seed": 0}, n_ent_anchors_vals=only)
+    assert params == g[method]["retrieval_params"]
+    # k_i = 0 under fixed_anc_ent_cur is an all-zero approximation (pure ties; torch.topk's order is unspecified) -> skipped there;
+    # fixed_anc_ent enters ONE evaluation under every anchor count, 0 included
+    n_cmp, n_bad, worst = _compare_grid(res, g[method]["eval_res_common_frac_mean_std"],
+                                        skip_ki=() if method == "fixed_anc_ent" else (0,), only_ki=only)
+    assert n_cmp > 900
+    assert n_bad <= 0.02 * n_cmp and worst <= 0.05, (n_bad, n_cmp, worst)
+
+
+@pytest.mark.gpu
+def test_bienc_and_tfidf_served_from_precomputed_embeddings(tmp_path, gold, dump, methods_gold):
+    """bienc / tfidf: after their (out-of-scope) embedding step the reference executes the fixed_anc_ent lines -- so with the
+    fixed-anchor embeddings passed in as 'precomputed embeddings' both must reproduce the fixed_anc_ent golden numbers on
+    the base k_r grid (the grid of those methods, :246-247), tfidf indexing the mention embeddings by ment_idxs (:378)."""
+    g = methods_gold
+    a = gold["splits"]["args"]
+    F.write_splits(dump, a["num_train_ment_vals"], a["num_splits"], a["seed"], a["dev_frac"], str(tmp_path))
+    n_fixed = g["n_fixed_anc_ent"]
+    anchors = g["topk_ents"][0][:n_fixed]
+    np.save(str(tmp_path / "ent.npy"), g["ent_to_ent_scores"][:, :n_fixed])
+    all_ment = dump["ment_to_ent_scores"].numpy()[:, anchors]                 # embeddings of ALL 64 mentions
+    np.save(str(tmp_path / "ment_all.npy"), all_ment)
+    test_idx = F.load_m2e_pickle(str(tmp_path / g["test"]))["ment_idxs"]
+    np.save(str(tmp_path / "ment_test.npy"), all_ment[test_idx])
+    want = g["fixed_anc_ent"]["eval_res_common_frac_mean_std"]
+    for method, ment_file in (("tfidf", "ment_all.npy"), ("bienc", "ment_test.npy"), ("bienc", "ment_all.npy")):
+        args = {"ent_embed_file": str(tmp_path / "ent.npy"), "ment_embed_file": str(tmp_path / ment_file)}
+        res, params = F.run_eval_method(method, str(tmp_path / g["test"]), str(tmp_path / g["train"]), bienc_args=args, tfidf_args=args)
+        assert params["top_k_retr_vals"] == [1, 10, 50, 100, 200, 500, 1000]
+        n_cmp = 0
+        for tk, v in res.items():
+            for kr, v2 in v.items():
+                for an, m in v2.items():
+                    assert abs(m["exact_vs_reranked_approx_retvr~common_frac_mean"] - want[tk][kr][an][0]) <= 1e-3, (method, tk, kr, an)
+                    n_cmp += 1
+        assert n_cmp > 500
+    with pytest.raises(ValueError):
+        F.run_eval_method("bienc", str(tmp_path / g["test"]), str(tmp_path / g["train"]), bienc_args={})
+
+
+@pytest.mark.gpu
+def test_cli_serves_fixed_anc_ent(tmp_path, gold, dump, methods_gold):
+    from anncur_b200.run_fixed_split_eval import main
+    g = methods_gold
+    a = gold["splits"]["args"]
+    F.write_splits(dump, a["num_train_ment_vals"], a["num_splits"], a["seed"], a["dev_frac"], str(tmp_path / "splits"))
+    e2e = str(tmp_path / "e2e.pkl")
+    F.save_e2e_pickle(e2e, F.make_e2e_dict(g["ent_to_ent_scores"], g["topk_ents"]))
+    f = main(["--eval_method", "fixed_anc_ent", "--res_dir", str(tmp_path / "res"), "--misc", "t", "--e2e_fname", e2e,
+              "--n_fixed_anc_ent", str(g["n_fixed_anc_ent"]), "--test_data_file", str(tmp_path / "splits" / g["test"]),
+              "--train_data_file", str(tmp_path / "splits" / g["train"]), "--k_r", "100", "500"])
+    d = json.load(open(f))
+    assert os.path.basename(f) == "method=fixed_anc_ent_t.json" and d["other_args"]["eval_method"] == "fixed_anc_ent"
+    want = g["fixed_anc_ent"]["eval_res_common_frac_mean_std"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"][0]
+    assert abs(d["seed=0"]["top_k=10"]["k_retvr=100"]["anc_n_m=30_anc_n_e=50"]["exact_vs_reranked_approx_retvr~common_frac_mean"] - want) <= 1e-3

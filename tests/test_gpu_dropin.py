@@ -99,6 +99,38 @@ def test_sweep_eval_dropin_matches_reference_golden(golden_dir):
             _close_dict(ours[grp], ref[grp], atol=3e-3)
 
 
+def test_sweep_tool_grid_matches_reference_golden_point(golden_dir, tmp_path):
+    """run_sweep / the run_sweep_eval CLI (the k_q x k_i grid of eval/run_retrieval_eval_wrt_exact_crossenc.py:227-233 as one
+    run): the grid point the golden fixture holds must come out with the reference's numbers, seed-averaged over one seed,
+    under the reference's key layout; the other points must be present and sane."""
+    from anncur_b200 import data_formats as F
+    from anncur_b200.eval_retrieval import run_sweep, sweep_grids
+    from anncur_b200.run_sweep_eval import main
+    g = _load(golden_dir, "sweep_eval")
+    k_q, k_i, top_k, k_r, seed = [int(x) for x in g["params"]]
+    assert seed == 0
+    A = torch.from_numpy(g["A"])
+    gm, ge = sweep_grids(*A.shape)
+    assert gm == [v for v in [50, 100, 200, 500, 1000, 2000, 5000] if v <= A.shape[0]] and ge[-1] == A.shape[1]
+    res = run_sweep(A, n_seeds=1, top_k_vals=[top_k], top_k_retr_vals=[k_r], n_ment_anchors_vals=[k_q, gm[0]], n_ent_anchors_vals=[k_i, ge[0]])
+    for method in ("cur", "cur_oracle"):
+        ref = json.loads(str(g[method + "_json"]))
+        ours = res[method][f"top_k={top_k}"][f"k_retvr={k_r}"][f"anc_n_m={k_q}~anc_n_e={k_i}"]
+        for grp in ("anchor", "non_anchor", "all"):
+            _close_dict(ours[grp], ref[grp], atol=3e-3)
+        assert len(res[method][f"top_k={top_k}"][f"k_retvr={k_r}"]) == len({k_q, gm[0]}) * len({k_i, ge[0]})
+    assert res["other_args"]["n_ment_anchors_vals"] == [k_q, gm[0]]
+    # the CLI: pickle in, reference-layout JSON out, matrix rank next to it
+    F.save_m2e_pickle(str(tmp_path / "m2e.pkl"), F.make_m2e_dict(A, [{}] * A.shape[0], [[0]] * A.shape[0]))
+    f = main(["--m2e_file", str(tmp_path / "m2e.pkl"), "--res_dir", str(tmp_path / "res"), "--methods", "cur", "--k_q", str(gm[0]),
+              "--k_i", str(ge[0]), "--rank"])
+    d = json.load(open(f))
+    assert f.endswith(f"nm={A.shape[0]}_ne={A.shape[1]}_s=1/retrieval_wrt_exact_crossenc.json")
+    pt = d["cur"]["top_k=10"]["k_retvr=500"][f"anc_n_m={gm[0]}~anc_n_e={ge[0]}"]
+    assert set(pt) == {"anchor", "non_anchor", "all"} and 0.0 < pt["all"]["approx_error_relative"] < 2.0
+    assert d["other_args"]["matrix_rank"] == int(np.linalg.matrix_rank(g["A"])) and d["other_args"]["timing"]["grid_points"] == 1
+
+
 def test_fixed_split_eval_dropin_matches_reference_golden(golden_dir):
     from anncur_b200 import eval_approx_score_mat, eval_approx_score_mat_for_all_topk, fixed_split_cur_eval
     g = _load(golden_dir, "fixed_split_eval")

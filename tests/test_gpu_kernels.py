@@ -242,6 +242,43 @@ def test_singular_values_and_matrix_rank(eng):
         assert eng.matrix_rank(torch.from_numpy(A)) == np.linalg.matrix_rank(A) == r
 
 
+def test_orthonormalize_gives_left_singular_vectors(eng):
+    rng = np.random.default_rng(1)
+    Y = (rng.standard_normal((700, 48)) * np.logspace(0, -5, 48)[None, :]).astype(np.float32)
+    Y[:, 5] = Y[:, 2]                                                  # rank-deficient: one zero column must come out
+    Q, s = eng.orthonormalize(torch.from_numpy(Y).cuda())
+    Q, s = Q.cpu().double().numpy(), s.cpu().numpy()
+    keep = np.linalg.norm(Q, axis=0) > 0.5
+    assert keep.sum() == 47
+    G = Q[:, keep].T @ Q[:, keep]
+    assert np.abs(G - np.eye(47)).max() < 1e-5                          # orthonormal (fp32 output)
+    ref = np.linalg.svd(Y.astype(np.float64), compute_uv=False)
+    assert np.allclose(np.sort(s)[::-1][:47], ref[:47], rtol=1e-6, atol=1e-9 * ref[0])
+    # same column space: projecting Y onto span(Q) loses nothing
+    P = Q[:, keep] @ (Q[:, keep].T @ Y.astype(np.float64))
+    assert np.linalg.norm(P - Y) < 1e-5 * np.linalg.norm(Y)
+
+
+def test_matrix_rank_large_randomised_matches_numpy(eng):
+    """eval/compute_m2e_matrix_ranks.py:50 at a size where both routes run: randomised subspace iteration (GEMMs + Jacobi on
+    small matrices) against np.linalg.matrix_rank / np.linalg.svd of the same matrix -- low-rank + noise (the rank is then
+    the number of values above numpy's tolerance, not the noise dimension), exact low rank, and a block that must grow."""
+    rng = np.random.default_rng(2)
+    n, N, r = 900, 20000, 40
+    sig = np.linspace(60.0, 5.0, r)
+    A = ((rng.standard_normal((n, r)) * sig[None, :]) @ rng.standard_normal((r, N)) / np.sqrt(n) + 0.01 * rng.standard_normal((n, N))).astype(np.float32)
+    At = torch.from_numpy(A).cuda()
+    ref_s = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    s = eng.leading_singular_values(At, 96, n_iter=4).cpu().numpy()
+    assert np.allclose(s[:r], ref_s[:r], rtol=2e-4)
+    assert eng.matrix_rank_large(At, n_values=96) == np.linalg.matrix_rank(A)
+    assert eng.matrix_rank_large(At.t().contiguous(), n_values=96) == np.linalg.matrix_rank(A)        # tall orientation
+    assert eng.matrix_rank_large(At, n_values=16) == np.linalg.matrix_rank(A)                        # block doubles until it holds the rank
+    assert eng.matrix_rank_large(At, tol=1.0, n_values=64) == int((ref_s > 1.0).sum())
+    B = (rng.standard_normal((300, 7)) @ rng.standard_normal((7, 5000))).astype(np.float32)          # exact rank 7
+    assert eng.matrix_rank_large(torch.from_numpy(B).cuda(), n_values=32) == 7 == np.linalg.matrix_rank(B)
+
+
 def test_topk_rows_large_rows_sampled_path(eng):
     """Rows long enough for the sampled-threshold kernel (>= 32768 columns): random, sorted ascending / descending,
     heavy ties (falls back to the radix path), unaligned row starts, k from 1 to 1000."""
