@@ -49,6 +49,7 @@ PROTOTYPES = {
     "anncur_peer_close": (_i, [_vp]),
     "anncur_peer_scatter_keys": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.c_uint32, C.POINTER(_vp), _vp]),
     "anncur_peer_merge_owned": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_peer_cert_failures": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_uint), _vp]),
     "anncur_peer_error": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_int), _vp]),
     "anncur_rerank_overlap": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp, _i, C.POINTER(C.c_int), _i, _vp, _vp, _vp, _vp]),
     "anncur_overlap_counts": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

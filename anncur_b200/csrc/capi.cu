@@ -301,9 +301,14 @@ int anncur_peer_merge_owned(void* local_base, int rank, int world, int rows_owne
                             void* stream) {
     ANNCUR_REQUIRE(local_base && workspace && (rows_owned == 0 || (out_vals && out_idx)), "peer_merge_owned: null pointer");
     ANNCUR_REQUIRE(k_out >= 1 && k_out <= 1024, "peer_merge_owned: k_out = %d outside [1, 1024]", k_out);
+    ANNCUR_REQUIRE(k_out <= world * k_cap, "peer_merge_owned: k_out = %d > world * k_cap = %d", k_out, world * k_cap);
     if (workspace_bytes < anncur_merge_topk_keys_workspace_bytes(rows_owned)) { set_error("peer_merge_owned workspace too small"); return ANNCUR_E_WORKSPACE; }
     return peer_merge_owned(local_base, rank, world, rows_owned, rows_cap, k_cap, k_out, epoch, out_vals, out_idx,
                             reinterpret_cast<uint32_t*>(workspace), cudaStream_t(stream));
+}
+int anncur_peer_cert_failures(void* local_base, int world, int rows_cap, int k_cap, int reset, unsigned* count_host, void* stream) {
+    ANNCUR_REQUIRE(local_base && count_host, "peer_cert_failures: null pointer");
+    return peer_cert_failures(local_base, world, rows_cap, k_cap, reset, count_host, cudaStream_t(stream));
 }
 int anncur_peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, void* stream) {
     ANNCUR_REQUIRE(local_base && err_host, "peer_error: null pointer");

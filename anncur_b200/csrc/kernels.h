@@ -80,6 +80,7 @@ int peer_scatter_keys(const float* vals, const int64_t* idx, int n_rows, int k, 
                       uint32_t epoch, void* const* peer_bases, cudaStream_t stream);
 int peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int rows_cap, int k_cap, int k_out, uint32_t epoch,
                      float* out_vals, int64_t* out_idx, uint32_t* scratch_rows, cudaStream_t stream);
+int peer_cert_failures(void* local_base, int world, int rows_cap, int k_cap, int reset, unsigned* count_host, cudaStream_t stream);
 int peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, cudaStream_t stream);
 
 // smallest j with P[Binomial(n, p) >= j] <= eps (rank used by the sampled thresholds)

@@ -8,7 +8,7 @@
 // kernel, no staging copy, and only rows_owned x k x P keys arrive per rank instead of B x k x P.
 //
 // Layout of one channel's buffer (identical on every rank; allocated by anncur_peer_alloc, mapped into the peers with
-// CUDA IPC):   keys[2][P][rows_cap][k_cap]  |  flags[P]  |  done counter, error flag
+// CUDA IPC):   keys[2][P][rows_cap][k_cap]  |  flags[P]  |  done counter, error flag, certificate-failure counter
 //   keys[e & 1][s][r][:]  = sender s's list for this rank's owned row r at epoch e
 //   flags[s]              = last epoch whose lists sender s has completely stored here
 // Two key buffers alternate by epoch parity.  Calls on one channel must be stream-ordered on every rank (scatter(e),
@@ -82,6 +82,100 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t epo
             if (clock64() - t0 > PEER_WAIT_TIMEOUT_CYCLES) { atomicExch(error_flag, 1 + t); break; }
             __nanosleep(200);
         }
+    }
+}
+
+// Certificate of a merge whose senders shipped only their best k_cap < k_out candidates per row ("rank-budgeted" local
+// top-k: on P shards a row's global top-k takes ~k/P items from each, so a sender re-scores and ships k_cap ~ k/P + margin
+// instead of k).  The merged top-k_out is exact iff no FULL sender list was consumed entirely: a sender whose last shipped
+// key is >= the k_out-th merged key may hold further items above it.  Rows that fail are counted (cumulative counter in the
+// channel buffer) and the caller recomputes the batch with k_cap = k_out; rows that pass are exact, whatever the placement
+// of the items.  One thread per owned row.
+__global__ void merge_certificate_kernel(const uint64_t* __restrict__ keys, int world, int rows, int rows_cap, int k_cap,
+                                         const float* __restrict__ out_vals, const int64_t* __restrict__ out_idx, int k_out,
+                                         uint32_t* __restrict__ fail_counter) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int64_t i_k = out_idx[int64_t(row) * k_out + k_out - 1];
+    const uint64_t key_k = i_k < 0 ? 0ull : make_key(out_vals[int64_t(row) * k_out + k_out - 1], uint32_t(i_k));
+    bool fail = false;
+    for (int p = 0; p < world; ++p) {
+        const uint64_t last = __ldcg(keys + (size_t(p) * rows_cap + row) * k_cap + (k_cap - 1));
+        fail |= last != 0ull && last >= key_k;
+    }
+    if (fail) atomicAdd(fail_counter, 1u);
+}
+
+// ---- owner side in ONE kernel: wait for the senders, merge the P sorted lists of each owned row, certify ------------------
+// Every sender's list is sorted best-first (it is a local top-k; padding keys 0 at the end), so a key's place in the merged
+// order is known without sorting:  rank(x) = (its position in its own list) + sum over the other lists of #{y > x}, each
+// count one binary search.  One warp per row, the row's P x k_cap keys staged in shared memory; keys with rank < k_out go
+// straight to out[rank].  The certificate of the rank-budgeted form falls out of the same ranks: the merged row is exact
+// unless the LAST key of a full list made it into the top k_out (that sender may hold more above the cut).
+constexpr int MG_WARPS = 8;
+
+__device__ __forceinline__ uint32_t count_greater_desc(const uint64_t* __restrict__ list, uint32_t n, uint64_t x) {
+    // list[0 .. n) descending; number of entries > x
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (list[mid] > x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(MG_WARPS * 32)
+wait_merge_certify_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags, int world, uint32_t epoch,
+                          int rows, int rows_cap, int k_cap, int k_out, float* __restrict__ out_vals, int64_t* __restrict__ out_idx,
+                          uint32_t* __restrict__ fail_counter, int* __restrict__ error_flag) {
+    extern __shared__ __align__(16) uint64_t mg_smem[];
+    if (threadIdx.x < uint32_t(world)) {
+        const unsigned long long t0 = clock64();
+        while (int32_t(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            if (clock64() - t0 > PEER_WAIT_TIMEOUT_CYCLES) { atomicExch(error_flag, 1 + int(threadIdx.x)); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = int(lane_id());
+    const int total = world * k_cap;
+    uint64_t* mine = mg_smem + size_t(warp) * total;
+    for (int row = blockIdx.x * MG_WARPS + warp; row < rows; row += gridDim.x * MG_WARPS) {
+        for (int t = lane; t < total; t += 32) {
+            const int p = t / k_cap, i = t - p * k_cap;
+            mine[t] = __ldcg(keys + (size_t(p) * rows_cap + row) * k_cap + i);
+        }
+        __syncwarp();
+        uint32_t n_real = 0;
+        bool fail = false;
+        for (int t = lane; t < total; t += 32) {
+            const uint64_t x = mine[t];
+            if (x == 0ull) continue;
+            ++n_real;
+            const int p = t / k_cap, i = t - p * k_cap;
+            uint32_t rank = uint32_t(i);
+            for (int q = 0; q < world; ++q)
+                if (q != p) rank += count_greater_desc(mine + q * k_cap, uint32_t(k_cap), x);
+            if (rank < uint32_t(k_out)) {
+                out_vals[int64_t(row) * k_out + rank] = key_score(x);
+                out_idx[int64_t(row) * k_out + rank] = int64_t(key_index(x));
+                fail |= (i == k_cap - 1);                 // the last key of a FULL list is part of the answer
+            }
+        }
+        n_real = warp_sum(n_real);
+        for (int t = int(n_real) + lane; t < k_out; t += 32) {      // fewer candidates than k_out: pad
+            out_vals[int64_t(row) * k_out + t] = ANNCUR_PAD_VAL;
+            out_idx[int64_t(row) * k_out + t] = -1;
+        }
+        if (k_cap < k_out) {
+            fail = __any_sync(0xffffffffu, fail);
+            // a row that comes out short of k_out although some sender's list was full fails as well
+            bool any_full = false;
+            for (int q = lane; q < world; q += 32) any_full |= mine[q * k_cap + k_cap - 1] != 0ull;
+            any_full = __any_sync(0xffffffffu, any_full);
+            if (lane == 0 && (fail || (n_real < uint32_t(k_out) && any_full))) atomicAdd(fail_counter, 1u);
+        }
+        __syncwarp();
     }
 }
 
@@ -161,11 +255,37 @@ int peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int 
     const size_t kb = peer_keys_bytes(world, rows_cap, k_cap);
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(base + kb);
     int* err = reinterpret_cast<int*>(base + kb + 256 + 4);
+    const uint64_t* keys = reinterpret_cast<const uint64_t*>(base) + size_t(epoch & 1u) * size_t(world) * rows_cap * k_cap;
+    const size_t mg_smem = sizeof(uint64_t) * size_t(MG_WARPS) * world * k_cap;
+    if (rows_owned > 0 && mg_smem <= 96 * 1024) {
+        // the usual case: wait + merge + certificate in one launch
+        uint32_t* fails = reinterpret_cast<uint32_t*>(base + kb + 256 + 8);
+        ANNCUR_CUDA_OK(cudaFuncSetAttribute(wait_merge_certify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mg_smem)));
+        int grid = (rows_owned + MG_WARPS - 1) / MG_WARPS;
+        if (grid > 8 * sm_count()) grid = 8 * sm_count();
+        wait_merge_certify_kernel<<<grid, MG_WARPS * 32, mg_smem, stream>>>(keys, flags, world, epoch, rows_owned, rows_cap, k_cap, k_out,
+                                                                            out_vals, out_idx, fails, err);
+        ANNCUR_LAUNCH_OK("wait_merge_certify_kernel");
+        return ANNCUR_OK;
+    }
     wait_flags_kernel<<<1, 32 * ((world + 31) / 32), 0, stream>>>(flags, world, epoch, err);
     ANNCUR_LAUNCH_OK("wait_flags_kernel");
     if (rows_owned == 0) return ANNCUR_OK;
-    const uint64_t* keys = reinterpret_cast<const uint64_t*>(base) + size_t(epoch & 1u) * size_t(world) * rows_cap * k_cap;
-    return merge_topk_keys_strided(keys, world, rows_owned, k_cap, int64_t(rows_cap) * k_cap, k_out, out_vals, out_idx, scratch_rows, stream);
+    int rc = merge_topk_keys_strided(keys, world, rows_owned, k_cap, int64_t(rows_cap) * k_cap, k_out, out_vals, out_idx, scratch_rows, stream);
+    if (rc != ANNCUR_OK || k_cap >= k_out || world == 1) return rc;
+    uint32_t* fails = reinterpret_cast<uint32_t*>(base + kb + 256 + 8);
+    merge_certificate_kernel<<<(rows_owned + 127) / 128, 128, 0, stream>>>(keys, world, rows_owned, rows_cap, k_cap, out_vals, out_idx, k_out, fails);
+    ANNCUR_LAUNCH_OK("merge_certificate_kernel");
+    return ANNCUR_OK;
+}
+
+// rows (cumulative over the calls on this channel) whose rank-budgeted merge failed its certificate (blocks on the stream)
+int peer_cert_failures(void* local_base, int world, int rows_cap, int k_cap, int reset, unsigned* count_host, cudaStream_t stream) {
+    char* p = reinterpret_cast<char*>(local_base) + peer_keys_bytes(world, rows_cap, k_cap) + 256 + 8;
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(count_host, p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    if (reset) ANNCUR_CUDA_OK(cudaMemsetAsync(p, 0, sizeof(unsigned), stream));
+    ANNCUR_CUDA_OK(cudaStreamSynchronize(stream));
+    return ANNCUR_OK;
 }
 
 // 0 = no sender timed out so far; 1 + s = the wait for sender s gave up (blocks on the stream)

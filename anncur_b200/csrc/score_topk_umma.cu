@@ -58,6 +58,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -84,7 +85,11 @@ constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, e
 constexpr int EPI_HALVES = NUM_EPI_WARPS / 4;
 constexpr int FUSED_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
+// mbarrier watchdog: a wait that outlasts this many SM cycles (~3 s) sets the workspace's error flag and traps instead of
+// hanging the GPU for good.  A trap takes the whole CUDA context with it, so the limit is a run-time knob:
+// ANNCUR_WAIT_TIMEOUT_CYCLES=<n> (0 = no watchdog, e.g. under cuda-gdb / compute-sanitizer, where clock64 keeps running
+// while the kernel is stopped).
+constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 6000000000ull;
 
 // CG = CTAs per MMA (1, or 2 = CTA pair: each CTA stages its own 128 queries and HALF of the 256-item tile)
 template <int PASSES, int CG> struct StageCfg {
@@ -126,6 +131,7 @@ struct FusedParams {
     int filter;              // MODE_MAIN, F32R: scores are upper bounds -> lists are never cut back; a list that fills up is
                              // marked (top bit of its count) and the row goes to REDO
     int* error_flag;
+    unsigned long long wait_timeout;   // mbarrier watchdog in SM cycles, 0 = off (see WAIT_TIMEOUT_CYCLES)
     // EPI_DENSE: out[row][col] = score; EPI_ERR: err2[row] += (score - exact[row][col])^2, norm2[row] += exact[row][col]^2
     const float* row_inv_scale;     // accumulator (scaled units) * row_inv_scale[row] = score
     float* dense_out;  int64_t ldo;
@@ -154,12 +160,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+struct WaitCtx { int* error_flag; unsigned long long timeout; };
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
-            if (error_flag) atomicExch(error_flag, 1);
+        if (w.timeout != 0ull && clock64() - t0 > w.timeout) {
+            if (w.error_flag) atomicExch(w.error_flag, 1);
             __trap();
         }
     }
@@ -346,6 +353,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
+    const WaitCtx wctx{p.error_flag, p.wait_timeout};
 
     // REDO launch without a flagged row (the normal case): nothing to do, leave before any TMEM / barrier set-up
     if (p.mtile_flags != nullptr && __ldg(p.mtile_flags + p.m_tiles) == 0u) return;
@@ -411,7 +419,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     const int item0 = tile * BLOCK_N + int(cta_rank) * (BLOCK_N / CG);     // this CTA's share of the item tile
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += Cfg::kKbPerStage) {
                         const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
-                        mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag);
+                        mbar_wait(empty_bar(stage), phase ^ 1u, wctx);
                         if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * n_sub * Cfg::kSubBytes));
                         for (int u = 0; u < n_sub; ++u) {
                             const int kb = kb0 + u;
@@ -456,12 +464,12 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                 const int t0 = int((int64_t(chunk) * p.n_tiles) / p.n_chunks);
                 const int t1 = int((int64_t(chunk + 1) * p.n_tiles) / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
-                    mbar_wait(tempty_bar(buf), acc_phase ^ 1u, p.error_flag);
+                    mbar_wait(tempty_bar(buf), acc_phase ^ 1u, wctx);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + uint32_t(buf) * BLOCK_N;
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += Cfg::kKbPerStage) {
                         const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
-                        mbar_wait(full_bar(stage), phase, p.error_flag);
+                        mbar_wait(full_bar(stage), phase, wctx);
                         tcgen05_fence_after();
                         const uint32_t lo0 = smem_desc_lo(smem_base + uint32_t(stage) * Cfg::kStageBytes);
 #pragma unroll
@@ -637,7 +645,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     thr = INFINITY;
                     if (row_ok && overflow == 0u) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
                 }
-                mbar_wait(tfull_bar(buf), acc_phase, p.error_flag);
+                mbar_wait(tfull_bar(buf), acc_phase, wctx);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
                 uint32_t ra[32], rb[32];
@@ -1200,6 +1208,14 @@ int binomial_tail_rank(int n, double p, double eps) {
 
 static int cta_group_for(int m_tiles);
 
+static unsigned long long wait_timeout_cycles() {
+    static unsigned long long v = [] {
+        const char* e = getenv("ANNCUR_WAIT_TIMEOUT_CYCLES");
+        return e ? strtoull(e, nullptr, 10) : WAIT_TIMEOUT_CYCLES;
+    }();
+    return v;
+}
+
 struct FusedPlan {
     int num_kb, m_tiles, n_tiles, n_chunks;
     uint32_t cap;
@@ -1499,6 +1515,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     FusedParams fp{};
     fp.n_queries = n_queries; fp.num_kb = pl.num_kb; fp.k = k; fp.m_tiles = pl.m_tiles;
     fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err; fp.smax = smax; fp.n_smax = pl.n_smax;
+    fp.wait_timeout = wait_timeout_cycles();
     // query high-plane variant of the last k-block (F32R only): +b at num_kb - 1, -b at num_kb, plain scores at num_kb + 1
     const int akb_upper = pl.num_kb - 1, akb_lower = refine ? pl.num_kb : pl.num_kb - 1, akb_plain = refine ? pl.num_kb + 1 : pl.num_kb - 1;
     fp.a_last_kb = akb_plain;
@@ -1634,6 +1651,7 @@ static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_que
     FusedParams fp{};
     fp.mode = MODE_MAIN; fp.n_queries = n_queries; fp.n_items = int(n_items); fp.num_kb = pl.num_kb; fp.k = 1;
     fp.m_tiles = pl.m_tiles; fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks; fp.error_flag = err;
+    fp.wait_timeout = wait_timeout_cycles();
     fp.a_last_kb = kind == ANNCUR_KIND_F32R ? pl.num_kb + 1 : pl.num_kb - 1;     // plain scores: bound slot = 0
     fp.row_inv_scale = inv_scale; fp.dense_out = out; fp.ldo = ldo; fp.exact = exact; fp.lda = lda; fp.err2 = err2; fp.norm2 = norm2;
     fp.smax = reinterpret_cast<float*>(ws); fp.cand = reinterpret_cast<uint64_t*>(ws); fp.counts = thr; fp.thr_shared = thr;   // unused by these epilogues

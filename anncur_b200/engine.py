@@ -227,6 +227,10 @@ class PackedItems:
         self.k_dim, self.n_items = int(E.shape[0]), int(E.shape[1])
         self.device = E.device
         nbytes = lib.anncur_packed_items_bytes(self.n_items, self.k_dim, self.kind)
+        if self.n_items and self.k_dim and not bool(torch.isfinite(E).all()):
+            # the scales are chosen from the finite entries only; an inf / NaN item embedding would make every score of
+            # that item undefined without any error -- refuse it here, once, at index build
+            raise ValueError("PackedItems: the item embeddings contain inf / NaN")
         self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=E.device)
         self.scale = torch.ones(1, dtype=torch.float32, device=E.device)
         with torch.cuda.device(E.device):
@@ -252,11 +256,12 @@ def score_topk(Q, packed, k, idx_offset=0, out=None, ws=None):
     else:
         vals, idx = out
     if B > 0:
-        nbytes = lib.anncur_score_topk_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
-        if ws is None:
-            ws = WORKSPACE.get("score_topk", nbytes, Q.device)
-        assert ws.numel() >= nbytes and ws.device == Q.device
-        with torch.cuda.device(Q.device):
+        with torch.cuda.device(Q.device):              # the plan (SM count) is that of the index's device, not the current one
+            nbytes = lib.anncur_score_topk_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
+            if ws is None:
+                ws = WORKSPACE.get("score_topk", nbytes, Q.device)
+            assert ws.numel() >= nbytes and ws.device == Q.device
+            _LAST_FUSED_WS[Q.device.index] = (ws, 0, B, int(k))
             _lib.check(lib.anncur_score_topk(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), packed.n_items,
                                              packed.k_dim, packed.kind, int(k), int(idx_offset), _ptr(vals), _ptr(idx),
                                              _ptr(ws), ws.numel(), _stream()))
@@ -275,9 +280,9 @@ def score_dense(Q, packed, out=None):
         out = torch.empty((B, N), dtype=torch.float32, device=Q.device)
     assert out.shape == (B, N) and out.dtype == torch.float32 and out.stride(1) == 1
     if B > 0 and N > 0:
-        nbytes = lib.anncur_score_dense_workspace_bytes(B, N, packed.k_dim, packed.kind)
-        ws = WORKSPACE.get("score_dense", nbytes, Q.device)
         with torch.cuda.device(Q.device):
+            nbytes = lib.anncur_score_dense_workspace_bytes(B, N, packed.k_dim, packed.kind)
+            ws = WORKSPACE.get("score_dense", nbytes, Q.device)
             _lib.check(lib.anncur_score_dense(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), N, packed.k_dim,
                                               packed.kind, _ptr(out), _ld(out), _ptr(ws), ws.numel(), _stream()))
     return out
@@ -364,16 +369,22 @@ class GraphedSearch:
         return self.vals, self.idx
 
 
+_LAST_FUSED_WS = {}          # device index -> (workspace tensor, byte offset of the fused workspace, n_queries, k) of the last call
+
+
 def last_redo_rows(n_queries, packed, k):
-    """Rows of the last score_topk(Q[n_queries x k_dim], packed, k) call on this device that the fallback pass had to
-    recompute (anncur_score_topk_redo_rows) -- 0 when the fast path served every row.  Synchronises the stream."""
+    """Rows of the last fused search on the index's device -- score_topk, GraphedSearch or search_host, on whatever stream
+    and workspace it ran -- that the fallback pass had to recompute (anncur_score_topk_redo_rows): 0 when the fast path
+    served every row.  (n_queries, k) must be those of that call.  Synchronises the current stream."""
     lib = _lib.load()
-    nbytes = lib.anncur_score_topk_workspace_bytes(n_queries, packed.n_items, packed.k_dim, k, packed.kind)
-    ws = WORKSPACE.get("score_topk", nbytes, packed.device)
+    last = _LAST_FUSED_WS.get(packed.device.index)
+    if last is None or (last[2], last[3]) != (int(n_queries), int(k)):
+        raise RuntimeError("last_redo_rows: no fused search with this (n_queries, k) has run on this device")
+    ws, off = last[0], last[1]
     n = C.c_int(0)
     with torch.cuda.device(packed.device):
-        _lib.check(lib.anncur_score_topk_redo_rows(_ptr(ws), int(n_queries), packed.n_items, packed.k_dim, int(k), packed.kind,
-                                                   C.byref(n), _stream()))
+        _lib.check(lib.anncur_score_topk_redo_rows(C.c_void_p(ws.data_ptr() + off), int(n_queries), packed.n_items, packed.k_dim,
+                                                   int(k), packed.kind, C.byref(n), _stream()))
     return n.value
 
 
@@ -389,9 +400,11 @@ def search_host(Q_host, packed, k, out_vals_host, out_idx_host, idx_offset=0, ws
     assert out_idx_host.shape == (B, k) and out_idx_host.dtype == torch.int64 and out_idx_host.is_contiguous()
     assert not out_vals_host.is_cuda and not out_idx_host.is_cuda
     if B > 0:
-        nbytes = lib.anncur_search_host_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
-        ws = WORKSPACE.get(ws_key, nbytes, packed.device)
         with torch.cuda.device(packed.device):
+            nbytes = lib.anncur_search_host_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
+            inner = lib.anncur_score_topk_workspace_bytes(B, packed.n_items, packed.k_dim, k, packed.kind)
+            ws = WORKSPACE.get(ws_key, nbytes, packed.device)
+            _LAST_FUSED_WS[packed.device.index] = (ws, int(nbytes - inner), B, int(k))     # the fused workspace follows the staging buffers
             _lib.check(lib.anncur_search_host(_ptr(Q_host), _ld(Q_host), B, _ptr(packed.buf), _ptr(packed.scale),
                                               packed.n_items, packed.k_dim, packed.kind, int(k), int(idx_offset),
                                               _ptr(out_vals_host), _ptr(out_idx_host), _ptr(ws), ws.numel(), _stream()))

@@ -34,7 +34,8 @@ def _stats_strings(common, k):
     common = np.asarray(common, dtype=np.float64)
     if common.size == 0:
         return {m: ("mean 0.0", "std 0.0", "p50 0.0") for m in METRICS}
-    per_metric = {"common": common, "diff": k - common, "total": np.full_like(common, k),
+    k = np.asarray(k, dtype=np.float64)                        # a scalar, or one list length per row
+    per_metric = {"common": common, "diff": k - common, "total": np.broadcast_to(k, common.shape).astype(np.float64),
                   "common_frac": common / k, "diff_frac": (k - common) / k}
     return {m: ("mean {:.4f}".format(np.mean(v)), "std {:.4f}".format(np.std(v)),
                 "p50 {:.4f}".format(np.percentile(v, 50))) for m, v in per_metric.items()}
@@ -49,17 +50,45 @@ def _flatten(strings):
     return out
 
 
+def _overlap_rows_gpu(a, b):
+    """Per-row |set(a_r) & set(b_r)| for two rectangular (n x k) index arrays: the K6 kernel up to k = 4096, sort + binary
+    search on the GPU beyond (torch ops on the device; still no host arithmetic)."""
+    if a.shape[1] <= 4096:
+        return engine.overlap_counts(a, b).cpu().numpy()
+    engine.require_cuda()
+    dev = a.device if a.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    out = np.zeros(a.shape[0], dtype=np.int64)
+    for r in range(a.shape[0]):
+        ua, ub = torch.unique(a[r].to(dev)), torch.unique(b[r].to(dev))
+        out[r] = int(torch.isin(ua, ub).sum().item())
+    return out
+
+
 def compute_overlap(indices_list1, indices_list2):
-    """|set(a) & set(b)| per row pair and the reference's mean/std/p50 strings."""
-    n = len(indices_list1)
-    if n == 0 or len(indices_list2) == 0:
+    """|set(a) & set(b)| per row pair and the reference's mean/std/p50 strings (eval/eval_utils.py:115-150).  Like the
+    reference, rows may differ in length from each other (each PAIR must match, :143): rows are grouped by length and every
+    group goes through the GPU kernel."""
+    n = min(len(indices_list1), len(indices_list2))                  # zip() semantics of the reference (:123)
+    if n == 0:
         return {m: ("mean 0.0", "std 0.0", "p50 0.0") for m in METRICS}
-    a = indices_list1 if torch.is_tensor(indices_list1) else torch.as_tensor(np.asarray(indices_list1))
-    b = indices_list2 if torch.is_tensor(indices_list2) else torch.as_tensor(np.asarray(indices_list2))
-    assert a.shape == b.shape, f"Len of both indices is not same => {a.shape[-1]} != {b.shape[-1]}"
-    k = a.shape[1]
-    common = engine.overlap_counts(a, b)                                             # K6 kernel (set semantics)
-    return _stats_strings(common.cpu().numpy(), k)
+    rect = torch.is_tensor(indices_list1) or (isinstance(indices_list1, np.ndarray) and indices_list1.dtype != object)
+    if rect:
+        a = indices_list1 if torch.is_tensor(indices_list1) else torch.as_tensor(np.asarray(indices_list1))
+        b = indices_list2 if torch.is_tensor(indices_list2) else torch.as_tensor(np.asarray(indices_list2))
+        assert a.shape == b.shape, f"Len of both indices is not same => {a.shape[-1]} != {b.shape[-1]}"
+        return _stats_strings(_overlap_rows_gpu(a, b), a.shape[1])
+    lens = np.array([len(x) for x in indices_list1[:n]])
+    for r in range(n):
+        assert len(indices_list1[r]) == len(indices_list2[r]), f"Len of both indices is not same => {len(indices_list1[r])} != {len(indices_list2[r])}"
+    common = np.zeros(n, dtype=np.int64)
+    for L in np.unique(lens):
+        rows = np.nonzero(lens == L)[0]
+        if L == 0:
+            raise ZeroDivisionError("division by zero")               # what the reference's n_intersection / n does (:149)
+        a = torch.as_tensor(np.asarray([list(indices_list1[r]) for r in rows], dtype=np.int64))
+        b = torch.as_tensor(np.asarray([list(indices_list2[r]) for r in rows], dtype=np.int64))
+        common[rows] = _overlap_rows_gpu(a, b)
+    return _stats_strings(common, lens)
 
 
 def retrieve_rerank_overlap(all_scores, approx_scores, k_list, top_k_retvr, *, approx_topk=None):
@@ -68,6 +97,14 @@ def retrieve_rerank_overlap(all_scores, approx_scores, k_list, top_k_retvr, *, a
     ``approx_topk``: optional precomputed (vals, idx) of the approximate top-k_retvr (fused path)."""
     exact = engine._f32(all_scores)
     k_max = max(k_list)
+    if k_max > top_k_retvr:
+        # the reference re-ranks inside an N-long row of -1e14 (..._w_fixed_train_test_splits.py:91-96), so for top_k > k_retvr
+        # it pads the re-ranked list with (top_k - k_retvr) arbitrary never-retrieved items (torch.topk's order among the
+        # equal -1e14 entries is unspecified): there is no defined answer to reproduce
+        raise ValueError(f"top_k = {k_max} > top_k_retvr = {top_k_retvr}: the reference pads the re-ranked list with unspecified "
+                         "items in this case; evaluate with top_k <= top_k_retvr")
+    if top_k_retvr > engine.MAX_K:
+        raise ValueError(f"top_k_retvr = {top_k_retvr} > {engine.MAX_K}: retrieved lists longer than ANNCUR_MAX_K are not supported")
     ex_v, ex_i = engine.topk_rows(exact, k_max)
     if approx_topk is None:
         ap_v, ap_i = engine.topk_rows(engine._f32(approx_scores, device=exact.device), top_k_retvr)

@@ -13,6 +13,9 @@ against its slice with the fused kernel and emits a local top-k carrying GLOBAL 
                     straight into the owner's receive buffer through NVLink peer memory, flags instead of a
                     collective (csrc/peer_exchange.cu) -- or ``exchange="nccl"``: topk_to_keys +
                     ``all_to_all_single``.  Returns this rank's block of the answer.
+                    With ``local_k`` < k each shard re-scores and ships only its best ``local_k`` candidates per row
+                    (a row's global top-k takes ~k/P from each of P shards); the merge certifies every row on the device
+                    and ``search_rowblock_verified`` falls back to the full-k exchange when a certificate fails.
 ``search_owned``    the same for a query batch that arrives distributed (each rank passes ITS block of rows,
                     e.g. straight from its own host buffer): one all-gather of the query blocks, then
                     ``search_rowblock``.  Host traffic per step is then that of a single GPU in total.
@@ -33,6 +36,18 @@ import torch.distributed as dist
 def shard_bounds(n_items, world_size):
     """Contiguous balanced item ranges: [(lo_0, hi_0), ...]; sizes differ by at most one."""
     return [((p * n_items) // world_size, ((p + 1) * n_items) // world_size) for p in range(world_size)]
+
+
+def suggest_local_k(k, world_size):
+    """Candidates a shard re-scores and ships per row in the rank-budgeted exchange: the share of a row's global top-k that
+    falls into one of P equal shards is Binomial(k, 1/P) for items placed independently of their scores -- mean k/P plus six
+    standard deviations plus 8.  (A placement that defeats this only costs the fallback; the certificate catches it.)"""
+    P = int(world_size)
+    if P <= 1:
+        return int(k)
+    mean = k / P
+    budget = int(mean + 6.0 * (mean * (1.0 - 1.0 / P)) ** 0.5 + 8.0 + 0.999)
+    return max(1, min(int(k), max(budget, -(-int(k) // P))))
 
 
 def pack_candidates(vals, idx):
@@ -111,6 +126,15 @@ class PeerChannel:
                                                     C.c_void_p(out_i.data_ptr()), C.c_void_p(self._ws.data_ptr()),
                                                     self._ws.numel(), stream))
         return out_v, out_i
+
+    def cert_failures(self, reset=False):
+        """Rows whose rank-budgeted merge (k_out > this channel's k) failed the exactness certificate since the last reset,
+        on THIS rank's owned rows (synchronises the current stream)."""
+        n = C.c_uint(0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.anncur_peer_cert_failures(C.c_void_p(self.base), self.world, self.rows_cap, self.k, 1 if reset else 0,
+                                                            C.byref(n), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return int(n.value)
 
     def error(self):
         """0, or 1 + s when a wait for sender s timed out (synchronises the current stream)."""
@@ -211,14 +235,22 @@ class ShardedIndex:
         if self.exchange == "p2p" and self.world_size > 1:
             self._channel(n_rows, k, device if device is not None else self._packed.device)
 
-    def search_rowblock(self, Q, k):
-        """Replicated Q (B x k_i) -> (vals, idx) of this rank's owned rows ``row_block(B)``."""
-        vals, idx = self.local_topk(Q, k)
+    def search_rowblock(self, Q, k, local_k=None):
+        """Replicated Q (B x k_i) -> (vals, idx) of this rank's owned rows ``row_block(B)``.
+
+        ``local_k`` < k (peer-memory exchange only) is the rank-budgeted form: every shard re-scores and ships only its best
+        ``local_k`` candidates per row (see ``suggest_local_k``), the owner's merge evaluates the exactness certificate of
+        every row on the device, and ``certificate_failures()`` tells whether any row of any call since the last check
+        needs the full-k answer -- ``search_rowblock_verified`` does that bookkeeping."""
+        k_loc = int(k) if (local_k is None or self.exchange != "p2p" or self.world_size == 1) else max(1, min(int(local_k), int(k)))
+        if k_loc * self.world_size < k:
+            k_loc = -(-int(k) // self.world_size)
+        vals, idx = self.local_topk(Q, k_loc)
         B = vals.shape[0]
         if self.world_size == 1:
             return vals, idx
         if self.exchange == "p2p":
-            return self._channel(B, k, vals.device).exchange(vals, idx)
+            return self._channel(B, k_loc, vals.device).exchange(vals, idx, k_out=k)
         bounds = shard_bounds(B, self.world_size)
         rows = [hi - lo for lo, hi in bounds]
         mine = rows[self.rank]
@@ -234,7 +266,26 @@ class ShardedIndex:
         cand_vals, cand_idx = unpack_candidates(recv.view(self.world_size, mine, 2 * k), k)
         return self._merge(cand_vals, cand_idx, k)
 
-    def search_owned(self, Q_block, n_rows_total, k):
+    def certificate_failures(self, reset=True):
+        """Collective: rows (over all ranks and all rank-budgeted calls since the last reset) whose merge failed its
+        certificate.  0 = every answer returned so far is the exact top-k."""
+        n = sum(ch.cert_failures(reset) for ch in self._channels.values())
+        if self.world_size > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=self._packed.device if self._cuda else "cpu")
+            dist.all_reduce(t, group=self.group)
+            n = int(t.item())
+        return n
+
+    def search_rowblock_verified(self, Q, k, local_k=None):
+        """``search_rowblock`` with the rank-budgeted shortcut made safe: if any row of the batch fails the certificate (on any
+        rank) the batch is recomputed with local_k = k.  Synchronises (one small all-reduce + host read-back per call)."""
+        out = self.search_rowblock(Q, k, local_k)
+        if local_k is not None and local_k < k and self.exchange == "p2p" and self.world_size > 1:
+            if self.certificate_failures(reset=True) > 0:
+                out = self.search_rowblock(Q, k, None)
+        return out
+
+    def search_owned(self, Q_block, n_rows_total, k, local_k=None):
         """Q_block = this rank's ``row_block(n_rows_total)`` of the batch.  All-gathers the blocks (NVLink), searches,
         and returns the answer for the same rows."""
         if self.world_size == 1:
@@ -252,7 +303,7 @@ class ShardedIndex:
             allq = torch.empty((self.world_size * cap, Q_block.shape[1]), dtype=Q_block.dtype, device=Q_block.device)
             dist.all_gather_into_tensor(allq, mine, group=self.group)
             Q = torch.cat([allq[p * cap:p * cap + rows[p]] for p in range(self.world_size)], dim=0)
-        return self.search_rowblock(Q, k)
+        return self.search_rowblock(Q, k, local_k)
 
     def close(self):
         for ch in self._channels.values():

@@ -324,6 +324,8 @@ def workload_config(args, world, shard):
                "nccl": "NCCL all_to_all_single of candidate keys by row block + merge of owned rows",
                "allgather": "NCCL all-gather of candidate keys + merge of every row on every rank"}[args.exchange]
         par = f"items sharded over {world} ranks (E[:, N/{world}] per GPU), same batch on every rank; exchange: {how}"
+        if args.exchange == "p2p" and getattr(args, "local_k", "full") != "full":
+            par += "; rank-budgeted: each shard ships its best k/P + 6 sigma + 8 candidates per row, every merged row certified exact on the device (full-k fallback)"
     else:
         par = f"dp{world}: E replicated, queries sharded, no collective"
     return {"workload": f"{args.workload}: ANNCUR score+top-{k}, N={N} items, k_i={k_i}, batch {B} queries/step",
@@ -356,10 +358,15 @@ class Harness:
         salt = 0 if (self.sharded or world == 1) else 97 * rank                       # replicas: every rank its own queries
         self.batches = [self.syn.query_batch(j, salt) for j in range(N_BATCHES)]
         self.index = None
+        self.local_k = None
         if self.sharded:
+            from anncur_b200.sharded import suggest_local_k
             self.index = ShardedIndex(self.E, self.lo, self.N, precision=args.precision, packed=self.packed,
                                       exchange="nccl" if args.exchange == "allgather" else args.exchange)
             self.row_lo, self.row_hi = self.index.row_block(self.B)
+            if args.exchange == "p2p" and args.local_k != "full":
+                lk = suggest_local_k(self.k, world) if args.local_k == "auto" else int(args.local_k)
+                self.local_k = lk if lk < self.k else None
         self.out_v = torch.empty((self.B, self.k), dtype=torch.float32, device=self.device)
         self.out_i = torch.empty((self.B, self.k), dtype=torch.int64, device=self.device)
 
@@ -370,7 +377,7 @@ class Harness:
             return self.engine.score_topk(Q, self.packed, self.k, idx_offset=self.lo, out=(self.out_v, self.out_i))
         if self.args.exchange == "allgather":
             return self.index.search(Q, self.k)
-        return self.index.search_rowblock(Q, self.k)
+        return self.index.search_rowblock(Q, self.k, self.local_k)
 
     def sync_all(self):
         if self.world > 1:
@@ -441,11 +448,20 @@ def quick_extra(args, name, rank, local_rank, world, shard, steps):
     """Device-resident figure of another BASELINE config inside the same run (no e2e / CPU legs)."""
     h = Harness(args, name, rank, local_rank, world, shard)
     ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3)
+    cert = None
+    if h.local_k is not None:
+        cert = {"local_k": h.local_k, "certificate_failures": h.index.certificate_failures(reset=True)}
+        if cert["certificate_failures"]:
+            h.local_k = None
+            ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3)
+            cert["action"] = "certificate failed: timed again with local_k = k"
     out = {"workload": workload_config(argparse.Namespace(**{**vars(args), "workload": name}), world, shard)["workload"],
            "value": h.units_per_step() * steps / (ms_total * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
            "ms_per_step": ms_total / steps, "main_kernel_ms": fused_ms / max(fused_n, 1),
            "parallelism": workload_config(argparse.Namespace(**{**vars(args), "workload": name}), world, shard)["parallelism"],
            "index_build_s": h.build_s}
+    if cert is not None:
+        out["rank_budgeted_exchange"] = cert
     h.close()
     return out
 
@@ -460,6 +476,8 @@ def main():
     ap.add_argument("--precision", default="f32r", choices=["f32r", "f32x3", "bf16"])
     ap.add_argument("--shard", default=None, choices=["queries", "items"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "allgather"])
+    ap.add_argument("--local-k", default="auto", help="item-sharded p2p exchange: candidates a shard re-scores and ships per row: 'auto' "
+                    "(k/P + 6 sigma + 8, certified on the device, full-k fallback), 'full' (= k), or an integer")
     ap.add_argument("--extras", default=None, help="comma list of other workloads measured in the same run (default: c2,c4 at N=1, c4 at N>1; 'none')")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-precision / recall / pipelined side measurements and the extras")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -495,6 +513,16 @@ def main():
 
     # ---- device-resident timing (one stream, in order) -------------------------------------------------
     ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, sample_clocks=True, local_rank=local_rank)
+    cert = None
+    if h.local_k is not None:
+        # rank-budgeted exchange: every merged row was certified on the device inside the timed region; rows that failed are
+        # counted.  A run with failures is NOT reported: the loop is timed again with the full-k exchange.
+        n_fail = index.certificate_failures(reset=True)
+        cert = {"local_k": h.local_k, "k": k, "rows_certified": h.B * (args.steps + max(args.warmup, 2)), "certificate_failures": n_fail}
+        if n_fail:
+            h.local_k = None
+            ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, sample_clocks=True, local_rank=local_rank)
+            cert["action"] = "certificate failed: timed again with local_k = k"
     qps = h.units_per_step() * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the host-facing call ---------------------------------------------------------
@@ -520,7 +548,7 @@ def main():
             if args.exchange == "allgather":        # replicated batch in, full answer out on every rank
                 v, i = index.search(q_stage[s], k)
             else:                                   # own block of rows in, NVLink all-gather of the blocks, own rows out
-                v, i = index.search_owned(q_stage[s], B, k)
+                v, i = index.search_owned(q_stage[s], B, k, h.local_k)
             vh[s].copy_(v, non_blocking=True)
             ih[s].copy_(i, non_blocking=True)
 
@@ -538,6 +566,8 @@ def main():
         h.sync_all()
     t_e2e = statistics.median(e2e_times)
     e2e_qps = h.units_per_step() * e2e_steps / t_e2e
+    if cert is not None and h.local_k is not None:
+        cert["certificate_failures_e2e"] = index.certificate_failures(reset=True)
     replicated_io = index is not None and args.exchange == "allgather"
     io_ranks = world if (replicated_io or (world > 1 and index is None)) else 1
     h2d = B * k_i * 4 * io_ranks           # bytes over all ranks per step (item-sharded row-block form: each rank moves B/P rows)
@@ -566,7 +596,7 @@ def main():
     # ---- multi-GPU: the sharded answer must equal the single-GPU answer (rank 0 builds the whole index) ----
     sharded_check = None
     if index is not None:
-        got_v, got_i = index.search_rowblock(batches[0], k) if args.exchange != "allgather" else index.search(batches[0], k)
+        got_v, got_i = index.search_rowblock_verified(batches[0], k, h.local_k) if args.exchange != "allgather" else index.search(batches[0], k)
         peer_err = [ch.error() for ch in index._channels.values()]
         if rank == 0:
             if N <= 2_000_000:
@@ -651,6 +681,34 @@ def main():
     }
     if sharded_check is not None:
         line["sharded_equals_single_gpu"] = sharded_check
+    if cert is not None:
+        line["rank_budgeted_exchange"] = cert
+    if index is not None and args.exchange != "allgather":
+        # where the step goes on this rank: local search (pack .. refine / REDO) against exchange (scatter, wait for the
+        # slowest sender, merge), CUDA events on the launching stream, 50 steps
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(50)]
+        h.sync_all()
+        for j, (a0, a1, a2) in enumerate(evs):
+            Qj = batches[j % N_BATCHES]
+            k_loc = h.local_k or k
+            a0.record()
+            lv, li = index.local_topk(Qj, k_loc)
+            a1.record()
+            if index.exchange == "p2p":
+                index._channel(B, k_loc, lv.device).exchange(lv, li, k_out=k)
+            else:
+                index.search_rowblock(Qj, k)                      # (NCCL form: includes a second local search; see local_ms)
+            a2.record()
+        h.sync_all()
+        loc = sum(a0.elapsed_time(a1) for a0, a1, _ in evs) / len(evs)
+        exc = sum(a1.elapsed_time(a2) for _, a1, a2 in evs) / len(evs)
+        if index.exchange != "p2p":
+            exc -= loc
+        line["step_breakdown_ms"] = {"local_search_max_over_ranks": h.max_over_ranks(loc), "local_search_min_over_ranks": -h.max_over_ranks(-loc),
+                                     "exchange_max_over_ranks": h.max_over_ranks(exc), "exchange_min_over_ranks": -h.max_over_ranks(-exc),
+                                     "note": "exchange = key scatter + wait for the slowest sender + merge of the owned rows"}
+        if h.local_k is not None:
+            index.certificate_failures(reset=True)
     if index is None:
         # rows of the last device-resident batch that needed the fallback pass (0 = the fast path served the whole batch)
         engine.score_topk(batches[0], packed, k, idx_offset=lo, out=(h.out_v, h.out_i))

@@ -218,6 +218,13 @@ ANNCUR_API int anncur_peer_scatter_keys(const float* vals, const int64_t* idx, i
 ANNCUR_API int anncur_peer_merge_owned(void* local_base, int rank, int world, int rows_owned, int rows_cap, int k_cap,
                             int k_out, uint32_t epoch, float* out_vals, int64_t* out_idx, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* Rank-budgeted form: when the senders ship only their best k_cap < k_out candidates per row (a row's global top-k takes
+ * ~k/P items from each of P shards, so a sender need not re-score k), anncur_peer_merge_owned also runs the exactness
+ * certificate of every merged row -- exact iff no full sender list was consumed entirely -- and counts the rows that fail
+ * (cumulative per channel).  The caller reads the count (anncur_peer_cert_failures; reset != 0 clears it) and recomputes
+ * with k_cap = k_out when it is not 0: results are never silently short, whatever the placement of the items. */
+ANNCUR_API int anncur_peer_cert_failures(void* local_base, int world, int rows_cap, int k_cap, int reset,
+                              unsigned* count_host, void* stream);
 /* 0 = every wait so far was served; 1 + s = the wait for sender s timed out (~10 s) and the merged rows are invalid. */
 ANNCUR_API int anncur_peer_error(void* local_base, int world, int rows_cap, int k_cap, int* err_host, void* stream);
 

@@ -38,8 +38,8 @@ def test_curapprox_dropin_matches_reference_golden(golden_dir, name, where):
     dense = ap.get_complete_row(Q)
     assert dense.device.type == where
     assert_scores_close(dense.cpu().numpy(), g["rows_get_complete_row"], rel=max(1e-4, tol))
-    for precision in ("f32x3", "f32"):
-        tk = ap.topk_in_row(Q, k, precision=precision)
+    for precision in (None, "f32r", "f32x3", "f32"):              # None = the default kind (f32r), as a reference script would call it
+        tk = ap.topk_in_row(Q, k) if precision is None else ap.topk_in_row(Q, k, precision=precision)
         assert tk.indices.dtype == torch.int64 and tk.values.device.type == where
         assert_sorted_desc(tk.values.cpu().numpy())
         assert_topk_sets_match(tk.indices.cpu().numpy(), g["rows_topk_indices"], full_scores=g["rows_get_complete_row"],

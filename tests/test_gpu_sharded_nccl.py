@@ -23,7 +23,7 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from anncur_b200 import engine
-        from anncur_b200.sharded import ShardedIndex
+        from anncur_b200.sharded import ShardedIndex, suggest_local_k
         rng = np.random.default_rng(4)
         E = torch.from_numpy(rng.standard_normal((96, 150_001), dtype=np.float32)).cuda()
         Q = torch.from_numpy(rng.standard_normal((300, 96), dtype=np.float32)).cuda()
@@ -44,6 +44,13 @@ def _worker(rank, world, port, ret):
                 ok &= int(torch.equal(i, ri[r0:r1]) and torch.allclose(v, rv[r0:r1], rtol=1e-5, atol=1e-5))
                 if exchange == "p2p":
                     ok &= int(all(ch.error() == 0 for ch in ix._channels.values()))
+                    # rank-budgeted form: ship local_k < k candidates per row, certified on the device
+                    lk = suggest_local_k(k, world)
+                    v, i = ix.search_rowblock_verified(Q, k, lk)
+                    ok &= int(torch.equal(i, ri[r0:r1]) and torch.allclose(v, rv[r0:r1], rtol=1e-5, atol=1e-5))
+                    v, i = ix.search_rowblock(Q, k, max(1, k // world))           # too small a budget: rows must fail, never pass short
+                    n_fail = ix.certificate_failures()
+                    ok &= int(n_fail > 0 or torch.equal(i, ri[r0:r1]))
                 ix.close()
         out = torch.tensor([ok], device="cuda")
         dist.all_reduce(out, op=dist.ReduceOp.MIN)
