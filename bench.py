@@ -12,6 +12,7 @@ reference).  Workloads (BASELINE.json):
   n1m  N = 1 000 000 items, k_i = 500, B = 4096, top-100   <- default: the size north_star quotes its target on
   c2   N = 100 000 items,   k_i = 500, B = 4096, top-100      (configs[1]; carried as an extra key of the default run at N = 1)
   c4   N = 10 000 000 items, k_i = 500, B = 4096, top-100     (configs[3]; carried as an extra key of every default run)
+  (c3  adaptive multi-round ANNCUR, N = 100 000, 4 rounds x 125 anchors (configs[2]) is an extra key of the default run at N = 1)
 
 N = 1: the whole index on one GPU.  N > 1 (torchrun, one rank per GPU): **items sharded** -- rank p holds E[:, lo_p:hi_p],
 every rank scores the same batch against its slice, then ONE exchange step: each row's P candidate lists travel to the rank
@@ -22,7 +23,9 @@ regions; total work is fixed as N grows (``scaling: "strong"``).  In every multi
 and asserts that the sharded answer equals the single-GPU answer on a row sample.  ``--shard queries`` = replicas of the
 index, no collective (weak scaling; kept for comparison).
 
-``value``  : device-resident throughput (queries already in HBM), CUDA events, max over ranks, one stream, in order.
+``value``  : device-resident throughput (queries already in HBM), CUDA events, max over ranks; N = 1 one stream in order, N > 1
+             two rotating streams (the exchange of batch j overlaps the kernels of batch j + 1; the in-order figure is printed
+             beside it as ``value_with_1_stream``).
 ``e2e``    : the same through the host-facing call: N = 1 ``anncur_search_host`` (C ABI: pinned host Q -> H2D -> kernels ->
              D2H of values + indices every step); N > 1 ``ShardedIndex.search_owned``: every rank uploads ITS block of the
              batch, the blocks are all-gathered over NVLink, and every rank downloads the merged rows it owns.
@@ -56,6 +59,7 @@ WORKLOADS = {
 DEFAULT_STEPS = {"c2": 200, "n1m": 200, "c4": 30}
 RANK_LOW, NOISE = 64, 0.05
 N_BATCHES = 4            # distinct query batches rotated through the steps
+DEV_STREAMS = 2          # multi-GPU device-resident loop: rotating streams (see main)
 CHECK_ROWS = 256         # rows of the sharded == single-GPU assertion
 
 
@@ -249,6 +253,31 @@ def cpu_topk_throughput(fn, E_host, Q_host, k, repeats, warmup=1):
             times.append(dt)
     med = statistics.median(times)
     return Q_host.shape[0] / med, times
+
+
+def pin_rank_to_cores(local_rank, world):
+    """One process per GPU: give each rank its own slice of the cores NVML reports as local to its GPU (all ranks of a box
+    usually report the same set -- then the set is split evenly), so that the launch threads of the ranks do not migrate
+    over each other.  Returns the core list, or None when affinity cannot be set."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+    except Exception:
+        local = []
+    allowed = sorted(os.sched_getaffinity(0))
+    cores = [c for c in local if c in allowed] or allowed
+    per = max(1, len(cores) // world)
+    mine = cores[(local_rank * per) % len(cores):(local_rank * per) % len(cores) + per] or cores
+    try:
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -447,13 +476,13 @@ class Harness:
 def quick_extra(args, name, rank, local_rank, world, shard, steps):
     """Device-resident figure of another BASELINE config inside the same run (no e2e / CPU legs)."""
     h = Harness(args, name, rank, local_rank, world, shard)
-    ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3)
+    ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3, streams=DEV_STREAMS if h.index is not None else 1)
     cert = None
     if h.local_k is not None:
         cert = {"local_k": h.local_k, "certificate_failures": h.index.certificate_failures(reset=True)}
         if cert["certificate_failures"]:
             h.local_k = None
-            ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3)
+            ms_total, _, fused_ms, fused_n, _ = h.time_device(steps, 3, streams=DEV_STREAMS if h.index is not None else 1)
             cert["action"] = "certificate failed: timed again with local_k = k"
     out = {"workload": workload_config(argparse.Namespace(**{**vars(args), "workload": name}), world, shard)["workload"],
            "value": h.units_per_step() * steps / (ms_total * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
@@ -464,6 +493,35 @@ def quick_extra(args, name, rank, local_rank, world, shard, steps):
         out["rank_budgeted_exchange"] = cert
     h.close()
     return out
+
+
+def run_c3(device, steps=3, B=4096, N=100_000, k_q=500, rounds=4, per_round=125, k=100):
+    """BASELINE configs[2]: adaptive multi-round ANNCUR (NOT in the reference, parity unpinned): per query 4
+    rounds of 125 anchor items chosen by re-solving e_q = c_q . pinv(R_anc[:, I_t]) and re-scoring all items; the exact-score
+    matrix stands in for the cross-encoder calls and stays on the device.  A step = the whole procedure for one batch."""
+    import torch
+    from anncur_b200 import adaptive_anncur
+    g = torch.Generator(device=device)
+    g.manual_seed(0)
+    r = RANK_LOW
+    Y = torch.randn((N, r), generator=g, device=device)
+    R = torch.randn((k_q, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((k_q, N), generator=g, device=device)
+    X = torch.randn((B, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((B, N), generator=g, device=device)
+    first = torch.randperm(N, generator=g, device=device)[:per_round].sort().values
+    adaptive_anncur(R, X[:256], first, rounds, per_round, k)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        anc, idx, val = adaptive_anncur(R, X, first, rounds, per_round, k)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    exact = torch.topk(X[:512], k, dim=1).indices
+    recall = (idx[:512].unsqueeze(2) == exact.unsqueeze(1)).any(2).float().mean().item()
+    return {"workload": f"c3: adaptive ANNCUR, N={N} items, k_q={k_q}, {rounds} rounds x {per_round} anchors, batch {B} queries/step, top-{k} by exact score",
+            "value": B / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": steps, "ms_per_step": ms,
+            "recall_at_k_vs_exact": recall, "parity": "unpinned (no reference implementation; checked against our own CPU restatement)"}
 
 
 def main():
@@ -478,6 +536,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "allgather"])
     ap.add_argument("--local-k", default="auto", help="item-sharded p2p exchange: candidates a shard re-scores and ships per row: 'auto' "
                     "(k/P + 6 sigma + 8, certified on the device, full-k fallback), 'full' (= k), or an integer")
+    ap.add_argument("--pin-cores", action="store_true", help="multi-GPU: pin each rank to its own slice of the GPU-local host cores")
     ap.add_argument("--extras", default=None, help="comma list of other workloads measured in the same run (default: c2,c4 at N=1, c4 at N>1; 'none')")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-precision / recall / pipelined side measurements and the extras")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -501,6 +560,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    # measured on a 4-GPU box (round 2): pinning each rank to its own 1/P slice of the cores made nothing faster and the
+    # host-timed legs slightly slower (NCCL's proxy / watchdog threads then share the slice with the launch thread) -> opt-in
+    pinned_cores = pin_rank_to_cores(local_rank, world) if args.pin_cores else None
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -512,7 +574,11 @@ def main():
     lo = h.lo
 
     # ---- device-resident timing (one stream, in order) -------------------------------------------------
-    ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, sample_clocks=True, local_rank=local_rank)
+    # N = 1: one stream, in order.  N > 1: the same steps issued over DEV_STREAMS rotating streams (each with its own exchange
+    # channel), so that a rank waiting for the slowest sender of batch j already runs the kernels of batch j + 1 -- the GPUs of
+    # a box drift apart by several % per step under their power caps, and an in-order loop pays the slowest rank every step.
+    dev_streams = DEV_STREAMS if index is not None else 1
+    ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, streams=dev_streams, sample_clocks=True, local_rank=local_rank)
     cert = None
     if h.local_k is not None:
         # rank-budgeted exchange: every merged row was certified on the device inside the timed region; rows that failed are
@@ -521,7 +587,7 @@ def main():
         cert = {"local_k": h.local_k, "k": k, "rows_certified": h.B * (args.steps + max(args.warmup, 2)), "certificate_failures": n_fail}
         if n_fail:
             h.local_k = None
-            ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, sample_clocks=True, local_rank=local_rank)
+            ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, streams=dev_streams, sample_clocks=True, local_rank=local_rank)
             cert["action"] = "certificate failed: timed again with local_k = k"
     qps = h.units_per_step() * args.steps / (ms_total * 1e-3)
 
@@ -679,6 +745,8 @@ def main():
                 "streams": N_SLOTS},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "index_build_s": h.build_s,
     }
+    if pinned_cores is not None:
+        line["host_cores_of_rank0"] = pinned_cores
     if sharded_check is not None:
         line["sharded_equals_single_gpu"] = sharded_check
     if cert is not None:
@@ -715,11 +783,15 @@ def main():
         line["redo_rows_last_batch"] = engine.last_redo_rows(B, packed, k)
 
     # ---- side measurements ---------------------------------------------------------------------------------
+    line["device_streams"] = dev_streams
     if not args.no_extra:
-        # the same in-order work issued over two rotating streams (exchange / tail of batch j under the kernels of batch j+1)
-        ms2, _, _, _, _ = h.time_device(args.steps, 4, streams=2)
-        line["pipelined_2_streams"] = {"value": h.units_per_step() * args.steps / (ms2 * 1e-3), "unit": "queries/s",
-                                       "ms_per_step": ms2 / args.steps}
+        # the same steps over other stream counts (1 = strictly in order: every step pays the slowest rank of that step)
+        for ns in [n for n in (1, 2, 3) if n != dev_streams]:
+            ms2, _, _, _, _ = h.time_device(args.steps, 4, streams=ns)
+            line[f"value_with_{ns}_stream{'s' if ns > 1 else ''}"] = {"value": h.units_per_step() * args.steps / (ms2 * 1e-3), "unit": "queries/s",
+                                                                  "ms_per_step": ms2 / args.steps}
+        if cert is not None and h.local_k is not None:
+            cert["certificate_failures_other_stream_counts"] = index.certificate_failures(reset=True)
     if world == 1 and not args.no_extra:
         line["other_precision"] = []
         v_a, i_a = engine.score_topk(batches[0], packed, k)
@@ -764,13 +836,18 @@ def main():
 
     # ---- the other BASELINE configs, device-resident figure only ---------------------------------------------
     if args.extras is None:
-        extras = [] if (args.no_extra or args.workload != "n1m") else (["c2", "c4"] if world == 1 else ["c4"])
+        extras = [] if (args.no_extra or args.workload != "n1m") else (["c2", "c3", "c4"] if world == 1 else ["c4"])
     else:
         extras = [e for e in args.extras.split(",") if e and e != "none"]
     if extras:
         line["extras"] = {}
         for name in extras:
             try:
+                if name == "c3":
+                    if world == 1:
+                        line["extras"][name] = run_c3(device)
+                        torch.cuda.empty_cache()
+                    continue
                 line["extras"][name] = quick_extra(args, name, rank, local_rank, world, shard, steps=min(args.steps, 100 if name == "c2" else 20))
             except Exception as exc:                                     # an extra never takes the headline line down
                 line["extras"][name] = {"error": f"{type(exc).__name__}: {exc}"}
