@@ -87,13 +87,16 @@ def profile_read():
 
 # ---- K1 -------------------------------------------------------------------------------------------
 def pinv(A, rcond=1e-15, return_cond=False):
-    """pinv of an (m x n) fp32 matrix -> (n x m) fp32 on the GPU (eval/matrix_approx_zeshel.py:47,49)."""
+    """pinv of an (m x n) fp32 matrix -> (n x m) fp32 on the GPU (eval/matrix_approx_zeshel.py:47,49).
+    Full-rank, well-conditioned inputs take the fp64 normal-equations route (Gram + cooperative Cholesky + triangular solves),
+    everything else -- rank-deficient, ill-conditioned, rcond > 1e-10, or ``return_cond=True`` (singular values wanted) -- the
+    fp64 Jacobi SVD; the choice is made on the device."""
     lib = _lib.load()
     A = _f32(A)
     assert A.dim() == 2
     m, n = A.shape
     out = torch.empty((n, m), dtype=torch.float32, device=A.device)
-    cond = torch.zeros(2, dtype=torch.float64, device=A.device)
+    cond = torch.zeros(2, dtype=torch.float64, device=A.device) if return_cond else None
     if m > 0 and n > 0:
         nbytes = lib.anncur_pinv_workspace_bytes(m, n)
         ws = WORKSPACE.get("pinv", nbytes, A.device)

@@ -67,8 +67,9 @@ class CURApprox(object):
             U = engine.gemm(engine.gemm(engine.pinv(self._C_dev, rcond), A_dev), engine.pinv(self._R_dev, rcond))
             self._cond = None
         else:               # U = pinv(C[row_idxs, :])                (reference :49)
-            U, cond = engine.pinv(intersect, rcond, return_cond=True)
-            self._cond = cond
+            U = engine.pinv(intersect, rcond)
+            self._cond = "lazy"               # singular values only when somebody reads intersect_cond
+            self._intersect = intersect
         self._U_dev = U                                                      # k_c x k_r
         if approx_preference == "cols":                                      # reference :60-62
             self._latent_rows_dev = engine.gemm(self._C_dev, U)              # n x k_r
@@ -105,7 +106,14 @@ class CURApprox(object):
         """s_max / s_min_kept of the inverted intersection (None for the cur_oracle construction)."""
         if self._cond is None:
             return None
-        s_max, s_min = self._cond.tolist()
+        if isinstance(self._cond, str):
+            if self._intersect.numel() == 0:
+                return None
+            s = engine.singular_values(self._intersect)
+            cutoff = max(self.rcond, 1e-13) * float(s[0])
+            kept = s[s > cutoff]
+            self._cond = (float(s[0]), float(kept[-1]) if kept.numel() else 0.0)
+        s_max, s_min = self._cond
         return float("inf") if s_min == 0 else s_max / s_min
 
     @staticmethod

@@ -67,7 +67,12 @@ ANNCUR_API const char* anncur_last_error(void);
  * A is m x n fp32 (lda), out is n x m fp32 (ldo).  One-sided Jacobi SVD in fp64; singular values
  * <= max(rcond, 8 tol) * s_max are dropped (numpy's rule with a floor at what fp64 sweeps resolve, see
  * anncur_jacobi_status; the reference uses numpy's default rcond = 1e-15).
- * cond_out (optional, device double[2]) receives {s_max, s_min_kept}. */
+ * cond_out (optional, device double[2]) receives {s_max, s_min_kept}.
+ * Route: with cond_out == NULL and rcond <= 1e-10 a full-rank, well-conditioned input is served by the fp64 normal equations
+ * (Gram, cooperative blocked Cholesky, two triangular solves per column; ~25x faster than the SVD); a pivot breakdown or a
+ * diagonal ratio of the factor above 3e3 (a lower bound of the condition number) falls through to the Jacobi SVD.  The
+ * decision is taken on the device (kernels of the route not taken return at once): the call stays asynchronous.
+ * ANNCUR_PINV_JACOBI_ONLY=1 in the environment disables the first route. */
 ANNCUR_API size_t anncur_pinv_workspace_bytes(int m, int n);
 ANNCUR_API int anncur_pinv_f32(const float* A, int m, int n, int lda, double rcond, float* out, int ldo,
                     double* cond_out, void* workspace, size_t workspace_bytes, void* stream);

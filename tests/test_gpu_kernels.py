@@ -134,12 +134,68 @@ def test_pinv_rank_deficient_anchor_columns(eng):
     assert float(eng.pinv(torch.zeros(9, 4).cuda()).abs().max()) == 0.0
 
 
+def _pinv_status(eng, shape):
+    import ctypes as C
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    ws = eng.WORKSPACE.get("pinv", lib.anncur_pinv_workspace_bytes(*shape), torch.device("cuda", torch.cuda.current_device()))
+    st = torch.zeros(4, dtype=torch.float64, device="cuda")
+    _lib.check(lib.anncur_jacobi_status(C.c_void_p(ws.data_ptr()), C.c_void_p(st.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return st.tolist()
+
+
+@pytest.mark.parametrize("m,n", [(2000, 500), (500, 2000), (64, 64), (333, 97), (40, 700), (1500, 33), (2, 2)])
+def test_pinv_cholesky_route_matches_numpy(eng, m, n):
+    """Full-rank, well-conditioned intersections (what the CUR build sees) take the fp64 normal-equations route: Gram +
+    cooperative Cholesky + triangular solves.  Same answer as np.linalg.pinv to fp32 output rounding, tall and wide; the
+    status says which route ran (0 sweeps = no Jacobi)."""
+    A = O.synthetic_scores(m, n, rank=min(m, n, 64), noise=0.05, seed=3 * m + n)
+    if m == n:
+        A = A + 3.0 * np.eye(m, dtype=np.float32)                    # keep the square case well conditioned
+    P = eng.pinv(torch.from_numpy(A).cuda()).cpu().numpy().astype(np.float64)
+    A64 = A.astype(np.float64)
+    s = np.linalg.svd(A64, compute_uv=False)
+    c = s[0] / s[-1]
+    ref = np.linalg.pinv(A64, rcond=1e-15)
+    assert np.linalg.norm(P - ref) / np.linalg.norm(ref) <= max(3e-7, c * c * 1e-14)
+    s_max, s_min, conv, sweeps = _pinv_status(eng, (m, n))
+    assert conv == 1.0
+    if c < 1e3:
+        assert sweeps == 0.0, "a well-conditioned input must be served by the Cholesky route"
+        assert s_max <= s[0] * (1 + 1e-9) and s_min >= s[-1] * (1 - 1e-9)      # diagonal of L: inside the singular range
+    # the Jacobi route on the same input agrees
+    PJ = eng.pinv(torch.from_numpy(A).cuda(), return_cond=True)[0].cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(P - PJ) / np.linalg.norm(ref) <= max(2e-7, c * c * 1e-14)
+
+
+def test_pinv_cholesky_route_refuses_hard_inputs(eng):
+    """Ill-conditioned (cond 1e7) and rank-deficient inputs must fall through to the Jacobi SVD on the device -- and give
+    the SVD's answer -- and a truncating rcond never takes the Cholesky route."""
+    rng = np.random.default_rng(8)
+    U, _ = np.linalg.qr(rng.standard_normal((400, 60)))
+    V, _ = np.linalg.qr(rng.standard_normal((60, 60)))
+    A = ((U * np.logspace(0, -7, 60)[None, :]) @ V.T).astype(np.float32)
+    P = eng.pinv(torch.from_numpy(A).cuda()).cpu().numpy().astype(np.float64)
+    assert _pinv_status(eng, A.shape)[3] >= 1.0                               # Jacobi sweeps ran
+    ref = np.linalg.pinv(A.astype(np.float64), rcond=1e-15)           # entries up to ~1e5: compare the inverse itself, the fp32
+    assert np.linalg.norm(P - ref) <= 1e-5 * np.linalg.norm(ref)      # rounding of the OUTPUT alone moves A P A by cond * eps_32
+    B = rng.standard_normal((200, 30)).astype(np.float32)
+    B[:, 11] = B[:, 4]
+    PB = eng.pinv(torch.from_numpy(B).cuda()).cpu().numpy().astype(np.float64)
+    assert _pinv_status(eng, B.shape)[3] >= 1.0
+    assert np.linalg.norm(PB - np.linalg.pinv(B.astype(np.float64), rcond=1e-10)) <= 1e-5 * np.linalg.norm(PB)
+    C_ = rng.standard_normal((300, 40)).astype(np.float32)
+    eng.pinv(torch.from_numpy(C_).cuda(), rcond=1e-3)
+    assert _pinv_status(eng, C_.shape)[3] >= 1.0
+    assert float(eng.pinv(torch.zeros(9, 4).cuda()).abs().max()) == 0.0
+
+
 def test_jacobi_status_reports_convergence(eng):
     import ctypes as C
     from anncur_b200 import _lib
     lib = _lib.load()
     A = torch.from_numpy(O.synthetic_scores(300, 64, rank=32, seed=2)).cuda()
-    eng.pinv(A)                                         # raises if the sweeps had not converged
+    eng.pinv(A, return_cond=True)                       # singular values wanted -> the Jacobi route; raises if not converged
     ws = eng.WORKSPACE.get("pinv", lib.anncur_pinv_workspace_bytes(300, 64), A.device)
     st = torch.zeros(4, dtype=torch.float64, device="cuda")
     _lib.check(lib.anncur_jacobi_status(C.c_void_p(ws.data_ptr()), C.c_void_p(st.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))

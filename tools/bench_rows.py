@@ -77,7 +77,7 @@ Q = A_test[:, anc].contiguous()
 U = engine.pinv(C)
 t = gpu_ms(lambda: engine.pinv(C), warm=1, reps=3)
 Ch = C.cpu()
-emit("A1", f"U = pinv(C[{N_TRAIN}x{K_I}])  (fp64 one-sided Jacobi SVD)", t, cpu_s(lambda: O.pinv_f32(Ch)), "full size, np.linalg.pinv",
+emit("A1", f"U = pinv(C[{N_TRAIN}x{K_I}])  (fp64 normal equations: Gram + cooperative Cholesky + solves; Jacobi SVD fallback)", t, cpu_s(lambda: O.pinv_f32(Ch)), "full size, np.linalg.pinv",
      bound="latency (tournament of column-pair rotations, ~10 sweeps x 499 rounds of small launches)")
 # A2 E = U R
 E = engine.gemm(U, R)
