@@ -56,6 +56,10 @@ PROTOTYPES = {
     "anncur_recon_error_f32": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),
     "anncur_adaptive_round_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
     "anncur_adaptive_round": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
+    "anncur_adaptive_solve_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
+    "anncur_adaptive_solve": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _sz, _vp]),
+    "anncur_transpose_f32": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),
+    "anncur_filter_excluded": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "anncur_profile_enable": (_i, [_i]),
     "anncur_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "anncur_kernel_launch_count": (C.c_uint64, []),

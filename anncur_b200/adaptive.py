@@ -3,8 +3,8 @@ statement of the same procedure is oracle.cur_oracle.adaptive_anncur, which the 
 
 Per query q, rounds t = 1..T with a growing anchor-item set I_t (|I_t| = t * k_per_round):
     c_q = exact_rows[q, I_t]                       stands in for CE(q, I_t): a gather from the exact score matrix
-    e_q = c_q . pinv(R_anc[:, I_t])                per-query least squares        } one anncur_adaptive_round call
-    s_q = e_q . R_anc with I_t masked              approximate scores of all items } for the whole batch
+    e_q = c_q . pinv(R_anc[:, I_t])                per-query least squares           anncur_adaptive_solve (whole batch)
+    s_q = e_q . R_anc with I_t masked              approximate scores of all items   fused score + top-k on the packed R_anc
     I_{t+1} = I_t  U  top-k_per_round(s_q)
 Round 1 uses ``first_anchors`` (shared by all queries).  The answer is the top-``top_k`` of I_T by EXACT score, so the last
 round needs no solve: T rounds cost T - 1 calls."""
@@ -13,17 +13,51 @@ import torch
 from . import engine
 
 
-def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top_k, rcond=1e-15):
-    """Returns (anchors [B x T*k_per_round] int64 in selection order, idx [B x top_k] int64, exact scores [B x top_k])."""
+class AdaptiveIndex:
+    """What stays fixed across rounds and batches: R_anc packed for the fused re-score (the anchor QUERIES' scores play the
+    items' embeddings, K = k_q), and its item-major fp32 copy for the per-query gathers of the solve.  ``sharded`` = a
+    ``ShardedIndex`` over this rank's item slice: the re-score then runs on every rank's slice with one exchange per round
+    (all ranks end with the same candidates, so the replicated solve stays in step)."""
+
+    def __init__(self, R_anc, precision="f32r", sharded=None):
+        self.R = engine._f32(R_anc)
+        self.k_q, self.N = self.R.shape
+        self.Rt = engine.transpose(self.R)
+        self.sharded = sharded
+        self.packed = None if sharded is not None else engine.PackedItems(self.R, precision)
+
+    def topk(self, e, k):
+        if self.sharded is not None:
+            return self.sharded.search(e, k)
+        return engine.score_topk(e, self.packed, k)
+
+
+def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top_k, rcond=1e-15, *, rescore="fused",
+                    index=None, precision="f32r"):
+    """Returns (anchors [B x T*k_per_round] int64 in selection order, idx [B x top_k] int64, exact scores [B x top_k]).
+
+    ``rescore="fused"`` (default): per round one ``anncur_adaptive_solve`` (e_b for the whole batch), the fused tensor-core
+    score + top-(k_per_round + m) on the packed R_anc -- no B x N block -- and ``anncur_filter_excluded`` to drop the anchors.
+    ``rescore="ffma"``: the round-1 path (one ``anncur_adaptive_round`` call: FFMA re-score of a B x N block + masked row top-k),
+    also taken when k_per_round + m exceeds the fused kernel's largest k.  ``index`` = an ``AdaptiveIndex`` to reuse."""
     R = engine._f32(R_anc)
     X = engine._f32(exact_rows, device=R.device)
     B = X.shape[0]
     first = torch.as_tensor(first_anchors, dtype=torch.int64, device=R.device)
     assert first.dim() == 1 and first.numel() == k_per_round and top_k <= n_rounds * k_per_round
     anchors = first.unsqueeze(0).expand(B, -1).contiguous()
+    fused = rescore == "fused" and n_rounds * k_per_round <= engine.MAX_K_FUSED and R.shape[1] >= 4 * n_rounds * k_per_round
+    if fused and index is None and n_rounds > 1:
+        index = AdaptiveIndex(R, precision)
     for t in range(n_rounds - 1):
         c = torch.gather(X, 1, anchors)                                          # exact scores of the anchors so far
-        nxt, _ = engine.adaptive_round(R, anchors, c, k_per_round, rcond)        # K8: re-solve + masked re-score + pick
+        m = anchors.shape[1]
+        if fused:
+            e = engine.adaptive_solve(R, anchors, c, rcond, Rt=index.Rt)         # K8a: per-query re-solve
+            cv, ci = index.topk(e, k_per_round + m)                              # K3+K4 on the packed R_anc: the re-score
+            _, nxt = engine.filter_excluded(cv, ci, anchors, k_per_round)        # the anchors leave the candidate lists
+        else:
+            nxt, _ = engine.adaptive_round(R, anchors, c, k_per_round, rcond)    # K8: re-solve + masked re-score + pick
         anchors = torch.cat([anchors, nxt], dim=1)
     ex = torch.gather(X, 1, anchors)
     vals, idx = engine.merge_topk(ex, anchors, top_k)                            # K9: best top_k of the anchors, ties -> lower index

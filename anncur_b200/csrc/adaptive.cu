@@ -308,6 +308,118 @@ static AdaptivePlan adaptive_plan(int k_q, int m, int64_t n_items) {
     return p;
 }
 
+// ---- split form: the per-query solve alone, and the anchor filter of a fused re-score --------------------------------------
+// adaptive_solve leaves e_b = c_b . pinv(R_anc[:, I_b]) (n_queries x k_q fp32); the caller re-scores with the fused tensor-core
+// kernel on the PACKED R_anc (anncur_score_topk with k = n_next + m: no B x N block, shardable) and drops the anchors from the
+// candidate lists with filter_excluded -- "masked re-score" without a mask in the inner loop: a row's m anchors can displace
+// at most m of the best n_next + m candidates.
+static AdaptivePlan adaptive_solve_plan(int k_q, int m, int64_t n_items) {
+    AdaptivePlan p{};
+    size_t off = 0;
+    p.off_rt = off; off += align_up(sizeof(float) * size_t(n_items) * k_q, 256);
+    p.off_mt = off; off += align_up(sizeof(float) * size_t(AD_QB) * m * k_q, 256);
+    p.off_g = off; off += align_up(sizeof(double) * size_t(AD_QB) * (m + 1) * m, 256);
+    p.off_y = off; off += align_up(sizeof(double) * size_t(AD_QB) * m, 256);
+    p.off_e = off; p.off_s = off;
+    p.total = off;
+    return p;
+}
+
+size_t adaptive_solve_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items) {
+    (void)n_queries;
+    if (k_q <= 0 || m <= 0 || n_items <= 0) return 256;
+    return adaptive_solve_plan(k_q, m, n_items).total;
+}
+
+// Rt_cached != nullptr: the item-major copy R_anc^T (n_items x k_q fp32) kept by the caller across rounds (it does not
+// change); otherwise it is rebuilt in the workspace.
+int adaptive_solve(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const float* Rt_cached, const int64_t* anchors,
+                   const float* c, int n_queries, int m, double rcond, float* e_out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
+    if (m > k_q) { set_error("adaptive_solve: m = %d anchors > k_q = %d anchor queries is not supported", m, k_q); return ANNCUR_E_UNSUPPORTED; }
+    const AdaptivePlan pl = adaptive_solve_plan(k_q, m, n_items);
+    if (workspace_bytes < pl.total) { set_error("adaptive_solve workspace too small: %zu < %zu", workspace_bytes, pl.total); return ANNCUR_E_WORKSPACE; }
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* Rt = reinterpret_cast<float*>(ws + pl.off_rt);
+    float* Mt = reinterpret_cast<float*>(ws + pl.off_mt);
+    double* G = reinterpret_cast<double*>(ws + pl.off_g);
+    double* y = reinterpret_cast<double*>(ws + pl.off_y);
+    const size_t ch_smem = sizeof(double) * (size_t(m + 1) * CH_LD + size_t(m));
+    if (ch_smem > 200 * 1024) { set_error("adaptive_solve: m = %d anchors need %zu bytes of shared memory per query", m, ch_smem); return ANNCUR_E_UNSUPPORTED; }
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(cholesky_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ch_smem)));
+    if (Rt_cached == nullptr) {
+        dim3 tgrid(unsigned((n_items + 31) / 32), unsigned((k_q + 31) / 32));
+        transpose_kernel<<<tgrid, dim3(32, 8), 0, stream>>>(R_anc, ldr, k_q, n_items, Rt);
+        ANNCUR_LAUNCH_OK("transpose_kernel");
+    }
+    const float* Rt_use = Rt_cached ? Rt_cached : Rt;
+    for (int q0 = 0; q0 < n_queries; q0 += AD_QB) {
+        const int nq = n_queries - q0 < AD_QB ? n_queries - q0 : AD_QB;
+        const int64_t* anc = anchors + int64_t(q0) * m;
+        const int64_t warps = int64_t(nq) * m;
+        gather_anchor_rows_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, stream>>>(Rt_use, k_q, anc, m, nq, Mt);
+        ANNCUR_LAUNCH_OK("gather_anchor_rows_kernel");
+        dim3 ggrid(unsigned((m + GR_T - 1) / GR_T), unsigned((m + GR_T - 1) / GR_T), unsigned(nq));
+        gram_kernel<<<ggrid, 256, 0, stream>>>(Mt, m, k_q, G);
+        ANNCUR_LAUNCH_OK("gram_kernel");
+        cholesky_solve_kernel<<<nq, 256, ch_smem, stream>>>(G, c + int64_t(q0) * m, Mt, m, k_q, rcond, y, e_out + int64_t(q0) * k_q);
+        ANNCUR_LAUNCH_OK("cholesky_solve_kernel");
+    }
+    return ANNCUR_OK;
+}
+
+// out[row] = the first n_out entries of cand[row] (best first; idx < 0 = padding) whose index is not in excl[row]; short rows
+// are padded with (ANNCUR_PAD_VAL, -1).  One warp per row, order kept.
+__global__ void __launch_bounds__(256)
+filter_excluded_kernel(const float* __restrict__ cand_vals, const int64_t* __restrict__ cand_idx, int n_rows, int k_in,
+                       const int64_t* __restrict__ excl, int m, int n_out, float* __restrict__ out_vals, int64_t* __restrict__ out_idx) {
+    extern __shared__ int64_t ex_s[];                          // [warps][m]
+    const int warp = threadIdx.x >> 5, lane = int(lane_id());
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= n_rows) return;
+    int64_t* ex = ex_s + size_t(warp) * m;
+    for (int t = lane; t < m; t += 32) ex[t] = excl[int64_t(row) * m + t];
+    __syncwarp();
+    int n_done = 0;
+    for (int t0 = 0; t0 < k_in && n_done < n_out; t0 += 32) {
+        const int t = t0 + lane;
+        const int64_t i = t < k_in ? cand_idx[int64_t(row) * k_in + t] : -1;
+        bool keep = i >= 0;
+        for (int u = 0; keep && u < m; ++u) keep = ex[u] != i;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        const int pos = n_done + __popc(ballot & ((1u << lane) - 1u));
+        if (keep && pos < n_out) {
+            out_vals[int64_t(row) * n_out + pos] = cand_vals[int64_t(row) * k_in + t];
+            out_idx[int64_t(row) * n_out + pos] = i;
+        }
+        n_done += __popc(ballot);
+    }
+    for (int t = (n_done < n_out ? n_done : n_out) + lane; t < n_out; t += 32) {
+        out_vals[int64_t(row) * n_out + t] = ANNCUR_PAD_VAL;
+        out_idx[int64_t(row) * n_out + t] = -1;
+    }
+}
+
+int filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows, int k_in, const int64_t* excl, int m, int n_out,
+                    float* out_vals, int64_t* out_idx, cudaStream_t stream) {
+    if (n_rows == 0) return ANNCUR_OK;
+    const int warps = 8;
+    const size_t smem = sizeof(int64_t) * size_t(warps) * (m > 0 ? m : 1);
+    if (smem > 200 * 1024) { set_error("filter_excluded: %d excluded indices per row do not fit shared memory", m); return ANNCUR_E_UNSUPPORTED; }
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(filter_excluded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    filter_excluded_kernel<<<(n_rows + warps - 1) / warps, warps * 32, smem, stream>>>(cand_vals, cand_idx, n_rows, k_in, excl, m, n_out,
+                                                                                     out_vals, out_idx);
+    ANNCUR_LAUNCH_OK("filter_excluded_kernel");
+    return ANNCUR_OK;
+}
+
+int transpose_rows(const float* in, int64_t ld_in, int rows, int64_t cols, float* out, cudaStream_t stream) {
+    dim3 tgrid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32));
+    transpose_kernel<<<tgrid, dim3(32, 8), 0, stream>>>(in, ld_in, rows, cols, out);
+    ANNCUR_LAUNCH_OK("transpose_kernel");
+    return ANNCUR_OK;
+}
+
 size_t adaptive_round_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items, int n_next) {
     (void)n_queries; (void)n_next;
     if (k_q <= 0 || m <= 0 || n_items <= 0) return 256;

@@ -364,4 +364,34 @@ int anncur_adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_it
                           workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+size_t anncur_adaptive_solve_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items) {
+    return adaptive_solve_workspace_bytes(n_queries, k_q, m, n_items);
+}
+
+int anncur_adaptive_solve(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const float* Rt_cached,
+                          const int64_t* anchors, const float* c, int n_queries, int m, double rcond, float* e_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && k_q > 0 && m > 0 && n_items > 0, "adaptive_solve: bad shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE((R_anc || Rt_cached) && anchors && c && e_out && workspace, "adaptive_solve: null pointer");
+    ANNCUR_REQUIRE(Rt_cached || ldr >= n_items, "adaptive_solve: ldr < n_items");
+    return adaptive_solve(R_anc, ldr, k_q, n_items, Rt_cached, anchors, c, n_queries, m, rcond, e_out, workspace, workspace_bytes,
+                          cudaStream_t(stream));
+}
+
+int anncur_transpose_f32(const float* in, int64_t ld_in, int rows, int64_t cols, float* out, void* stream) {
+    ANNCUR_REQUIRE(rows >= 0 && cols >= 0, "transpose: negative shape");
+    if (rows == 0 || cols == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(in && out && ld_in >= cols, "transpose: null pointer or ld_in < cols");
+    return transpose_rows(in, ld_in, rows, cols, out, cudaStream_t(stream));
+}
+
+int anncur_filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows, int k_in, const int64_t* excluded,
+                           int m, int n_out, float* out_vals, int64_t* out_idx, void* stream) {
+    ANNCUR_REQUIRE(n_rows >= 0 && k_in >= 1 && m >= 0 && n_out >= 1, "filter_excluded: bad shape");
+    if (n_rows == 0) return ANNCUR_OK;
+    ANNCUR_REQUIRE(cand_vals && cand_idx && out_vals && out_idx && (m == 0 || excluded), "filter_excluded: null pointer");
+    return filter_excluded(cand_vals, cand_idx, n_rows, k_in, excluded, m, n_out, out_vals, out_idx, cudaStream_t(stream));
+}
+
 }  // extern "C"

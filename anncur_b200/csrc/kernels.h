@@ -95,4 +95,12 @@ int adaptive_round(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, co
                    const float* c, int n_queries, int m, double rcond, int n_next, int64_t* next_idx,
                    float* next_val, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+size_t adaptive_solve_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items);
+int adaptive_solve(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const float* Rt_cached, const int64_t* anchors,
+                   const float* c, int n_queries, int m, double rcond, float* e_out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+int filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows, int k_in, const int64_t* excl, int m, int n_out,
+                    float* out_vals, int64_t* out_idx, cudaStream_t stream);
+int transpose_rows(const float* in, int64_t ld_in, int rows, int64_t cols, float* out, cudaStream_t stream);
+
 }  // namespace anncur

@@ -572,3 +572,53 @@ def adaptive_round(R_anc, anchors, c, n_next, rcond=1e-15):
                                                  float(rcond), int(n_next), _ptr(next_idx), _ptr(next_val), _ptr(ws),
                                                  ws.numel(), _stream()))
     return next_idx, next_val
+
+
+def transpose(X):
+    """X (rows x cols fp32) -> X^T contiguous (cols x rows) with the library's tiled transpose."""
+    lib = _lib.load()
+    X = _f32(X)
+    rows, cols = X.shape
+    out = torch.empty((cols, rows), dtype=torch.float32, device=X.device)
+    if rows > 0 and cols > 0:
+        with torch.cuda.device(X.device):
+            _lib.check(lib.anncur_transpose_f32(_ptr(X), _ld(X), rows, cols, _ptr(out), _stream()))
+    return out
+
+
+def adaptive_solve(R_anc, anchors, c, rcond=1e-15, Rt=None):
+    """e_b = c_b . pinv(R_anc[:, I_b]) for a batch of queries (anncur_adaptive_solve): (B x k_q) fp32.  ``Rt`` = R_anc^T kept
+    by the caller across rounds (``engine.transpose(R_anc)``)."""
+    lib = _lib.load()
+    R_anc = _f32(R_anc)
+    dev = R_anc.device
+    anchors = anchors.to(device=dev, dtype=torch.int64).contiguous()
+    c = _f32(c, device=dev).contiguous()
+    k_q, N = R_anc.shape
+    B, m = anchors.shape
+    e = torch.empty((B, k_q), dtype=torch.float32, device=dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            nbytes = lib.anncur_adaptive_solve_workspace_bytes(B, k_q, m, N)
+            ws = WORKSPACE.get("adaptive", nbytes, dev)
+            _lib.check(lib.anncur_adaptive_solve(_ptr(R_anc), _ld(R_anc), k_q, N, _ptr(Rt), _ptr(anchors), _ptr(c), B, m, float(rcond),
+                                                 _ptr(e), _ptr(ws), ws.numel(), _stream()))
+    return e
+
+
+def filter_excluded(cand_vals, cand_idx, excluded, n_out):
+    """First n_out candidates per row (order kept) whose index is not in the row's ``excluded`` list; padded with (-FLT_MAX, -1)."""
+    lib = _lib.load()
+    cand_vals = _f32(cand_vals).contiguous()
+    dev = cand_vals.device
+    cand_idx = cand_idx.to(device=dev, dtype=torch.int64).contiguous()
+    excluded = excluded.to(device=dev, dtype=torch.int64).contiguous()
+    n, k_in = cand_vals.shape
+    m = excluded.shape[1]
+    vals = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, n_out), dtype=torch.int64, device=dev)
+    if n > 0:
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_filter_excluded(_ptr(cand_vals), _ptr(cand_idx), n, k_in, _ptr(excluded), m, int(n_out), _ptr(vals),
+                                                  _ptr(idx), _stream()))
+    return vals, idx

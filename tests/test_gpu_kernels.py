@@ -265,7 +265,56 @@ def test_adaptive_round_matches_oracle_restatement(eng):
         assert np.allclose(val[q].cpu().numpy(), s[got], atol=10 * tau)
 
 
-def test_adaptive_multi_round_matches_oracle_restatement(eng):
+def test_adaptive_round_split_form_matches_oracle_restatement(eng):
+    """The same round through the split form the fused path uses: anncur_adaptive_solve (e_b), the fused tensor-core score +
+    top-(n_next + m) on the PACKED R_anc, anncur_filter_excluded.  Picks must equal the fp64 oracle's outside the tie band."""
+    rng = np.random.default_rng(1)
+    k_q, N, B, m, n_next = 48, 9000, 70, 24, 12
+    A = O.synthetic_scores(k_q + B, N, rank=12, noise=0.02, seed=4)
+    R, X = A[:k_q], A[k_q:]
+    anchors = np.stack([np.sort(rng.choice(N, m, replace=False)) for _ in range(B)])
+    c = np.take_along_axis(X, anchors, 1)
+    Rc = torch.from_numpy(R).cuda()
+    e = eng.adaptive_solve(Rc, torch.from_numpy(anchors).cuda(), torch.from_numpy(c).cuda(), Rt=eng.transpose(Rc))
+    e2 = eng.adaptive_solve(Rc, torch.from_numpy(anchors).cuda(), torch.from_numpy(c).cuda())       # Rt rebuilt in the workspace
+    assert torch.equal(e, e2)
+    cv, ci = eng.score_topk(e, eng.PackedItems(Rc, "f32r"), n_next + m)
+    val, nxt = eng.filter_excluded(cv, ci, torch.from_numpy(anchors).cuda(), n_next)
+    for q in range(B):
+        eq = c[q].astype(np.float64) @ np.linalg.pinv(R[:, anchors[q]].astype(np.float64))
+        assert np.allclose(e[q].cpu().numpy(), eq, atol=1e-4 * np.abs(eq).max())
+        sc = eq @ R.astype(np.float64)
+        sc[anchors[q]] = -np.inf
+        want = np.argsort(-sc, kind="stable")[:n_next]
+        tau = 1e-4 * np.abs(sc[np.isfinite(sc)]).max()
+        got = nxt[q].cpu().numpy()
+        assert all(sc[j] >= sc[want[-1]] - tau for j in got) and len(set(got.tolist())) == n_next
+        assert not set(got.tolist()) & set(anchors[q].tolist())
+        assert np.allclose(val[q].cpu().numpy(), sc[got], atol=10 * tau)
+
+
+def test_filter_excluded_keeps_order_and_pads(eng):
+    cv = torch.tensor([[9.0, 8.0, 7.0, 6.0, 5.0], [4.0, 3.0, 2.0, -3.4e38, -3.4e38]]).cuda()
+    ci = torch.tensor([[10, 11, 12, 13, 14], [5, 6, 7, -1, -1]]).cuda()
+    ex = torch.tensor([[11, 13, 99], [5, 6, 7]]).cuda()
+    v, i = eng.filter_excluded(cv, ci, ex, 3)
+    assert i.tolist() == [[10, 12, 14], [-1, -1, -1]] and v[0].tolist() == [9.0, 7.0, 5.0]
+    assert (v[1] == -np.finfo(np.float32).max).all()
+    v, i = eng.filter_excluded(cv, ci, ex[:, :0], 2)                      # nothing excluded
+    assert i.tolist() == [[10, 11], [5, 6]]
+    rng = np.random.default_rng(0)                                       # many rows, long lists: against a python loop
+    n, k_in, m, n_out = 300, 500, 375, 125
+    ci = torch.from_numpy(np.stack([rng.permutation(5000)[:k_in] for _ in range(n)])).cuda()
+    cv = torch.sort(torch.randn(n, k_in), dim=1, descending=True).values.cuda()
+    ex = torch.from_numpy(np.stack([rng.permutation(5000)[:m] for _ in range(n)])).cuda()
+    v, i = eng.filter_excluded(cv, ci, ex, n_out)
+    for r in range(0, n, 17):
+        keep = [j for j in ci[r].tolist() if j not in set(ex[r].tolist())][:n_out]
+        assert i[r].tolist()[:len(keep)] == keep and all(x == -1 for x in i[r].tolist()[len(keep):])
+
+
+@pytest.mark.parametrize("rescore", ["fused", "ffma"])
+def test_adaptive_multi_round_matches_oracle_restatement(eng, rescore):
     """The whole multi-round procedure (anncur_b200.adaptive_anncur: T - 1 K8 calls, exact-score gathers, K9 at the end)
     against oracle.cur_oracle.adaptive_anncur.  Picks of a round may differ from the oracle's only among near-ties of the
     approximate scores, so the comparison is on what the procedure is for: the final exact scores and the overlap of the
@@ -277,7 +326,7 @@ def test_adaptive_multi_round_matches_oracle_restatement(eng):
     R, X = A[:k_q], A[k_q:]
     first = np.sort(rng.choice(N, kpr, replace=False))
     want_anc, want_idx, want_val, _ = O.adaptive_anncur(R, X, first, T, kpr, top_k, rcond=1e-15)
-    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k)
+    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k, rescore=rescore)
     anc, idx, val = anc.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
     assert anc.shape == (B, T * kpr) and (anc[:, :kpr] == first[None, :]).all()
     assert all(len(set(r.tolist())) == T * kpr for r in anc)                 # anchors are never re-picked

@@ -52,6 +52,17 @@ def _worker(rank, world, port, ret):
                     n_fail = ix.certificate_failures()
                     ok &= int(n_fail > 0 or torch.equal(i, ri[r0:r1]))
                 ix.close()
+        # adaptive multi-round ANNCUR with the re-score item-sharded: one exchange per round, every rank ends with the same
+        # anchors as the single-GPU run ("the per-query solve is replicated; re-score is sharded")
+        from anncur_b200 import adaptive_anncur
+        from anncur_b200.adaptive import AdaptiveIndex
+        from oracle import cur_oracle as O
+        A = torch.from_numpy(O.synthetic_scores(60 + 40, 20000, rank=10, noise=0.05, seed=7)).cuda()
+        Ra, Xa = A[:60].contiguous(), A[60:].contiguous()
+        first = torch.arange(0, 20000, 20000 // 16)[:16]
+        a1, i1, v1 = adaptive_anncur(Ra, Xa, first, 4, 16, 10)
+        a2, i2, v2 = adaptive_anncur(Ra, Xa, first, 4, 16, 10, index=AdaptiveIndex(Ra, sharded=ShardedIndex.from_full(Ra)))
+        ok &= int(torch.equal(a1, a2) and torch.equal(i1, i2) and torch.equal(v1, v2))
         out = torch.tensor([ok], device="cuda")
         dist.all_reduce(out, op=dist.ReduceOp.MIN)
         if rank == 0:

@@ -19,6 +19,7 @@ ap.add_argument("--b", type=int, default=4096)
 ap.add_argument("--rounds", type=int, default=4)
 ap.add_argument("--per_round", type=int, default=125)
 ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--rescore", default="fused", choices=["fused", "ffma"])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
@@ -27,13 +28,15 @@ Y = torch.randn(a.n, r, device=dev)
 R = torch.randn(a.kq, r, device=dev) @ Y.t() / r ** 0.5 + 0.05 * torch.randn(a.kq, a.n, device=dev)
 X = torch.randn(a.b, r, device=dev) @ Y.t() / r ** 0.5 + 0.05 * torch.randn(a.b, a.n, device=dev)
 first = torch.randperm(a.n, device=dev)[:a.per_round].sort().values
-adaptive_anncur(R, X[:256], first, a.rounds, a.per_round, a.k)
+from anncur_b200.adaptive import AdaptiveIndex
+index = AdaptiveIndex(R) if a.rescore == "fused" else None
+adaptive_anncur(R, X[:256], first, a.rounds, a.per_round, a.k, rescore=a.rescore, index=index)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-anc, idx, val = adaptive_anncur(R, X, first, a.rounds, a.per_round, a.k)
+anc, idx, val = adaptive_anncur(R, X, first, a.rounds, a.per_round, a.k, rescore=a.rescore, index=index)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 exact = torch.topk(X, a.k, dim=1).indices
 recall = (idx.unsqueeze(2) == exact.unsqueeze(1)).any(2).float().mean().item()
-print(f"adaptive ANNCUR: {a.b} queries x {a.rounds} rounds x {a.per_round} anchors over {a.n} items: {dt * 1e3:.1f} ms "
+print(f"adaptive ANNCUR ({a.rescore} re-score): {a.b} queries x {a.rounds} rounds x {a.per_round} anchors over {a.n} items: {dt * 1e3:.1f} ms "
       f"({a.b / dt:.0f} q/s), recall@{a.k} vs exact = {recall:.3f}")
