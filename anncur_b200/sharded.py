@@ -64,6 +64,10 @@ def unpack_candidates(buf, k):
     return vals.contiguous(), idx.contiguous()
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """CUDA IPC / peer access is not available between some pair of ranks (raised on EVERY rank of the group)."""
+
+
 class PeerChannel:
     """One exchange channel of the peer-memory path: this rank's receive buffer (library-allocated, plain
     cudaMalloc) mapped into every peer with CUDA IPC, and the peers' buffers mapped here.  Collective to
@@ -92,6 +96,7 @@ class PeerChannel:
         dist.all_gather_object(handles, bytes(handle), group=group)
         self._mapped = []
         ptrs = (C.c_void_p * self.world)()
+        failure = None
         with torch.cuda.device(device):
             for p, h in enumerate(handles):
                 if p == self.rank:
@@ -99,9 +104,22 @@ class PeerChannel:
                     continue
                 m = C.c_void_p(0)
                 hb = (C.c_ubyte * 64).from_buffer_copy(h)
-                self._check(lib.anncur_peer_open(hb, C.byref(m)))
+                rc = lib.anncur_peer_open(hb, C.byref(m))
+                if rc != 0:
+                    failure = f"rank {self.rank}: cannot map rank {p}'s buffer: {lib.anncur_last_error().decode('utf-8', 'replace')}"
+                    break
                 self._mapped.append(m.value)
                 ptrs[p] = m.value
+        # every rank learns whether EVERY mapping worked (no peer access between some pair of GPUs -> nobody uses the channel)
+        failures = [None] * self.world
+        dist.all_gather_object(failures, failure, group=group)
+        if any(failures):
+            with torch.cuda.device(device):
+                for mm in self._mapped:
+                    lib.anncur_peer_close(C.c_void_p(mm))
+                lib.anncur_peer_free(C.c_void_p(self.base))
+            self._mapped, self.base = [], None
+            raise PeerMemoryUnavailable("; ".join(f for f in failures if f))
         self.ptrs = ptrs
         lo, hi = shard_bounds(self.n_rows, self.world)[self.rank]
         self.row_lo, self.rows_owned = lo, hi - lo
@@ -227,7 +245,13 @@ class ShardedIndex:
         key = (int(n_rows), int(k), torch.cuda.current_stream(device).cuda_stream)
         ch = self._channels.get(key)
         if ch is None:
-            ch = self._channels[key] = PeerChannel(n_rows, k, device, group=self.group)
+            try:
+                ch = self._channels[key] = PeerChannel(n_rows, k, device, group=self.group)
+            except PeerMemoryUnavailable as exc:          # the same on every rank: switch the whole group to the NCCL exchange
+                import sys
+                print(f"[anncur_b200.sharded] peer-memory exchange unavailable ({exc}); using NCCL all_to_all_single", file=sys.stderr, flush=True)
+                self.exchange = "nccl"
+                return None
         return ch
 
     def prepare(self, n_rows, k, device=None):
@@ -250,7 +274,11 @@ class ShardedIndex:
         if self.world_size == 1:
             return vals, idx
         if self.exchange == "p2p":
-            return self._channel(B, k_loc, vals.device).exchange(vals, idx, k_out=k)
+            ch = self._channel(B, k_loc, vals.device)
+            if ch is not None:
+                return ch.exchange(vals, idx, k_out=k)
+            if k_loc != k:                                # the NCCL form ships full lists: redo the local search with k
+                vals, idx = self.local_topk(Q, k)
         bounds = shard_bounds(B, self.world_size)
         rows = [hi - lo for lo, hi in bounds]
         mine = rows[self.rank]

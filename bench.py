@@ -581,6 +581,8 @@ def main():
     # a box drift apart by several % per step under their power caps, and an in-order loop pays the slowest rank every step.
     dev_streams = DEV_STREAMS if index is not None else 1
     ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, streams=dev_streams, sample_clocks=True, local_rank=local_rank)
+    if index is not None and args.exchange == "p2p" and index.exchange != "p2p":
+        args.exchange, h.local_k = "nccl", None           # peer memory was not available on this box: the line says what ran
     cert = None
     if h.local_k is not None:
         # rank-budgeted exchange: every merged row was certified on the device inside the timed region; rows that failed are
@@ -794,6 +796,12 @@ def main():
                                                                   "ms_per_step": ms2 / args.steps}
         if cert is not None and h.local_k is not None:
             cert["certificate_failures_other_stream_counts"] = index.certificate_failures(reset=True)
+            # the same loop with every shard shipping all k candidates (no budget, no certificate needed)
+            lk, h.local_k = h.local_k, None
+            ms3, _, _, _, _ = h.time_device(args.steps, 4, streams=dev_streams)
+            h.local_k = lk
+            line["value_with_local_k_equal_k"] = {"value": h.units_per_step() * args.steps / (ms3 * 1e-3), "unit": "queries/s",
+                                                  "ms_per_step": ms3 / args.steps}
     if world == 1 and not args.no_extra:
         line["other_precision"] = []
         v_a, i_a = engine.score_topk(batches[0], packed, k)
