@@ -60,6 +60,12 @@ PROTOTYPES = {
     "anncur_adaptive_solve": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _sz, _vp]),
     "anncur_transpose_f32": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),
     "anncur_filter_excluded": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "anncur_adaptive_shared_bytes": (_sz, [_i, _i64, _i]),
+    "anncur_adaptive_prepare_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "anncur_adaptive_prepare": (_i, [_vp, _i, _i64, _vp, _i, _d, _vp, _sz, _vp, _sz, _vp]),
+    "anncur_adaptive_state_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "anncur_adaptive_begin": (_i, [_vp, _i, _i64, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "anncur_adaptive_extend": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
     "anncur_profile_enable": (_i, [_i]),
     "anncur_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "anncur_kernel_launch_count": (C.c_uint64, []),

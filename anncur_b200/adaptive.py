@@ -25,6 +25,15 @@ class AdaptiveIndex:
         self.Rt = engine.transpose(self.R)
         self.sharded = sharded
         self.packed = None if sharded is not None else engine.PackedItems(self.R, precision)
+        self._shared = {}
+
+    def shared_for(self, first_anchors, rcond):
+        """The once-per-(index, first anchors) part of the incremental solver (anncur_adaptive_prepare), cached."""
+        key = (tuple(first_anchors.tolist()), float(rcond))
+        if key not in self._shared:
+            self._shared.clear()
+            self._shared[key] = engine.AdaptiveShared(self.Rt, first_anchors, rcond)
+        return self._shared[key]
 
     def topk(self, e, k):
         if self.sharded is not None:
@@ -33,13 +42,17 @@ class AdaptiveIndex:
 
 
 def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top_k, rcond=1e-15, *, rescore="fused",
-                    index=None, precision="f32r"):
+                    index=None, precision="f32r", solver="incremental"):
     """Returns (anchors [B x T*k_per_round] int64 in selection order, idx [B x top_k] int64, exact scores [B x top_k]).
 
     ``rescore="fused"`` (default): per round one ``anncur_adaptive_solve`` (e_b for the whole batch), the fused tensor-core
     score + top-(k_per_round + m) on the packed R_anc -- no B x N block -- and ``anncur_filter_excluded`` to drop the anchors.
     ``rescore="ffma"``: the round-1 path (one ``anncur_adaptive_round`` call: FFMA re-score of a B x N block + masked row top-k),
-    also taken when k_per_round + m exceeds the fused kernel's largest k.  ``index`` = an ``AdaptiveIndex`` to reuse."""
+    also taken when k_per_round + m exceeds the fused kernel's largest k.  ``index`` = an ``AdaptiveIndex`` to reuse.
+    ``solver="incremental"`` (default, with the fused re-score): the per-query Cholesky factor is carried across rounds
+    (``anncur_adaptive_begin`` / ``anncur_adaptive_extend``: a round pays for its NEW anchors only); ``solver="full"``: every
+    round re-solves from scratch (``anncur_adaptive_solve``), also taken when a round adds more than
+    ANNCUR_ADAPTIVE_MAX_BLOCK anchors."""
     R = engine._f32(R_anc)
     X = engine._f32(exact_rows, device=R.device)
     B = X.shape[0]
@@ -49,14 +62,22 @@ def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top
     fused = rescore == "fused" and n_rounds * k_per_round <= engine.MAX_K_FUSED and R.shape[1] >= 4 * n_rounds * k_per_round
     if fused and index is None and n_rounds > 1:
         index = AdaptiveIndex(R, precision)
+    incremental = (fused and solver == "incremental" and n_rounds > 1 and k_per_round <= engine.ADAPTIVE_MAX_BLOCK
+                   and (n_rounds - 1) * k_per_round <= R.shape[0])
+    state, nxt = None, None
+    if incremental:
+        state = engine.AdaptiveState(index.shared_for(first, rcond), B, k_per_round, (n_rounds - 1) * k_per_round)
     for t in range(n_rounds - 1):
-        c = torch.gather(X, 1, anchors)                                          # exact scores of the anchors so far
         m = anchors.shape[1]
         if fused:
-            e = engine.adaptive_solve(R, anchors, c, rcond, Rt=index.Rt)         # K8a: per-query re-solve
+            if incremental:                                                      # K8 incremental: only the new anchors are paid for
+                e = state.begin(torch.gather(X, 1, anchors)) if t == 0 else state.extend(nxt, torch.gather(X, 1, nxt))
+            else:                                                                # K8a: per-query re-solve from scratch
+                e = engine.adaptive_solve(R, anchors, torch.gather(X, 1, anchors), rcond, Rt=index.Rt)
             cv, ci = index.topk(e, k_per_round + m)                              # K3+K4 on the packed R_anc: the re-score
             _, nxt = engine.filter_excluded(cv, ci, anchors, k_per_round)        # the anchors leave the candidate lists
         else:
+            c = torch.gather(X, 1, anchors)                                      # exact scores of the anchors so far
             nxt, _ = engine.adaptive_round(R, anchors, c, k_per_round, rcond)    # K8: re-solve + masked re-score + pick
         anchors = torch.cat([anchors, nxt], dim=1)
     ex = torch.gather(X, 1, anchors)

@@ -169,6 +169,7 @@ cholesky_solve_kernel(double* __restrict__ G, const float* __restrict__ c, const
                 const double ptj = P[t * CH_LD + jj];
                 for (int r = t + ty; r < nb; r += 8) P[r * CH_LD + t] -= P[r * CH_LD + jj] * ptj;
             }
+            __syncthreads();                                        // the next pivot was written by this update
         }
         __syncthreads();
         // 2b. the rows below it (incl. the right-hand side row): X L_d^T = P by forward substitution, one thread per row

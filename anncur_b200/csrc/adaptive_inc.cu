@@ -1,0 +1,590 @@
+// K8 (incremental form): adaptive multi-round ANNCUR with the per-query factorisation CARRIED ACROSS ROUNDS.
+// NOT in the reference (spec = SURVEY.md section 8a row A8, parity unpinned -- checked against
+// oracle.cur_oracle.adaptive_anncur).
+//
+// Round t solves e_b = c_b . pinv(M_b), M_b = R_anc[:, I_b] (k_q x m), through the normal equations G_b = M_b^T M_b = L L^T
+// in fp64.  adaptive.cu rebuilds G_b and L from scratch every round (m = 125, 250, 375: 218 MFLOP of Gram + 23 MFLOP of
+// Cholesky per query at BASELINE configs[2]).  Here the anchor set only GROWS, I_{t+1} = I_t U new_t, and round 1 is shared
+// by all queries, so with L_t = [[L_{t-1}, 0], [X, L_D]]:
+//     X   = B^T L_{t-1}^-T        B = M_{t-1}^T N   (N = the n new columns)
+//     L_D = chol(N^T N - X X^T)   z_t = [z_{t-1}, L_D^-1 (c_new - X z_{t-1})]        (forward substitution is incremental)
+//     y   = L_t^-T z_t            e = (M y)^T
+//  * the columns of X that belong to the SHARED first anchors are a gather: X_a = W_1[:, new], W_1 = L_1^-1 M_1^T R_anc
+//    (m_1 x N, built once per index by anncur_adaptive_prepare);
+//  * the inverse of every n x n diagonal block is kept, so every other step is a batched fp64 GEMM C -= A B^T on the
+//    fp64 tensor cores (DMMA 8x8x4) -- one generic kernel, operands either fp64 panels or fp32 rows of R_anc^T gathered by
+//    item index -- plus ONE small per-query kernel (Cholesky + triangular inverse of the n x n Schur complement, n <= 128);
+//  * per query and round: 45 MFLOP in total instead of 241.
+// Pivots at or below rcond^2 * (largest Gram diagonal) are dropped exactly as in adaptive.cu (that anchor's coordinate of y
+// is 0): zero pivot, zero column of L, zero row and column of the block inverse.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace anncur {
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Generic batched C_out = C_in + sign * A B^T on the fp64 tensor cores.  64 x 64 tile per CTA (8 warps, each 32 x 16 = 4 x 2
+// DMMA tiles), 32-wide k stages: the next stage's global loads are issued before the current stage's MMAs (registers), so the
+// L2 latency hides behind 64 DMMAs per warp.  Row stride 36 doubles: conflict-free fragment loads per half warp.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int DG_T = 64, DG_K = 32, DG_LD = DG_K + 4;
+constexpr int DG_ALL = 1 << 29;                           // diag_off: "no triangular skipping"
+
+struct DgArgs {
+    // GATHER mode: row i of A = fp32 row idxA[i] of Rt (row length K, row stride ld_rt); idx == nullptr: row i itself
+    const float* Rt; int64_t ld_rt;
+    const int64_t* idxA; int64_t bs_idxA;
+    const int64_t* idxB; int64_t bs_idxB;
+    // fp64 mode
+    const double* A; int64_t lda, bsA;
+    const double* B; int64_t ldb, bsB;
+    const double* Cin; int64_t ldcin, bsCin;               // nullptr: zero
+    double* Cout; int64_t ldc, bsC;
+    int M, N, K;
+    double sign;
+    int diag_off;                                          // entries with j > i + diag_off are neither computed nor stored
+    int vec4;                                              // GATHER: rows are 16-byte aligned and K % 4 == 0
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(256, 2)
+dgemm_nt_kernel(const DgArgs p) {
+    __shared__ __align__(16) double As[DG_T][DG_LD], Bs[DG_T][DG_LD];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * DG_T, j0 = blockIdx.x * DG_T;
+    if (int64_t(j0) > int64_t(i0) + DG_T - 1 + p.diag_off) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int lrow = tid >> 2, lq = tid & 3;               // loader: one tile row of A and of B per thread, k = lq + 4u / 4lq + ..
+    const bool va = i0 + lrow < p.M, vb = j0 + lrow < p.N;
+
+    const float* fa = nullptr; const float* fb = nullptr;
+    const double* da = nullptr; const double* db = nullptr;
+    if (GATHER) {
+        const int64_t ia = va ? (p.idxA ? p.idxA[int64_t(b) * p.bs_idxA + i0 + lrow] : int64_t(i0 + lrow)) : 0;
+        const int64_t ib = vb ? (p.idxB ? p.idxB[int64_t(b) * p.bs_idxB + j0 + lrow] : int64_t(j0 + lrow)) : 0;
+        fa = p.Rt + ia * p.ld_rt; fb = p.Rt + ib * p.ld_rt;
+    } else {
+        da = p.A + int64_t(b) * p.bsA + int64_t(va ? i0 + lrow : 0) * p.lda;
+        db = p.B + int64_t(b) * p.bsB + int64_t(vb ? j0 + lrow : 0) * p.ldb;
+    }
+    float4 ga[2], gb[2];                                   // GATHER stage registers: k = 4 lq + {0, 16} .. +3
+    double ra[8], rb[8];                                   // fp64 stage registers:   k = lq + 4 u
+    auto load_stage = [&](int k0) {
+        if (GATHER) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + 4 * lq + 16 * h;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+                if (p.vec4) {
+                    if (va && k < p.K) x = __ldg(reinterpret_cast<const float4*>(fa + k));
+                    if (vb && k < p.K) y = __ldg(reinterpret_cast<const float4*>(fb + k));
+                } else {
+                    if (va) { if (k < p.K) x.x = __ldg(fa + k); if (k + 1 < p.K) x.y = __ldg(fa + k + 1);
+                              if (k + 2 < p.K) x.z = __ldg(fa + k + 2); if (k + 3 < p.K) x.w = __ldg(fa + k + 3); }
+                    if (vb) { if (k < p.K) y.x = __ldg(fb + k); if (k + 1 < p.K) y.y = __ldg(fb + k + 1);
+                              if (k + 2 < p.K) y.z = __ldg(fb + k + 2); if (k + 3 < p.K) y.w = __ldg(fb + k + 3); }
+                }
+                ga[h] = x; gb[h] = y;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + lq + 4 * u;
+                ra[u] = (va && k < p.K) ? da[k] : 0.0;
+                rb[u] = (vb && k < p.K) ? db[k] : 0.0;
+            }
+        }
+    };
+    auto store_stage = [&]() {
+        if (GATHER) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double* pa = &As[lrow][4 * lq + 16 * h];
+                double* pb = &Bs[lrow][4 * lq + 16 * h];
+                pa[0] = double(ga[h].x); pa[1] = double(ga[h].y); pa[2] = double(ga[h].z); pa[3] = double(ga[h].w);
+                pb[0] = double(gb[h].x); pb[1] = double(gb[h].y); pb[2] = double(gb[h].z); pb[3] = double(gb[h].w);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { As[lrow][lq + 4 * u] = ra[u]; Bs[lrow][lq + 4 * u] = rb[u]; }
+        }
+    };
+
+    double acc[4][2][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
+
+    if (p.K > 0) load_stage(0);
+    for (int k0 = 0; k0 < p.K; k0 += DG_K) {
+        store_stage();
+        __syncthreads();
+        if (k0 + DG_K < p.K) load_stage(k0 + DG_K);
+#pragma unroll
+        for (int k4 = 0; k4 < DG_K; k4 += 4) {
+            double a[4], bb[2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = As[wr + r * 8 + fr][k4 + fc];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) bb[c] = Bs[wc + c * 8 + fr][k4 + fc];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[r][c][0]), "+d"(acc[r][c][1]) : "d"(a[r]), "d"(bb[c]));
+        }
+        __syncthreads();
+    }
+    const double* Cin = p.Cin ? p.Cin + int64_t(b) * p.bsCin : nullptr;
+    double* Cout = p.Cout + int64_t(b) * p.bsC;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + wr + r * 8 + fr, j = j0 + wc + c * 8 + fc * 2 + h;
+                if (i < p.M && j < p.N && int64_t(j) <= int64_t(i) + p.diag_off) {
+                    const double old = Cin ? Cin[int64_t(i) * p.ldcin + j] : 0.0;
+                    Cout[int64_t(i) * p.ldc + j] = old + p.sign * acc[r][c][h];
+                }
+            }
+}
+
+static int dgemm_launch(const DgArgs& a, bool gather, int batch, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || batch <= 0) return ANNCUR_OK;
+    dim3 grid(unsigned((a.N + DG_T - 1) / DG_T), unsigned((a.M + DG_T - 1) / DG_T), unsigned(batch));
+    if (gather) dgemm_nt_kernel<true><<<grid, 256, 0, stream>>>(a);
+    else dgemm_nt_kernel<false><<<grid, 256, 0, stream>>>(a);
+    ANNCUR_LAUNCH_OK("dgemm_nt_kernel");
+    return ANNCUR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Per query: in-place Cholesky of the n x n Schur complement S (lower triangle, n <= 128), the inverse of its factor, and the
+// new block of z.  Both triangles live PACKED in shared memory (index i (i + 1) / 2 + j: the accesses of both loops below
+// are conflict-free), 2 * n (n + 1) / 2 doubles = 126 KB at n = 125.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+__global__ void __launch_bounds__(256)
+chol_inv_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds,                   // in: S (lower), out: L_D (lower)
+                const double* __restrict__ rawdiag, int64_t bs_rd, int64_t ld_rd,       // raw Gram block of the new anchors (its diagonal = |column|^2)
+                double* __restrict__ maxd,                                              // [batch] running max of the Gram diagonal (in / out)
+                double* __restrict__ Linv, int64_t bsLinv,                              // out: L_D^-1, n x n row-major, upper triangle zeroed
+                int n, double rcond,
+                const double* __restrict__ X, int64_t bsX, int64_t ldx, int m_p,        // optional: the new rows of L, columns [0, m_p)
+                double* __restrict__ z, int64_t bsz,                                    //           z[0, m_p) in, z[m_p, m_p + n) out
+                const float* __restrict__ c_new, int64_t bsc) {
+    extern __shared__ __align__(16) double ci_smem[];
+    const int ntri = n * (n + 1) / 2;
+    double* Ls = ci_smem;                    // [ntri]
+    double* Li = Ls + ntri;                  // [ntri]
+    double* pivs = Li + ntri;                // [n]
+    double* invp = pivs + n;                 // [n]
+    double* tv = invp + n;                   // [n]
+    double* zs = tv + n;                     // [m_p] previous z
+    __shared__ double red[8];
+    __shared__ double s_maxd;
+    const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    double* S = Sbase + int64_t(b) * bsS;
+    for (int i = ty; i < n; i += 8)
+        for (int j = tx; j <= i; j += 32) Ls[tri(i, j)] = S[int64_t(i) * lds + j];
+    double md = 0.0;
+    if (rawdiag)
+        for (int i = tid; i < n; i += 256) md = fmax(md, rawdiag[int64_t(b) * bs_rd + int64_t(i) * ld_rd + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if (tx == 0) red[ty] = md;
+    if (z) for (int i = tid; i < m_p; i += 256) zs[i] = z[int64_t(b) * bsz + i];
+    __syncthreads();
+    if (tid == 0) {
+        double v = maxd[b];
+        for (int w = 0; w < 8; ++w) v = fmax(v, red[w]);
+        s_maxd = v; maxd[b] = v;
+    }
+    __syncthreads();
+    const double drop = fmax(rcond * rcond, 1e-28) * s_maxd;
+
+    // Cholesky, column by column; the diagonal keeps its raw value until the end (pivs holds the pivots)
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();                                              // trailing update of column j - 1 is complete
+        const double d = Ls[tri(j, j)];
+        const double piv = d > drop ? sqrt(d) : 0.0;
+        const double inv = piv > 0.0 ? 1.0 / piv : 0.0;              // dropped pivot: the column becomes 0
+        for (int i = j + 1 + tid; i < n; i += 256) Ls[tri(i, j)] *= inv;
+        if (tid == 0) { pivs[j] = piv; invp[j] = inv; }
+        __syncthreads();
+        for (int t = j + 1 + tx; t < n; t += 32) {
+            const double ptj = Ls[tri(t, j)];
+            for (int r = t + ty; r < n; r += 8) Ls[tri(r, t)] -= Ls[tri(r, j)] * ptj;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += 256) Ls[tri(j, j)] = pivs[j];
+    __syncthreads();
+    // inverse of the factor, one thread per column: x_j = 1 / L_jj, x_i = -(sum_{k = j}^{i-1} L_ik x_k) / L_ii
+    if (tid < n) {
+        const int j = tid;
+        Li[tri(j, j)] = invp[j];
+        for (int i = j + 1; i < n; ++i) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = j;
+            for (; k + 3 < i; k += 4) {
+                a0 = fma(Ls[tri(i, k)], Li[tri(k, j)], a0);
+                a1 = fma(Ls[tri(i, k + 1)], Li[tri(k + 1, j)], a1);
+                a2 = fma(Ls[tri(i, k + 2)], Li[tri(k + 2, j)], a2);
+                a3 = fma(Ls[tri(i, k + 3)], Li[tri(k + 3, j)], a3);
+            }
+            for (; k < i; ++k) a0 = fma(Ls[tri(i, k)], Li[tri(k, j)], a0);
+            Li[tri(i, j)] = -((a0 + a1) + (a2 + a3)) * invp[i];
+        }
+    }
+    __syncthreads();
+    // results to global memory
+    double* Lo = Linv + int64_t(b) * bsLinv;
+    for (int i = ty; i < n; i += 8) {
+        for (int j = tx; j < n; j += 32) {
+            if (j <= i) S[int64_t(i) * lds + j] = Ls[tri(i, j)];
+            Lo[int64_t(i) * n + j] = j <= i ? Li[tri(i, j)] : 0.0;
+        }
+    }
+    if (z == nullptr) return;
+    // t = c_new - X z_prev (one warp per row), then z_new = L_D^-1 t
+    const double* Xb = X + int64_t(b) * bsX;
+    for (int i = ty; i < n; i += 8) {
+        double part = 0.0;
+        for (int k = tx; k < m_p; k += 32) part = fma(Xb[int64_t(i) * ldx + k], zs[k], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (tx == 0) tv[i] = double(c_new[int64_t(b) * bsc + i]) - part;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        double a = 0.0;
+        for (int j = 0; j <= i; ++j) a = fma(Li[tri(i, j)], tv[j], a);
+        z[int64_t(b) * bsz + m_p + i] = a;
+    }
+}
+
+// z_0 = L_1^-1 c_1 for every query (the shared first block), and the running Gram-diagonal maximum starts at the shared one.
+__global__ void __launch_bounds__(128)
+z_shared_kernel(const double* __restrict__ L1inv, int s, const double* __restrict__ maxd_shared, const float* __restrict__ c,
+                double* __restrict__ z, int64_t bsz, double* __restrict__ maxd) {
+    extern __shared__ double zc[];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < s; i += blockDim.x) zc[i] = double(c[int64_t(b) * s + i]);
+    if (threadIdx.x == 0) maxd[b] = s > 0 ? *maxd_shared : 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < s; i += blockDim.x) {
+        double a = 0.0;
+        for (int j = 0; j <= i; ++j) a = fma(L1inv[int64_t(i) * s + j], zc[j], a);
+        z[int64_t(b) * bsz + i] = a;
+    }
+}
+
+// The new anchors join the query's list, and the columns of their rows of L that belong to the shared anchors are gathered
+// from W_1^T (one warp per new anchor).
+__global__ void __launch_bounds__(256)
+append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_queries, int r_done,
+                      int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ W1t, int s,
+                      double* __restrict__ Lq, int64_t bsLq, int ldl) {
+    const int64_t w = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    if (w >= int64_t(n_queries) * n) return;
+    const int b = int(w / n), i = int(w % n);
+    const int64_t item = new_anchors[w];
+    if (lane_id() == 0) anc_q[int64_t(b) * bs_anc + int64_t(r_done) * n + i] = item;
+    const double* src = W1t + item * s;
+    double* dst = Lq + int64_t(b) * bsLq + (int64_t(r_done) * n + i) * ldl;
+    for (int t = lane_id(); t < s; t += 32) dst[t] = src[t];
+}
+
+// y = L^-T z by blocks (the block inverses make every step a transposed matrix-vector product), then e = (M y)^T.
+__global__ void __launch_bounds__(256)
+backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restrict__ shared_anc, const double* __restrict__ L1inv, int s,
+                   const int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ Lq, int64_t bsLq, int ldl,
+                   const double* __restrict__ Linvq, int64_t bsLinv, const double* __restrict__ z, int64_t bsz, int n, int nblocks,
+                   float* __restrict__ e_out) {
+    extern __shared__ __align__(16) double bs_smem[];
+    const int m = s + nblocks * n;
+    double* ys = bs_smem;                                   // [m] right-hand side, becomes y block by block
+    int64_t* items = reinterpret_cast<int64_t*>(ys + m);    // [m]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < m; i += 256) {
+        ys[i] = z[int64_t(b) * bsz + i];
+        items[i] = i < s ? shared_anc[i] : anc_q[int64_t(b) * bs_anc + (i - s)];
+    }
+    __syncthreads();
+    const double* L = Lq + int64_t(b) * bsLq;
+    for (int q = nblocks; q >= 0; --q) {
+        // q = nblocks .. 1: per-query block q - 1; q = 0: the shared block
+        const int c0 = q > 0 ? s + (q - 1) * n : 0;
+        const int nb = q > 0 ? n : s;
+        if (nb == 0) continue;
+        const double* Iv = q > 0 ? Linvq + int64_t(b) * bsLinv + int64_t(q - 1) * n * n : L1inv;
+        double yj = 0.0;
+        if (tid < nb) {                                     // y_j = sum_{i >= j} Linv[i][j] rhs[i]
+            double a0 = 0.0, a1 = 0.0;
+            int i = tid;
+            for (; i + 1 < nb; i += 2) {
+                a0 = fma(Iv[int64_t(i) * nb + tid], ys[c0 + i], a0);
+                a1 = fma(Iv[int64_t(i + 1) * nb + tid], ys[c0 + i + 1], a1);
+            }
+            if (i < nb) a0 = fma(Iv[int64_t(i) * nb + tid], ys[c0 + i], a0);
+            yj = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < nb) ys[c0 + tid] = yj;
+        __syncthreads();
+        if (q > 0) {                                        // rhs[col] -= sum_i L[row i of the block][col] y_i, col < c0
+            const double* Lr = L + int64_t(q - 1) * n * ldl;
+            for (int col = tid; col < c0; col += 256) {
+                double a0 = 0.0, a1 = 0.0;
+                int i = 0;
+                for (; i + 1 < n; i += 2) {
+                    a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
+                    a1 = fma(Lr[int64_t(i + 1) * ldl + col], ys[c0 + i + 1], a1);
+                }
+                if (i < n) a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
+                ys[col] -= a0 + a1;
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < k_q; t += 256) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = 0;
+        for (; i + 3 < m; i += 4) {
+            const float v0 = __ldg(Rt + items[i] * k_q + t), v1 = __ldg(Rt + items[i + 1] * k_q + t);
+            const float v2 = __ldg(Rt + items[i + 2] * k_q + t), v3 = __ldg(Rt + items[i + 3] * k_q + t);
+            a0 = fma(ys[i], double(v0), a0); a1 = fma(ys[i + 1], double(v1), a1);
+            a2 = fma(ys[i + 2], double(v2), a2); a3 = fma(ys[i + 3], double(v3), a3);
+        }
+        for (; i < m; ++i) a0 = fma(ys[i], double(__ldg(Rt + items[i] * k_q + t)), a0);
+        e_out[int64_t(b) * k_q + t] = float((a0 + a1) + (a2 + a3));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// layouts
+// ---------------------------------------------------------------------------------------------------------------------------
+struct IncShared { size_t off_anc, off_maxd, off_l1, off_l1inv, off_w1t, total; };
+static IncShared inc_shared_layout(int64_t n_items, int s) {
+    IncShared p{};
+    size_t off = 0;
+    p.off_anc = off; off += align_up(sizeof(int64_t) * size_t(s > 0 ? s : 1), 256);
+    p.off_maxd = off; off += 256;
+    p.off_l1 = off; off += align_up(sizeof(double) * size_t(s) * s, 256);
+    p.off_l1inv = off; off += align_up(sizeof(double) * size_t(s) * s, 256);
+    p.off_w1t = off; off += align_up(sizeof(double) * size_t(n_items) * s, 256);
+    p.total = off > 0 ? off : 256;
+    return p;
+}
+
+struct IncState { int mq, ldl; size_t off_anc, off_maxd, off_z, off_lq, off_linv, off_t, total; int64_t bs_anc, bsz, bsLq, bsLinv, bsT; };
+static IncState inc_state_layout(int n_queries, int s, int n, int m_max) {
+    IncState p{};
+    p.mq = m_max - s;
+    p.ldl = (m_max + 1) & ~1;
+    const size_t B = size_t(n_queries > 0 ? n_queries : 1);
+    size_t off = 0;
+    p.bs_anc = p.mq; p.bsz = p.ldl; p.bsLq = int64_t(p.mq) * p.ldl; p.bsLinv = int64_t(p.mq) * n; p.bsT = int64_t(n) * p.ldl;
+    p.off_anc = off; off += align_up(sizeof(int64_t) * B * size_t(p.mq > 0 ? p.mq : 1), 256);
+    p.off_maxd = off; off += align_up(sizeof(double) * B, 256);
+    p.off_z = off; off += align_up(sizeof(double) * B * p.ldl, 256);
+    p.off_lq = off; off += align_up(sizeof(double) * B * size_t(p.bsLq > 0 ? p.bsLq : 1), 256);
+    p.off_linv = off; off += align_up(sizeof(double) * B * size_t(p.bsLinv > 0 ? p.bsLinv : 1), 256);
+    p.off_t = off; off += align_up(sizeof(double) * B * size_t(p.bsT), 256);
+    p.total = off;
+    return p;
+}
+
+static size_t chol_inv_smem(int n, int m_p) { return sizeof(double) * (size_t(n) * (n + 1) + 3 * size_t(n) + size_t(m_p > 0 ? m_p : 0)); }
+
+size_t adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared) {
+    (void)k_q;
+    if (m_shared < 0 || n_items <= 0) return 256;
+    return inc_shared_layout(n_items, m_shared).total;
+}
+size_t adaptive_prepare_workspace_bytes(int k_q, int64_t n_items, int m_shared) {
+    (void)k_q;
+    if (m_shared <= 0 || n_items <= 0) return 256;
+    return align_up(sizeof(double) * size_t(n_items) * m_shared, 256);
+}
+size_t adaptive_state_bytes(int n_queries, int k_q, int m_shared, int n_new, int m_max) {
+    (void)k_q;
+    if (n_new <= 0 || m_max < m_shared || m_shared < 0) return 256;
+    return inc_state_layout(n_queries, m_shared, n_new, m_max).total;
+}
+
+static int check_inc_shape(const char* who, int k_q, int s, int n, int m_max) {
+    if (s < 0 || s > ANNCUR_ADAPTIVE_MAX_BLOCK || n < 1 || n > ANNCUR_ADAPTIVE_MAX_BLOCK) {
+        set_error("%s: m_shared = %d / n_new = %d outside [0 | 1, %d]", who, s, n, ANNCUR_ADAPTIVE_MAX_BLOCK);
+        return ANNCUR_E_UNSUPPORTED;
+    }
+    if (m_max < s || (m_max - s) % n != 0) { set_error("%s: m_max = %d is not m_shared + a multiple of n_new", who, m_max); return ANNCUR_E_INVALID; }
+    if (m_max > k_q) { set_error("%s: m_max = %d anchors > k_q = %d anchor queries is not supported", who, m_max, k_q); return ANNCUR_E_UNSUPPORTED; }
+    if (m_max > 2048) { set_error("%s: m_max = %d > 2048", who, m_max); return ANNCUR_E_UNSUPPORTED; }
+    return ANNCUR_OK;
+}
+
+// Once per (index, first anchors): L_1, L_1^-1 and W_1^T = (L_1^-1 M_1^T R_anc)^T (n_items x m_shared fp64).
+int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* shared_anchors, int s, double rcond,
+                     void* shared, size_t shared_bytes, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    int rc = check_inc_shape("adaptive_prepare", k_q, s, 1, s);
+    if (rc != ANNCUR_OK) return rc;
+    const IncShared sl = inc_shared_layout(n_items, s);
+    if (shared_bytes < sl.total) { set_error("adaptive_prepare: shared blob too small: %zu < %zu", shared_bytes, sl.total); return ANNCUR_E_WORKSPACE; }
+    if (s == 0) return ANNCUR_OK;
+    if (workspace_bytes < adaptive_prepare_workspace_bytes(k_q, n_items, s)) { set_error("adaptive_prepare: workspace too small"); return ANNCUR_E_WORKSPACE; }
+    char* sb = reinterpret_cast<char*>(shared);
+    int64_t* anc = reinterpret_cast<int64_t*>(sb + sl.off_anc);
+    double* maxd = reinterpret_cast<double*>(sb + sl.off_maxd);
+    double* L1 = reinterpret_cast<double*>(sb + sl.off_l1);
+    double* L1inv = reinterpret_cast<double*>(sb + sl.off_l1inv);
+    double* W1t = reinterpret_cast<double*>(sb + sl.off_w1t);
+    double* V = reinterpret_cast<double*>(workspace);
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(anc, shared_anchors, sizeof(int64_t) * s, cudaMemcpyDeviceToDevice, stream));
+    ANNCUR_CUDA_OK(cudaMemsetAsync(maxd, 0, sizeof(double), stream));
+    const int vec4 = (k_q % 4 == 0) && (reinterpret_cast<uintptr_t>(Rt) % 16 == 0);
+    DgArgs g{};
+    g.Rt = Rt; g.ld_rt = k_q; g.idxA = anc; g.bs_idxA = 0; g.idxB = anc; g.bs_idxB = 0;
+    g.Cout = L1; g.ldc = s; g.bsC = 0; g.M = s; g.N = s; g.K = k_q; g.sign = 1.0; g.diag_off = 0; g.vec4 = vec4;
+    rc = dgemm_launch(g, true, 1, stream);
+    if (rc != ANNCUR_OK) return rc;
+    // V (workspace) first holds a copy of the raw Gram diagonal block (the Cholesky runs in place on L1)
+    ANNCUR_CUDA_OK(cudaMemcpyAsync(V, L1, sizeof(double) * size_t(s) * s, cudaMemcpyDeviceToDevice, stream));
+    const size_t smem = chol_inv_smem(s, 0);
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    chol_inv_kernel<<<1, 256, smem, stream>>>(L1, 0, s, V, 0, s, maxd, L1inv, 0, s, rcond, nullptr, 0, 0, 0, nullptr, 0, nullptr, 0);
+    ANNCUR_LAUNCH_OK("chol_inv_kernel");
+    // V = R_anc^T M_1 (n_items x s), W_1^T = V L_1^-T
+    DgArgs v{};
+    v.Rt = Rt; v.ld_rt = k_q; v.idxA = nullptr; v.idxB = anc; v.bs_idxB = 0;
+    v.Cout = V; v.ldc = s; v.bsC = 0; v.M = int(n_items); v.N = s; v.K = k_q; v.sign = 1.0; v.diag_off = DG_ALL; v.vec4 = vec4;
+    if (n_items > int64_t(65535) * DG_T) { set_error("adaptive_prepare: n_items = %lld too large", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
+    rc = dgemm_launch(v, true, 1, stream);
+    if (rc != ANNCUR_OK) return rc;
+    DgArgs w{};
+    w.A = V; w.lda = s; w.bsA = 0; w.B = L1inv; w.ldb = s; w.bsB = 0;
+    w.Cout = W1t; w.ldc = s; w.bsC = 0; w.M = int(n_items); w.N = s; w.K = s; w.sign = 1.0; w.diag_off = DG_ALL;
+    return dgemm_launch(w, false, 1, stream);
+}
+
+static int backsolve_launch(const float* Rt, int k_q, const IncShared& sl, const char* sb, int s, const IncState& st, char* stb,
+                            int n, int nblocks, int n_queries, float* e_out, cudaStream_t stream) {
+    const int m = s + nblocks * n;
+    const size_t smem = (sizeof(double) + sizeof(int64_t)) * size_t(m > 0 ? m : 1);
+    ANNCUR_CUDA_OK(cudaFuncSetAttribute(backsolve_e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    backsolve_e_kernel<<<n_queries, 256, smem, stream>>>(
+        Rt, k_q, reinterpret_cast<const int64_t*>(sb + sl.off_anc), reinterpret_cast<const double*>(sb + sl.off_l1inv), s,
+        reinterpret_cast<const int64_t*>(stb + st.off_anc), st.bs_anc, reinterpret_cast<const double*>(stb + st.off_lq), st.bsLq, st.ldl,
+        reinterpret_cast<const double*>(stb + st.off_linv), st.bsLinv, reinterpret_cast<const double*>(stb + st.off_z), st.bsz, n, nblocks,
+        e_out);
+    ANNCUR_LAUNCH_OK("backsolve_e_kernel");
+    return ANNCUR_OK;
+}
+
+// Round 1: the shared anchors.  z_0 = L_1^-1 c_1 per query, e = c_1 . pinv(M_1).
+int adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared, int s, const float* c, int n_queries, int n_new,
+                   int m_max, float* e_out, void* state, size_t state_bytes, cudaStream_t stream) {
+    int rc = check_inc_shape("adaptive_begin", k_q, s, n_new, m_max);
+    if (rc != ANNCUR_OK) return rc;
+    const IncShared sl = inc_shared_layout(n_items, s);
+    const IncState st = inc_state_layout(n_queries, s, n_new, m_max);
+    if (state_bytes < st.total) { set_error("adaptive_begin: state too small: %zu < %zu", state_bytes, st.total); return ANNCUR_E_WORKSPACE; }
+    if (n_queries == 0) return ANNCUR_OK;
+    const char* sb = reinterpret_cast<const char*>(shared);
+    char* stb = reinterpret_cast<char*>(state);
+    z_shared_kernel<<<n_queries, 128, sizeof(double) * size_t(s > 0 ? s : 1), stream>>>(
+        reinterpret_cast<const double*>(sb + sl.off_l1inv), s, reinterpret_cast<const double*>(sb + sl.off_maxd), c,
+        reinterpret_cast<double*>(stb + st.off_z), st.bsz, reinterpret_cast<double*>(stb + st.off_maxd));
+    ANNCUR_LAUNCH_OK("z_shared_kernel");
+    if (s == 0) { ANNCUR_CUDA_OK(cudaMemsetAsync(e_out, 0, sizeof(float) * size_t(n_queries) * k_q, stream)); return ANNCUR_OK; }
+    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n_new, 0, n_queries, e_out, stream);
+}
+
+// Round t + 1: every query gets n_new more anchors (m_cur = anchors so far = m_shared + r * n_new).
+int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* shared, int s, const int64_t* new_anchors,
+                    const float* c_new, int n_queries, int n, int m_max, int m_cur, double rcond, float* e_out, void* state,
+                    size_t state_bytes, cudaStream_t stream) {
+    int rc = check_inc_shape("adaptive_extend", k_q, s, n, m_max);
+    if (rc != ANNCUR_OK) return rc;
+    if (m_cur < s || (m_cur - s) % n != 0 || m_cur + n > m_max) { set_error("adaptive_extend: m_cur = %d does not fit m_shared = %d, n_new = %d, m_max = %d", m_cur, s, n, m_max); return ANNCUR_E_INVALID; }
+    const IncShared sl = inc_shared_layout(n_items, s);
+    const IncState st = inc_state_layout(n_queries, s, n, m_max);
+    if (state_bytes < st.total) { set_error("adaptive_extend: state too small: %zu < %zu", state_bytes, st.total); return ANNCUR_E_WORKSPACE; }
+    if (n_queries == 0) return ANNCUR_OK;
+    if (n_queries > 65535) { set_error("adaptive_extend: n_queries = %d > 65535 per call", n_queries); return ANNCUR_E_UNSUPPORTED; }
+    const char* sb = reinterpret_cast<const char*>(shared);
+    char* stb = reinterpret_cast<char*>(state);
+    int64_t* anc_q = reinterpret_cast<int64_t*>(stb + st.off_anc);
+    double* maxd = reinterpret_cast<double*>(stb + st.off_maxd);
+    double* z = reinterpret_cast<double*>(stb + st.off_z);
+    double* Lq = reinterpret_cast<double*>(stb + st.off_lq);
+    double* Linvq = reinterpret_cast<double*>(stb + st.off_linv);
+    double* T = reinterpret_cast<double*>(stb + st.off_t);
+    const double* W1t = reinterpret_cast<const double*>(sb + sl.off_w1t);
+    const int r = (m_cur - s) / n;                         // per-query blocks so far
+    const int64_t new_row0 = int64_t(r) * n * st.ldl;      // offset of the new rows inside a query's Lq
+    const int vec4 = (k_q % 4 == 0) && (reinterpret_cast<uintptr_t>(Rt) % 16 == 0);
+
+    // a. anchors join the lists; shared columns of the new rows = gather from W_1^T
+    {
+        const int64_t warps = int64_t(n_queries) * n;
+        append_anchors_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, stream>>>(new_anchors, n, n_queries, r, anc_q, st.bs_anc, W1t, s,
+                                                                                    Lq, st.bsLq, st.ldl);
+        ANNCUR_LAUNCH_OK("append_anchors_kernel");
+    }
+    // b. raw Gram rows of the new anchors against the per-query anchors (old, then new: lower triangle of the last block)
+    {
+        DgArgs g{};
+        g.Rt = Rt; g.ld_rt = k_q; g.idxA = anc_q + int64_t(r) * n; g.bs_idxA = st.bs_anc; g.idxB = anc_q; g.bs_idxB = st.bs_anc;
+        g.Cout = T + s; g.ldc = st.ldl; g.bsC = st.bsT; g.M = n; g.N = (r + 1) * n; g.K = k_q; g.sign = 1.0; g.diag_off = r * n; g.vec4 = vec4;
+        rc = dgemm_launch(g, true, n_queries, stream);
+        if (rc != ANNCUR_OK) return rc;
+    }
+    // c. the columns of the earlier per-query blocks: T_j -= X[:, 0:c0] L_j[:, 0:c0]^T, X_j = T_j L_jj^-T
+    for (int j = 0; j < r; ++j) {
+        const int c0 = s + j * n;
+        if (c0 > 0) {
+            DgArgs u{};
+            u.A = Lq + new_row0; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(j) * n * st.ldl; u.ldb = st.ldl; u.bsB = st.bsLq;
+            u.Cin = T + c0; u.ldcin = st.ldl; u.bsCin = st.bsT; u.Cout = T + c0; u.ldc = st.ldl; u.bsC = st.bsT;
+            u.M = n; u.N = n; u.K = c0; u.sign = -1.0; u.diag_off = DG_ALL;
+            rc = dgemm_launch(u, false, n_queries, stream);
+            if (rc != ANNCUR_OK) return rc;
+        }
+        DgArgs x{};
+        x.A = T + c0; x.lda = st.ldl; x.bsA = st.bsT; x.B = Linvq + int64_t(j) * n * n; x.ldb = n; x.bsB = st.bsLinv;
+        x.Cout = Lq + new_row0 + c0; x.ldc = st.ldl; x.bsC = st.bsLq; x.M = n; x.N = n; x.K = n; x.sign = 1.0; x.diag_off = DG_ALL;
+        rc = dgemm_launch(x, false, n_queries, stream);
+        if (rc != ANNCUR_OK) return rc;
+    }
+    // d. Schur complement S = N^T N - X X^T (lower) into the diagonal block
+    {
+        DgArgs d{};
+        d.A = Lq + new_row0; d.lda = st.ldl; d.bsA = st.bsLq; d.B = Lq + new_row0; d.ldb = st.ldl; d.bsB = st.bsLq;
+        d.Cin = T + m_cur; d.ldcin = st.ldl; d.bsCin = st.bsT; d.Cout = Lq + new_row0 + m_cur; d.ldc = st.ldl; d.bsC = st.bsLq;
+        d.M = n; d.N = n; d.K = m_cur; d.sign = -1.0; d.diag_off = 0;
+        rc = dgemm_launch(d, false, n_queries, stream);
+        if (rc != ANNCUR_OK) return rc;
+    }
+    // e. Cholesky + inverse of the Schur complement, new block of z
+    {
+        const size_t smem = chol_inv_smem(n, m_cur);
+        ANNCUR_CUDA_OK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        chol_inv_kernel<<<n_queries, 256, smem, stream>>>(Lq + new_row0 + m_cur, st.bsLq, st.ldl, T + m_cur, st.bsT, st.ldl, maxd,
+                                                          Linvq + int64_t(r) * n * n, st.bsLinv, n, rcond,
+                                                          Lq + new_row0, st.bsLq, st.ldl, m_cur, z, st.bsz, c_new, n);
+        ANNCUR_LAUNCH_OK("chol_inv_kernel");
+    }
+    // f. y = L^-T z, e = (M y)^T
+    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n, r + 1, n_queries, e_out, stream);
+}
+
+}  // namespace anncur

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libanncur_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["capi.cu", "select_topk.cu", "refine_topk.cu", "sgemm.cu", "pinv.cu", "rerank.cu", "score_topk_umma.cu", "adaptive.cu", "peer_exchange.cu"]
+SOURCES = ["capi.cu", "select_topk.cu", "refine_topk.cu", "sgemm.cu", "pinv.cu", "rerank.cu", "score_topk_umma.cu", "adaptive.cu", "adaptive_inc.cu", "peer_exchange.cu"]
 HEADERS = ["common.cuh", "kernels.h", "warp_select.cuh", os.path.join("..", "..", "include", "anncur_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -394,4 +394,33 @@ int anncur_filter_excluded(const float* cand_vals, const int64_t* cand_idx, int 
     return filter_excluded(cand_vals, cand_idx, n_rows, k_in, excluded, m, n_out, out_vals, out_idx, cudaStream_t(stream));
 }
 
+size_t anncur_adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared) { return adaptive_shared_bytes(k_q, n_items, m_shared); }
+size_t anncur_adaptive_prepare_workspace_bytes(int k_q, int64_t n_items, int m_shared) {
+    return adaptive_prepare_workspace_bytes(k_q, n_items, m_shared);
+}
+int anncur_adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* shared_anchors, int m_shared, double rcond,
+                            void* shared, size_t shared_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    ANNCUR_REQUIRE(k_q > 0 && n_items > 0 && m_shared >= 0, "adaptive_prepare: bad shape");
+    ANNCUR_REQUIRE(Rt && shared && (m_shared == 0 || (shared_anchors && workspace)), "adaptive_prepare: null pointer");
+    return adaptive_prepare(Rt, k_q, n_items, shared_anchors, m_shared, rcond, shared, shared_bytes, workspace, workspace_bytes,
+                            cudaStream_t(stream));
+}
+size_t anncur_adaptive_state_bytes(int n_queries, int k_q, int m_shared, int n_new, int m_max) {
+    return adaptive_state_bytes(n_queries, k_q, m_shared, n_new, m_max);
+}
+int anncur_adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared, int m_shared, const float* c, int n_queries,
+                          int n_new, int m_max, float* e_out, void* state, size_t state_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && k_q > 0 && n_items > 0 && m_shared >= 0, "adaptive_begin: bad shape");
+    ANNCUR_REQUIRE(Rt && shared && state && (n_queries == 0 || (e_out && (m_shared == 0 || c))), "adaptive_begin: null pointer");
+    return adaptive_begin(Rt, k_q, n_items, shared, m_shared, c, n_queries, n_new, m_max, e_out, state, state_bytes, cudaStream_t(stream));
+}
+int anncur_adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* shared, int m_shared, const int64_t* new_anchors,
+                           const float* c_new, int n_queries, int n_new, int m_max, int m_cur, double rcond, float* e_out,
+                           void* state, size_t state_bytes, void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && k_q > 0 && n_items > 0 && m_shared >= 0, "adaptive_extend: bad shape");
+    ANNCUR_REQUIRE(Rt && shared && state && (n_queries == 0 || (new_anchors && c_new && e_out)), "adaptive_extend: null pointer");
+    return adaptive_extend(Rt, k_q, n_items, shared, m_shared, new_anchors, c_new, n_queries, n_new, m_max, m_cur, rcond, e_out,
+                           state, state_bytes, cudaStream_t(stream));
+}
+
 }  // extern "C"

@@ -103,4 +103,16 @@ int filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows,
                     float* out_vals, int64_t* out_idx, cudaStream_t stream);
 int transpose_rows(const float* in, int64_t ld_in, int rows, int64_t cols, float* out, cudaStream_t stream);
 
+// adaptive_inc.cu
+size_t adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared);
+size_t adaptive_prepare_workspace_bytes(int k_q, int64_t n_items, int m_shared);
+int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* shared_anchors, int s, double rcond,
+                     void* shared, size_t shared_bytes, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t adaptive_state_bytes(int n_queries, int k_q, int m_shared, int n_new, int m_max);
+int adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared, int s, const float* c, int n_queries, int n_new,
+                   int m_max, float* e_out, void* state, size_t state_bytes, cudaStream_t stream);
+int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* shared, int s, const int64_t* new_anchors,
+                    const float* c_new, int n_queries, int n, int m_max, int m_cur, double rcond, float* e_out, void* state,
+                    size_t state_bytes, cudaStream_t stream);
+
 }  // namespace anncur

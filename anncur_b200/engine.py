@@ -8,6 +8,7 @@ import torch
 from . import _lib
 from ._lib import KIND_BF16, KIND_F32R, KIND_F32X3, MAX_K, MAX_K_DIM_F32R, MAX_K_FUSED  # noqa: F401
 
+ADAPTIVE_MAX_BLOCK = 128      # ANNCUR_ADAPTIVE_MAX_BLOCK
 KINDS = {"f32r": KIND_F32R, "f32x3": KIND_F32X3, "bf16": KIND_BF16}
 
 
@@ -622,3 +623,65 @@ def filter_excluded(cand_vals, cand_idx, excluded, n_out):
             _lib.check(lib.anncur_filter_excluded(_ptr(cand_vals), _ptr(cand_idx), n, k_in, _ptr(excluded), m, int(n_out), _ptr(vals),
                                                   _ptr(idx), _stream()))
     return vals, idx
+
+
+class AdaptiveShared:
+    """What anncur_adaptive_prepare builds once per (R_anc, shared first anchors): the Cholesky factor of the shared Gram
+    matrix, its inverse and W_1^T (n_items x m_shared fp64) -- see include/anncur_b200.h."""
+
+    def __init__(self, Rt, shared_anchors, rcond=1e-15):
+        lib = _lib.load()
+        self.Rt = _f32(Rt).contiguous()
+        dev = self.Rt.device
+        self.N, self.k_q = self.Rt.shape
+        self.anchors = torch.as_tensor(shared_anchors, dtype=torch.int64, device=dev).contiguous()
+        self.m_shared = int(self.anchors.numel())
+        self.rcond = float(rcond)
+        with torch.cuda.device(dev):
+            self.blob = torch.empty(lib.anncur_adaptive_shared_bytes(self.k_q, self.N, self.m_shared), dtype=torch.uint8, device=dev)
+            ws = torch.empty(lib.anncur_adaptive_prepare_workspace_bytes(self.k_q, self.N, self.m_shared), dtype=torch.uint8, device=dev)
+            _lib.check(lib.anncur_adaptive_prepare(_ptr(self.Rt), self.k_q, self.N, _ptr(self.anchors), self.m_shared, self.rcond,
+                                                   _ptr(self.blob), self.blob.numel(), _ptr(ws), ws.numel(), _stream()))
+            torch.cuda.current_stream(dev).synchronize()          # ws is dropped on return
+        del ws
+
+
+class AdaptiveState:
+    """Per-batch state of the incremental adaptive solver (anncur_adaptive_begin / anncur_adaptive_extend): call ``begin(c)``
+    with the exact scores of the shared anchors, then ``extend(new_anchors, c_new)`` once per round; both return e (B x k_q)."""
+
+    def __init__(self, shared, n_queries, n_new, m_max):
+        lib = _lib.load()
+        self.shared, self.B, self.n_new, self.m_max = shared, int(n_queries), int(n_new), int(m_max)
+        self.m_cur = None
+        dev = shared.Rt.device
+        with torch.cuda.device(dev):
+            nbytes = lib.anncur_adaptive_state_bytes(self.B, shared.k_q, shared.m_shared, self.n_new, self.m_max)
+            self.blob = WORKSPACE.get("adaptive_state", nbytes, dev)
+
+    def begin(self, c):
+        lib, sh = _lib.load(), self.shared
+        dev = sh.Rt.device
+        c = _f32(c, device=dev).contiguous()
+        assert c.shape == (self.B, sh.m_shared)
+        e = torch.empty((self.B, sh.k_q), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_adaptive_begin(_ptr(sh.Rt), sh.k_q, sh.N, _ptr(sh.blob), sh.m_shared, _ptr(c), self.B, self.n_new,
+                                                 self.m_max, _ptr(e), _ptr(self.blob), self.blob.numel(), _stream()))
+        self.m_cur = sh.m_shared
+        return e
+
+    def extend(self, new_anchors, c_new):
+        lib, sh = _lib.load(), self.shared
+        dev = sh.Rt.device
+        assert self.m_cur is not None, "begin() first"
+        new_anchors = new_anchors.to(device=dev, dtype=torch.int64).contiguous()
+        c_new = _f32(c_new, device=dev).contiguous()
+        assert new_anchors.shape == (self.B, self.n_new) and c_new.shape == (self.B, self.n_new)
+        e = torch.empty((self.B, sh.k_q), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.anncur_adaptive_extend(_ptr(sh.Rt), sh.k_q, sh.N, _ptr(sh.blob), sh.m_shared, _ptr(new_anchors), _ptr(c_new),
+                                                  self.B, self.n_new, self.m_max, self.m_cur, sh.rcond, _ptr(e), _ptr(self.blob),
+                                                  self.blob.numel(), _stream()))
+        self.m_cur += self.n_new
+        return e

@@ -292,6 +292,32 @@ ANNCUR_API int anncur_transpose_f32(const float* in, int64_t ld_in, int rows, in
 ANNCUR_API int anncur_filter_excluded(const float* cand_vals, const int64_t* cand_idx, int n_rows, int k_in,
                            const int64_t* excluded, int m, int n_out, float* out_vals, int64_t* out_idx, void* stream);
 
+/* Incremental form of K8: the per-query factorisation is CARRIED across rounds (I_{t+1} = I_t U new_t) and the first
+ * m_shared anchors are shared by all queries, so a round costs the Gram rows and the Cholesky rows of its n_new NEW
+ * anchors only (45 MFLOP per query over BASELINE configs[2]'s rounds instead of 241; csrc/adaptive_inc.cu).
+ *   Rt       R_anc^T, n_items x k_q fp32 (anncur_transpose_f32)
+ *   shared   blob of anncur_adaptive_shared_bytes: built ONCE per (R_anc, shared anchors) by anncur_adaptive_prepare
+ *            (Cholesky factor of the shared Gram matrix, its inverse, and W_1^T = (L_1^-1 M_1^T R_anc)^T, n_items x
+ *            m_shared fp64, from which every later round gathers its shared columns)
+ *   state    blob of anncur_adaptive_state_bytes: per-query factor rows, block inverses, z = L^-1 c, anchor lists
+ *   anncur_adaptive_begin   round 1: e_b = c_b . pinv(R_anc[:, shared])            (c: n_queries x m_shared)
+ *   anncur_adaptive_extend  every later round: n_new more anchors per query (m_cur = anchors held before the call, =
+ *                           m_shared + r n_new), their exact scores c_new, e_b for the grown set (n_queries x k_q fp32)
+ * m_shared and n_new <= ANNCUR_ADAPTIVE_MAX_BLOCK, m_max = m_shared + (rounds) n_new <= k_q.  Same pivot rule as
+ * anncur_adaptive_solve (pivots <= rcond^2 * largest Gram diagonal are dropped: that anchor's coordinate is 0). */
+#define ANNCUR_ADAPTIVE_MAX_BLOCK 128
+ANNCUR_API size_t anncur_adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared);
+ANNCUR_API size_t anncur_adaptive_prepare_workspace_bytes(int k_q, int64_t n_items, int m_shared);
+ANNCUR_API int anncur_adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* shared_anchors, int m_shared,
+                            double rcond, void* shared, size_t shared_bytes, void* workspace, size_t workspace_bytes,
+                            void* stream);
+ANNCUR_API size_t anncur_adaptive_state_bytes(int n_queries, int k_q, int m_shared, int n_new, int m_max);
+ANNCUR_API int anncur_adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared, int m_shared, const float* c,
+                          int n_queries, int n_new, int m_max, float* e_out, void* state, size_t state_bytes, void* stream);
+ANNCUR_API int anncur_adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* shared, int m_shared,
+                           const int64_t* new_anchors, const float* c_new, int n_queries, int n_new, int m_max, int m_cur,
+                           double rcond, float* e_out, void* state, size_t state_bytes, void* stream);
+
 /* ---- per-kernel device timing (bench.py's roofline) ---------------------------------------------
  * While enabled, every anncur_score_topk call records a CUDA-event pair around its fused tcgen05
  * kernel on the call's stream.  anncur_profile_read waits for the recorded events (it is the one

@@ -313,7 +313,102 @@ def test_filter_excluded_keeps_order_and_pads(eng):
         assert i[r].tolist()[:len(keep)] == keep and all(x == -1 for x in i[r].tolist()[len(keep):])
 
 
-@pytest.mark.parametrize("rescore", ["fused", "ffma"])
+def _np_pinv_e(R, anchors_q, c_q, rcond=1e-15):
+    return c_q.astype(np.float64) @ np.linalg.pinv(R[:, anchors_q].astype(np.float64), rcond=rcond)
+
+
+@pytest.mark.parametrize("k_q,N,B,s,n,rounds", [(60, 700, 9, 7, 12, 3), (64, 900, 5, 0, 16, 3), (500, 5000, 6, 125, 125, 2),
+                                                (130, 1500, 3, 128, 1, 2), (96, 800, 4, 20, 33, 2)])
+def test_adaptive_incremental_solver_matches_fp64_pinv(eng, k_q, N, B, s, n, rounds):
+    """anncur_adaptive_prepare / _begin / _extend (the factor carried across rounds, shared first anchors gathered from
+    W_1) against numpy's fp64 pinv of the grown anchor set, and against the from-scratch anncur_adaptive_solve."""
+    rng = np.random.default_rng(3)
+    A = O.synthetic_scores(k_q + B, N, rank=max(8, k_q // 8), noise=0.05, seed=11)
+    R, X = A[:k_q], A[k_q:]
+    Rc = torch.from_numpy(R).cuda()
+    Rt = eng.transpose(Rc)
+    perm = np.stack([rng.permutation(N) for _ in range(B)])
+    first = np.sort(perm[0, :s])
+    shared = eng.AdaptiveShared(Rt, torch.from_numpy(first), 1e-15)
+    state = eng.AdaptiveState(shared, B, n, s + rounds * n)
+    e = state.begin(torch.from_numpy(X[:, first]).cuda()).cpu().numpy()
+    cur = np.tile(first[None, :], (B, 1))
+    for q in range(B):
+        if s > 0:
+            want = _np_pinv_e(R, cur[q], X[q, cur[q]])
+            assert np.allclose(e[q], want, atol=2e-5 * np.abs(want).max()), (q, np.abs(e[q] - want).max(), np.abs(want).max())
+        else:
+            assert (e[q] == 0).all()
+    for t in range(rounds):
+        new = np.stack([[j for j in perm[q] if j not in set(first.tolist())][t * n:(t + 1) * n] for q in range(B)]).astype(np.int64)
+        c_new = np.take_along_axis(X, new, 1)
+        e = state.extend(torch.from_numpy(new).cuda(), torch.from_numpy(c_new).cuda()).cpu().numpy()
+        cur = np.concatenate([cur, new], 1)
+        full = eng.adaptive_solve(Rc, torch.from_numpy(cur).cuda(), torch.from_numpy(np.take_along_axis(X, cur, 1)).cuda(), Rt=Rt).cpu().numpy()
+        for q in range(B):
+            want = _np_pinv_e(R, cur[q], X[q, cur[q]])
+            scale = np.abs(want).max()
+            assert np.allclose(e[q], want, atol=2e-5 * scale), (t, q, np.abs(e[q] - want).max(), scale)
+            assert np.allclose(e[q], full[q], atol=2e-5 * scale)
+
+
+def test_adaptive_incremental_solver_drops_dependent_anchors_like_the_full_solve(eng):
+    """Two anchors with identical columns of R_anc: the later one's pivot falls below rcond^2 * max diagonal and its
+    coordinate is dropped -- in the block form exactly as in the from-scratch Cholesky."""
+    rng = np.random.default_rng(5)
+    k_q, N, B, s, n = 48, 600, 4, 8, 8
+    A = O.synthetic_scores(k_q + B, N, rank=10, noise=0.05, seed=13)
+    A[:, 100] = A[:, 7]                                   # item 100 duplicates item 7 (also in the exact rows: consistent system)
+    A[:, 200] = A[:, 300]
+    R, X = A[:k_q], A[k_q:]
+    Rc = torch.from_numpy(R).cuda()
+    Rt = eng.transpose(Rc)
+    first = np.array([3, 7, 50, 90, 120, 200, 310, 400])
+    new = np.stack([np.array([100, 5, 300, 11, 13, 17, 19, 23]) + 0 * q for q in range(B)]).astype(np.int64)
+    new[1, 3] = 555
+    shared = eng.AdaptiveShared(Rt, torch.from_numpy(first), 1e-6)
+    state = eng.AdaptiveState(shared, B, n, s + n)
+    state.begin(torch.from_numpy(X[:, first]).cuda())
+    e = state.extend(torch.from_numpy(new).cuda(), torch.from_numpy(np.take_along_axis(X, new, 1)).cuda()).cpu().numpy()
+    cur = np.concatenate([np.tile(first[None], (B, 1)), new], 1)
+    full = eng.adaptive_solve(Rc, torch.from_numpy(cur).cuda(), torch.from_numpy(np.take_along_axis(X, cur, 1)).cuda(), rcond=1e-6, Rt=Rt).cpu().numpy()
+    assert np.isfinite(e).all() and np.allclose(e, full, atol=1e-5 * np.abs(full).max())
+    for q in range(B):                                    # consistent duplicates: dropping one of the pair IS the pinv answer
+        want = _np_pinv_e(R, cur[q], X[q, cur[q]], rcond=1e-9)
+        assert np.allclose(e[q], want, atol=1e-4 * np.abs(want).max())
+
+
+def test_adaptive_rounds_pick_exactly_outside_the_tie_band(eng):
+    """Every round of the whole procedure (incremental solver + fused re-score + anchor filter) against the fp64 statement
+    of that round ON THE SAME ANCHOR SET: each pick must score within tau = 1e-4 max|s| of the oracle's n-th best unmasked
+    item (so picks differ from the oracle's only among ties inside the band), never repeat an anchor, and come best first."""
+    from anncur_b200 import adaptive_anncur
+    rng = np.random.default_rng(9)
+    k_q, N, B, T, kpr, top_k = 64, 5000, 20, 4, 16, 10
+    A = O.synthetic_scores(k_q + B, N, rank=12, noise=0.05, seed=17)
+    R, X = A[:k_q], A[k_q:]
+    first = np.sort(rng.choice(N, kpr, replace=False))
+    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k)
+    anc = anc.cpu().numpy()
+    R64 = R.astype(np.float64)
+    n_exact = 0
+    for q in range(B):
+        for t in range(1, T):
+            cur, got = anc[q, :t * kpr], anc[q, t * kpr:(t + 1) * kpr]
+            sc = _np_pinv_e(R, cur, X[q, cur]) @ R64
+            sc[cur] = -np.inf
+            order = np.argsort(-sc, kind="stable")
+            tau = 1e-4 * np.abs(sc[np.isfinite(sc)]).max()
+            assert len(set(got.tolist())) == kpr and not set(got.tolist()) & set(cur.tolist())
+            assert all(sc[j] >= sc[order[kpr - 1]] - tau for j in got), (q, t)
+            assert all(sc[got[i]] >= sc[got[i + 1]] - tau for i in range(kpr - 1))
+            n_exact += set(got.tolist()) == set(order[:kpr].tolist())
+    assert n_exact >= 0.9 * B * (T - 1)                   # and almost always it IS the oracle's set
+    want_anc, want_idx, want_val, _ = O.adaptive_anncur(R, X, first, T, kpr, top_k, rcond=1e-15)
+    assert np.mean([len(set(anc[q].tolist()) & set(want_anc[q].tolist())) / (T * kpr) for q in range(B)]) > 0.97
+
+
+@pytest.mark.parametrize("rescore", ["fused", "fused-full", "ffma"])
 def test_adaptive_multi_round_matches_oracle_restatement(eng, rescore):
     """The whole multi-round procedure (anncur_b200.adaptive_anncur: T - 1 K8 calls, exact-score gathers, K9 at the end)
     against oracle.cur_oracle.adaptive_anncur.  Picks of a round may differ from the oracle's only among near-ties of the
@@ -326,7 +421,8 @@ def test_adaptive_multi_round_matches_oracle_restatement(eng, rescore):
     R, X = A[:k_q], A[k_q:]
     first = np.sort(rng.choice(N, kpr, replace=False))
     want_anc, want_idx, want_val, _ = O.adaptive_anncur(R, X, first, T, kpr, top_k, rcond=1e-15)
-    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k, rescore=rescore)
+    anc, idx, val = adaptive_anncur(torch.from_numpy(R), torch.from_numpy(X), first, T, kpr, top_k, rescore=rescore.split("-")[0],
+                                    solver="full" if rescore.endswith("full") else "incremental")
     anc, idx, val = anc.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
     assert anc.shape == (B, T * kpr) and (anc[:, :kpr] == first[None, :]).all()
     assert all(len(set(r.tolist())) == T * kpr for r in anc)                 # anchors are never re-picked
