@@ -173,21 +173,16 @@ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 __global__ void __launch_bounds__(256)
 chol_inv_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds,                   // in: S (lower), out: L_D (lower)
-                const double* __restrict__ rawdiag, int64_t bs_rd, int64_t ld_rd,       // raw Gram block of the new anchors (its diagonal = |column|^2)
+                const double* __restrict__ rawdiag, int64_t bs_rd, int64_t ld_rd,       // raw Gram block (its diagonal = |column|^2)
                 double* __restrict__ maxd,                                              // [batch] running max of the Gram diagonal (in / out)
                 double* __restrict__ Linv, int64_t bsLinv,                              // out: L_D^-1, n x n row-major, upper triangle zeroed
-                int n, double rcond,
-                const double* __restrict__ X, int64_t bsX, int64_t ldx, int m_p,        // optional: the new rows of L, columns [0, m_p)
-                double* __restrict__ z, int64_t bsz,                                    //           z[0, m_p) in, z[m_p, m_p + n) out
-                const float* __restrict__ c_new, int64_t bsc) {
+                int n, double rcond) {
     extern __shared__ __align__(16) double ci_smem[];
     const int ntri = n * (n + 1) / 2;
     double* Ls = ci_smem;                    // [ntri]
     double* Li = Ls + ntri;                  // [ntri]
     double* pivs = Li + ntri;                // [n]
     double* invp = pivs + n;                 // [n]
-    double* tv = invp + n;                   // [n]
-    double* zs = tv + n;                     // [m_p] previous z
     __shared__ double red[8];
     __shared__ double s_maxd;
     const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -195,12 +190,10 @@ chol_inv_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds,           
     for (int i = ty; i < n; i += 8)
         for (int j = tx; j <= i; j += 32) Ls[tri(i, j)] = S[int64_t(i) * lds + j];
     double md = 0.0;
-    if (rawdiag)
-        for (int i = tid; i < n; i += 256) md = fmax(md, rawdiag[int64_t(b) * bs_rd + int64_t(i) * ld_rd + i]);
+    for (int i = tid; i < n; i += 256) md = fmax(md, rawdiag[int64_t(b) * bs_rd + int64_t(i) * ld_rd + i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
     if (tx == 0) red[ty] = md;
-    if (z) for (int i = tid; i < m_p; i += 256) zs[i] = z[int64_t(b) * bsz + i];
     __syncthreads();
     if (tid == 0) {
         double v = maxd[b];
@@ -245,7 +238,6 @@ chol_inv_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds,           
         }
     }
     __syncthreads();
-    // results to global memory
     double* Lo = Linv + int64_t(b) * bsLinv;
     for (int i = ty; i < n; i += 8) {
         for (int j = tx; j < n; j += 32) {
@@ -253,22 +245,65 @@ chol_inv_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds,           
             Lo[int64_t(i) * n + j] = j <= i ? Li[tri(i, j)] : 0.0;
         }
     }
-    if (z == nullptr) return;
-    // t = c_new - X z_prev (one warp per row), then z_new = L_D^-1 t
-    const double* Xb = X + int64_t(b) * bsX;
-    for (int i = ty; i < n; i += 8) {
-        double part = 0.0;
-        for (int k = tx; k < m_p; k += 32) part = fma(Xb[int64_t(i) * ldx + k], zs[k], part);
+}
+
+// The same for a block of w <= 32 columns, ONE WARP per query and everything in registers: lane i holds row i of the block,
+// broadcasts are shuffles, all loops are unrolled (rows / columns >= w are padded with the identity).  ~1000 shuffles and
+// ~1000 DFMAs per block; 12 warps per SM overlap their dependency chains.
+constexpr int CB = 32;
+__global__ void __launch_bounds__(128, 3)
+chol_inv32_kernel(double* __restrict__ Sbase, int64_t bsS, int64_t lds, const double* __restrict__ rawdiag, int64_t bs_rd, int64_t ld_rd,
+                  double* __restrict__ maxd, double* __restrict__ Linv, int64_t bsLinv, int w, double rcond, int n_queries) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= n_queries) return;
+    constexpr uint32_t FULL = 0xffffffffu;
+    double* S = Sbase + int64_t(b) * bsS;
+    double a[CB], x[CB];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (tx == 0) tv[i] = double(c_new[int64_t(b) * bsc + i]) - part;
+    for (int j = 0; j < CB; ++j) a[j] = (lane < w && j <= lane) ? S[int64_t(lane) * lds + j] : (j == lane ? 1.0 : 0.0);
+    double md = lane < w ? rawdiag[int64_t(b) * bs_rd + int64_t(lane) * ld_rd + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(FULL, md, o));
+    md = fmax(md, maxd[b]);
+    __syncwarp();
+    if (lane == 0) maxd[b] = md;
+    const double drop = fmax(rcond * rcond, 1e-28) * md;
+    double myinv = 0.0;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        const double piv = j < w ? (d > drop ? sqrt(d) : 0.0) : 1.0;
+        const double inv = piv > 0.0 ? 1.0 / piv : 0.0;
+        double l = a[j] * inv;
+        if (lane == j) { l = piv; myinv = inv; }
+        if (lane < j) l = 0.0;
+        a[j] = l;
+#pragma unroll
+        for (int t = j + 1; t < CB; ++t) {
+            const double ltj = __shfl_sync(FULL, l, t);
+            if (lane >= t) a[t] = fma(-l, ltj, a[t]);
+        }
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-        double a = 0.0;
-        for (int j = 0; j <= i; ++j) a = fma(Li[tri(i, j)], tv[j], a);
-        z[int64_t(b) * bsz + m_p + i] = a;
+    // lane = column of the inverse
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = __shfl_sync(FULL, a[k], i);
+            if (k & 1) acc1 = fma(lik, x[k], acc1); else acc0 = fma(lik, x[k], acc0);
+        }
+        const double invi = __shfl_sync(FULL, myinv, i);
+        x[i] = i == lane ? invi : (i > lane ? -(acc0 + acc1) * invi : 0.0);
     }
+    double* Lo = Linv + int64_t(b) * bsLinv;
+#pragma unroll
+    for (int i = 0; i < CB; ++i)
+        if (i < w && lane < w) Lo[i * CB + lane] = x[i];
+#pragma unroll
+    for (int j = 0; j < CB; ++j)
+        if (lane < w && j <= lane) S[int64_t(lane) * lds + j] = a[j];
 }
 
 // z_0 = L_1^-1 c_1 for every query (the shared first block), and the running Gram-diagonal maximum starts at the shared one.
@@ -303,57 +338,101 @@ append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_quer
     for (int t = lane_id(); t < s; t += 32) dst[t] = src[t];
 }
 
-// y = L^-T z by blocks (the block inverses make every step a transposed matrix-vector product), then e = (M y)^T.
+// Per query, after the round's rows of L are complete: the new blocks of z (forward substitution through the new rows, one
+// sub-block of <= 32 after the other), then y = L^-T z by blocks in reverse (the block inverses make every step a transposed
+// matrix-vector product), then e = (M y)^T.  Per-query rows come in rounds of n, each cut into sub-blocks of <= 32 columns
+// whose 32 x 32 inverses sit at Linvq + (local row) * 32; the shared block (s columns) has its s x s inverse L1inv.
 __global__ void __launch_bounds__(256)
 backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restrict__ shared_anc, const double* __restrict__ L1inv, int s,
                    const int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ Lq, int64_t bsLq, int ldl,
-                   const double* __restrict__ Linvq, int64_t bsLinv, const double* __restrict__ z, int64_t bsz, int n, int nblocks,
-                   float* __restrict__ e_out) {
+                   const double* __restrict__ Linvq, int64_t bsLinv, double* __restrict__ z, int64_t bsz, int n, int rounds_done,
+                   int new_round, const float* __restrict__ c_new, float* __restrict__ e_out) {
+    // rounds_done: per-query rounds whose z is already in the state; new_round = 1: one more round (rows rounds_done * n ..)
+    // is forward-substituted here from c_new.
     extern __shared__ __align__(16) double bs_smem[];
-    const int m = s + nblocks * n;
-    double* ys = bs_smem;                                   // [m] right-hand side, becomes y block by block
-    int64_t* items = reinterpret_cast<int64_t*>(ys + m);    // [m]
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int rounds = rounds_done + new_round;
+    const int m = s + rounds * n;
+    double* zs = bs_smem;                                   // [m] z
+    double* ys = zs + m;                                    // [m] right-hand side, becomes y block by block
+    double* tv = ys + m;                                    // [32]
+    int64_t* items = reinterpret_cast<int64_t*>(tv + CB);   // [m]
+    const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int m_old = s + rounds_done * n;
     for (int i = tid; i < m; i += 256) {
-        ys[i] = z[int64_t(b) * bsz + i];
+        zs[i] = i < m_old ? z[int64_t(b) * bsz + i] : 0.0;
         items[i] = i < s ? shared_anc[i] : anc_q[int64_t(b) * bs_anc + (i - s)];
     }
     __syncthreads();
     const double* L = Lq + int64_t(b) * bsLq;
-    for (int q = nblocks; q >= 0; --q) {
-        // q = nblocks .. 1: per-query block q - 1; q = 0: the shared block
-        const int c0 = q > 0 ? s + (q - 1) * n : 0;
-        const int nb = q > 0 ? n : s;
-        if (nb == 0) continue;
-        const double* Iv = q > 0 ? Linvq + int64_t(b) * bsLinv + int64_t(q - 1) * n * n : L1inv;
-        double yj = 0.0;
-        if (tid < nb) {                                     // y_j = sum_{i >= j} Linv[i][j] rhs[i]
-            double a0 = 0.0, a1 = 0.0;
-            int i = tid;
-            for (; i + 1 < nb; i += 2) {
-                a0 = fma(Iv[int64_t(i) * nb + tid], ys[c0 + i], a0);
-                a1 = fma(Iv[int64_t(i + 1) * nb + tid], ys[c0 + i + 1], a1);
+    const double* Iq = Linvq + int64_t(b) * bsLinv;
+    const int nsub = (n + CB - 1) / CB;
+    if (new_round) {
+        for (int k = 0; k < nsub; ++k) {
+            const int rho = rounds_done * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
+            for (int i = ty; i < w; i += 8) {               // t_i = c_i - sum_{col < c0} L[row i][col] z[col]
+                const double* Lr = L + int64_t(rho + i) * ldl;
+                double p0 = 0.0, p1 = 0.0;
+                int col = tx;
+                for (; col + 32 < c0; col += 64) { p0 = fma(Lr[col], zs[col], p0); p1 = fma(Lr[col + 32], zs[col + 32], p1); }
+                if (col < c0) p0 = fma(Lr[col], zs[col], p0);
+                p0 += p1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                if (tx == 0) tv[i] = double(c_new[int64_t(b) * n + k * CB + i]) - p0;
             }
-            if (i < nb) a0 = fma(Iv[int64_t(i) * nb + tid], ys[c0 + i], a0);
-            yj = a0 + a1;
+            __syncthreads();
+            if (tid < w) {
+                const double* Iv = Iq + int64_t(rho) * CB;
+                double acc = 0.0;
+                for (int j = 0; j <= tid; ++j) acc = fma(Iv[tid * CB + j], tv[j], acc);
+                zs[c0 + tid] = acc;
+                z[int64_t(b) * bsz + c0 + tid] = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid < nb) ys[c0 + tid] = yj;
-        __syncthreads();
-        if (q > 0) {                                        // rhs[col] -= sum_i L[row i of the block][col] y_i, col < c0
-            const double* Lr = L + int64_t(q - 1) * n * ldl;
+    }
+    for (int i = tid; i < m; i += 256) ys[i] = zs[i];
+    __syncthreads();
+    for (int rr = rounds - 1; rr >= 0; --rr) {
+        for (int k = nsub - 1; k >= 0; --k) {
+            const int rho = rr * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
+            const double* Iv = Iq + int64_t(rho) * CB;
+            double yj = 0.0;
+            if (tid < w) {                                  // y_j = sum_{i >= j} Linv[i][j] rhs[i]
+                for (int i = tid; i < w; ++i) yj = fma(Iv[i * CB + tid], ys[c0 + i], yj);
+            }
+            __syncthreads();
+            if (tid < w) ys[c0 + tid] = yj;
+            __syncthreads();
+            const double* Lr = L + int64_t(rho) * ldl;      // rhs[col] -= sum_i L[row i of the block][col] y_i, col < c0
             for (int col = tid; col < c0; col += 256) {
                 double a0 = 0.0, a1 = 0.0;
                 int i = 0;
-                for (; i + 1 < n; i += 2) {
+                for (; i + 1 < w; i += 2) {
                     a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
                     a1 = fma(Lr[int64_t(i + 1) * ldl + col], ys[c0 + i + 1], a1);
                 }
-                if (i < n) a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
+                if (i < w) a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
                 ys[col] -= a0 + a1;
             }
             __syncthreads();
         }
+    }
+    if (s > 0) {                                            // the shared block: y_0 = L_1^-T rhs_0
+        double yj = 0.0;
+        if (tid < s) {
+            double a0 = 0.0, a1 = 0.0;
+            int i = tid;
+            for (; i + 1 < s; i += 2) {
+                a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
+                a1 = fma(L1inv[int64_t(i + 1) * s + tid], ys[i + 1], a1);
+            }
+            if (i < s) a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
+            yj = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < s) ys[tid] = yj;
+        __syncthreads();
     }
     for (int t = tid; t < k_q; t += 256) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -392,7 +471,7 @@ static IncState inc_state_layout(int n_queries, int s, int n, int m_max) {
     p.ldl = (m_max + 1) & ~1;
     const size_t B = size_t(n_queries > 0 ? n_queries : 1);
     size_t off = 0;
-    p.bs_anc = p.mq; p.bsz = p.ldl; p.bsLq = int64_t(p.mq) * p.ldl; p.bsLinv = int64_t(p.mq) * n; p.bsT = int64_t(n) * p.ldl;
+    p.bs_anc = p.mq; p.bsz = p.ldl; p.bsLq = int64_t(p.mq) * p.ldl; p.bsLinv = int64_t(p.mq) * CB; p.bsT = int64_t(n) * p.ldl;
     p.off_anc = off; off += align_up(sizeof(int64_t) * B * size_t(p.mq > 0 ? p.mq : 1), 256);
     p.off_maxd = off; off += align_up(sizeof(double) * B, 256);
     p.off_z = off; off += align_up(sizeof(double) * B * p.ldl, 256);
@@ -403,7 +482,7 @@ static IncState inc_state_layout(int n_queries, int s, int n, int m_max) {
     return p;
 }
 
-static size_t chol_inv_smem(int n, int m_p) { return sizeof(double) * (size_t(n) * (n + 1) + 3 * size_t(n) + size_t(m_p > 0 ? m_p : 0)); }
+static size_t chol_inv_smem(int n) { return sizeof(double) * (size_t(n) * (n + 1) + 2 * size_t(n)); }
 
 size_t adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared) {
     (void)k_q;
@@ -458,9 +537,9 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     if (rc != ANNCUR_OK) return rc;
     // V (workspace) first holds a copy of the raw Gram diagonal block (the Cholesky runs in place on L1)
     ANNCUR_CUDA_OK(cudaMemcpyAsync(V, L1, sizeof(double) * size_t(s) * s, cudaMemcpyDeviceToDevice, stream));
-    const size_t smem = chol_inv_smem(s, 0);
+    const size_t smem = chol_inv_smem(s);
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    chol_inv_kernel<<<1, 256, smem, stream>>>(L1, 0, s, V, 0, s, maxd, L1inv, 0, s, rcond, nullptr, 0, 0, 0, nullptr, 0, nullptr, 0);
+    chol_inv_kernel<<<1, 256, smem, stream>>>(L1, 0, s, V, 0, s, maxd, L1inv, 0, s, rcond);
     ANNCUR_LAUNCH_OK("chol_inv_kernel");
     // V = R_anc^T M_1 (n_items x s), W_1^T = V L_1^-T
     DgArgs v{};
@@ -476,15 +555,15 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
 }
 
 static int backsolve_launch(const float* Rt, int k_q, const IncShared& sl, const char* sb, int s, const IncState& st, char* stb,
-                            int n, int nblocks, int n_queries, float* e_out, cudaStream_t stream) {
-    const int m = s + nblocks * n;
-    const size_t smem = (sizeof(double) + sizeof(int64_t)) * size_t(m > 0 ? m : 1);
+                            int n, int rounds_done, int new_round, const float* c_new, int n_queries, float* e_out, cudaStream_t stream) {
+    const int m = s + (rounds_done + new_round) * n;
+    const size_t smem = sizeof(double) * (2 * size_t(m) + CB) + sizeof(int64_t) * size_t(m > 0 ? m : 1);
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(backsolve_e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     backsolve_e_kernel<<<n_queries, 256, smem, stream>>>(
         Rt, k_q, reinterpret_cast<const int64_t*>(sb + sl.off_anc), reinterpret_cast<const double*>(sb + sl.off_l1inv), s,
         reinterpret_cast<const int64_t*>(stb + st.off_anc), st.bs_anc, reinterpret_cast<const double*>(stb + st.off_lq), st.bsLq, st.ldl,
-        reinterpret_cast<const double*>(stb + st.off_linv), st.bsLinv, reinterpret_cast<const double*>(stb + st.off_z), st.bsz, n, nblocks,
-        e_out);
+        reinterpret_cast<const double*>(stb + st.off_linv), st.bsLinv, reinterpret_cast<double*>(stb + st.off_z), st.bsz, n, rounds_done,
+        new_round, c_new, e_out);
     ANNCUR_LAUNCH_OK("backsolve_e_kernel");
     return ANNCUR_OK;
 }
@@ -505,7 +584,7 @@ int adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared
         reinterpret_cast<double*>(stb + st.off_z), st.bsz, reinterpret_cast<double*>(stb + st.off_maxd));
     ANNCUR_LAUNCH_OK("z_shared_kernel");
     if (s == 0) { ANNCUR_CUDA_OK(cudaMemsetAsync(e_out, 0, sizeof(float) * size_t(n_queries) * k_q, stream)); return ANNCUR_OK; }
-    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n_new, 0, n_queries, e_out, stream);
+    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n_new, 0, 0, nullptr, n_queries, e_out, stream);
 }
 
 // Round t + 1: every query gets n_new more anchors (m_cur = anchors so far = m_shared + r * n_new).
@@ -548,24 +627,27 @@ int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* share
         rc = dgemm_launch(g, true, n_queries, stream);
         if (rc != ANNCUR_OK) return rc;
     }
-    // c. the columns of the earlier per-query blocks: T_j -= X[:, 0:c0] L_j[:, 0:c0]^T, X_j = T_j L_jj^-T
-    for (int j = 0; j < r; ++j) {
-        const int c0 = s + j * n;
-        if (c0 > 0) {
-            DgArgs u{};
-            u.A = Lq + new_row0; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(j) * n * st.ldl; u.ldb = st.ldl; u.bsB = st.bsLq;
-            u.Cin = T + c0; u.ldcin = st.ldl; u.bsCin = st.bsT; u.Cout = T + c0; u.ldc = st.ldl; u.bsC = st.bsT;
-            u.M = n; u.N = n; u.K = c0; u.sign = -1.0; u.diag_off = DG_ALL;
-            rc = dgemm_launch(u, false, n_queries, stream);
+    // c. the columns of the earlier per-query sub-blocks, in order: T_j -= X[:, 0:c0] L_j[:, 0:c0]^T, X_j = T_j L_jj^-T
+    const int nsub = (n + CB - 1) / CB;
+    for (int rr = 0; rr < r; ++rr) {
+        for (int k = 0; k < nsub; ++k) {
+            const int rho = rr * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
+            if (c0 > 0) {
+                DgArgs u{};
+                u.A = Lq + new_row0; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(rho) * st.ldl; u.ldb = st.ldl; u.bsB = st.bsLq;
+                u.Cin = T + c0; u.ldcin = st.ldl; u.bsCin = st.bsT; u.Cout = T + c0; u.ldc = st.ldl; u.bsC = st.bsT;
+                u.M = n; u.N = w; u.K = c0; u.sign = -1.0; u.diag_off = DG_ALL;
+                rc = dgemm_launch(u, false, n_queries, stream);
+                if (rc != ANNCUR_OK) return rc;
+            }
+            DgArgs x{};
+            x.A = T + c0; x.lda = st.ldl; x.bsA = st.bsT; x.B = Linvq + int64_t(rho) * CB; x.ldb = CB; x.bsB = st.bsLinv;
+            x.Cout = Lq + new_row0 + c0; x.ldc = st.ldl; x.bsC = st.bsLq; x.M = n; x.N = w; x.K = w; x.sign = 1.0; x.diag_off = DG_ALL;
+            rc = dgemm_launch(x, false, n_queries, stream);
             if (rc != ANNCUR_OK) return rc;
         }
-        DgArgs x{};
-        x.A = T + c0; x.lda = st.ldl; x.bsA = st.bsT; x.B = Linvq + int64_t(j) * n * n; x.ldb = n; x.bsB = st.bsLinv;
-        x.Cout = Lq + new_row0 + c0; x.ldc = st.ldl; x.bsC = st.bsLq; x.M = n; x.N = n; x.K = n; x.sign = 1.0; x.diag_off = DG_ALL;
-        rc = dgemm_launch(x, false, n_queries, stream);
-        if (rc != ANNCUR_OK) return rc;
     }
-    // d. Schur complement S = N^T N - X X^T (lower) into the diagonal block
+    // d. Schur complement of everything before this round: S = N^T N - X X^T (lower) into the diagonal block
     {
         DgArgs d{};
         d.A = Lq + new_row0; d.lda = st.ldl; d.bsA = st.bsLq; d.B = Lq + new_row0; d.ldb = st.ldl; d.bsB = st.bsLq;
@@ -574,17 +656,32 @@ int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* share
         rc = dgemm_launch(d, false, n_queries, stream);
         if (rc != ANNCUR_OK) return rc;
     }
-    // e. Cholesky + inverse of the Schur complement, new block of z
-    {
-        const size_t smem = chol_inv_smem(n, m_cur);
-        ANNCUR_CUDA_OK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        chol_inv_kernel<<<n_queries, 256, smem, stream>>>(Lq + new_row0 + m_cur, st.bsLq, st.ldl, T + m_cur, st.bsT, st.ldl, maxd,
-                                                          Linvq + int64_t(r) * n * n, st.bsLinv, n, rcond,
-                                                          Lq + new_row0, st.bsLq, st.ldl, m_cur, z, st.bsz, c_new, n);
-        ANNCUR_LAUNCH_OK("chol_inv_kernel");
+    // e. right-looking factorisation of the n x n block in sub-blocks of <= 32: warp-level Cholesky + inverse of the diagonal
+    //    sub-block, the rows below it times the inverse (in place: one column tile, every CTA reads only the rows it writes),
+    //    rank-w update of what is left
+    for (int k = 0; k < nsub; ++k) {
+        const int rho = r * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, ck = m_cur + k * CB;
+        double* blk = Lq + int64_t(rho) * st.ldl + ck;
+        chol_inv32_kernel<<<(n_queries + 3) / 4, 128, 0, stream>>>(blk, st.bsLq, st.ldl, T + int64_t(k) * CB * st.ldl + ck, st.bsT, st.ldl, maxd,
+                                                                 Linvq + int64_t(rho) * CB, st.bsLinv, w, rcond, n_queries);
+        ANNCUR_LAUNCH_OK("chol_inv32_kernel");
+        const int mb = n - k * CB - w;
+        if (mb <= 0) continue;
+        double* below = Lq + int64_t(rho + w) * st.ldl + ck;
+        DgArgs x{};
+        x.A = below; x.lda = st.ldl; x.bsA = st.bsLq; x.B = Linvq + int64_t(rho) * CB; x.ldb = CB; x.bsB = st.bsLinv;
+        x.Cout = below; x.ldc = st.ldl; x.bsC = st.bsLq; x.M = mb; x.N = w; x.K = w; x.sign = 1.0; x.diag_off = DG_ALL;
+        rc = dgemm_launch(x, false, n_queries, stream);
+        if (rc != ANNCUR_OK) return rc;
+        DgArgs t{};
+        t.A = below; t.lda = st.ldl; t.bsA = st.bsLq; t.B = below; t.ldb = st.ldl; t.bsB = st.bsLq;
+        t.Cin = below + w; t.ldcin = st.ldl; t.bsCin = st.bsLq; t.Cout = below + w; t.ldc = st.ldl; t.bsC = st.bsLq;
+        t.M = mb; t.N = mb; t.K = w; t.sign = -1.0; t.diag_off = 0;
+        rc = dgemm_launch(t, false, n_queries, stream);
+        if (rc != ANNCUR_OK) return rc;
     }
-    // f. y = L^-T z, e = (M y)^T
-    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n, r + 1, n_queries, e_out, stream);
+    // f. new blocks of z, y = L^-T z, e = (M y)^T
+    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n, r, 1, c_new, n_queries, e_out, stream);
 }
 
 }  // namespace anncur
