@@ -139,8 +139,11 @@ dgemm_nt_kernel(const DgArgs p) {
         }
         __syncthreads();
     }
+    // epilogue: all old values are fetched before the first store (C_in may alias C_out, so the compiler would otherwise
+    // keep every load behind the previous store: 16 L2 round trips in a row)
     const double* Cin = p.Cin ? p.Cin + int64_t(b) * p.bsCin : nullptr;
     double* Cout = p.Cout + int64_t(b) * p.bsC;
+    double old[4][2][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -148,10 +151,18 @@ dgemm_nt_kernel(const DgArgs p) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int i = i0 + wr + r * 8 + fr, j = j0 + wc + c * 8 + fc * 2 + h;
-                if (i < p.M && j < p.N && int64_t(j) <= int64_t(i) + p.diag_off) {
-                    const double old = Cin ? Cin[int64_t(i) * p.ldcin + j] : 0.0;
-                    Cout[int64_t(i) * p.ldc + j] = old + p.sign * acc[r][c][h];
-                }
+                const bool ok = i < p.M && j < p.N && int64_t(j) <= int64_t(i) + p.diag_off;
+                old[r][c][h] = (Cin && ok) ? __ldcg(Cin + int64_t(i) * p.ldcin + j) : 0.0;
+            }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + wr + r * 8 + fr, j = j0 + wc + c * 8 + fc * 2 + h;
+                if (i < p.M && j < p.N && int64_t(j) <= int64_t(i) + p.diag_off)
+                    Cout[int64_t(i) * p.ldc + j] = old[r][c][h] + p.sign * acc[r][c][h];
             }
 }
 
@@ -348,14 +359,16 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
                    const double* __restrict__ Linvq, int64_t bsLinv, double* __restrict__ z, int64_t bsz, int n, int rounds_done,
                    int new_round, const float* __restrict__ c_new, float* __restrict__ e_out) {
     // rounds_done: per-query rounds whose z is already in the state; new_round = 1: one more round (rows rounds_done * n ..)
-    // is forward-substituted here from c_new.
+    // is forward-substituted here from c_new.  The kernel is a chain of dependent steps per query, so every step keeps
+    // many independent loads in flight (its time is L2 round trips, not bytes).
     extern __shared__ __align__(16) double bs_smem[];
     const int rounds = rounds_done + new_round;
     const int m = s + rounds * n;
     double* zs = bs_smem;                                   // [m] z
     double* ys = zs + m;                                    // [m] right-hand side, becomes y block by block
     double* tv = ys + m;                                    // [32]
-    int64_t* items = reinterpret_cast<int64_t*>(tv + CB);   // [m]
+    double* Ivs = tv + CB;                                  // [32 x 32] the sub-block's inverse
+    int64_t* items = reinterpret_cast<int64_t*>(Ivs + CB * CB);   // [m]
     const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int m_old = s + rounds_done * n;
     for (int i = tid; i < m; i += 256) {
@@ -369,22 +382,32 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
     if (new_round) {
         for (int k = 0; k < nsub; ++k) {
             const int rho = rounds_done * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
-            for (int i = ty; i < w; i += 8) {               // t_i = c_i - sum_{col < c0} L[row i][col] z[col]
-                const double* Lr = L + int64_t(rho + i) * ldl;
-                double p0 = 0.0, p1 = 0.0;
-                int col = tx;
-                for (; col + 32 < c0; col += 64) { p0 = fma(Lr[col], zs[col], p0); p1 = fma(Lr[col + 32], zs[col + 32], p1); }
-                if (col < c0) p0 = fma(Lr[col], zs[col], p0);
-                p0 += p1;
+            double iv[4];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                if (tx == 0) tv[i] = double(c_new[int64_t(b) * n + k * CB + i]) - p0;
+            for (int u = 0; u < 4; ++u) iv[u] = (tid + 256 * u) < w * CB ? Iq[int64_t(rho) * CB + tid + 256 * u] : 0.0;
+            // t_i = c_i - sum_{col < c0} L[row i][col] z[col]: a warp takes rows ty, ty + 8, ty + 16, ty + 24 together
+            double p[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* Lr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Lr[u] = L + int64_t(rho + (ty + 8 * u < w ? ty + 8 * u : 0)) * ldl;
+            for (int col = tx; col < c0; col += 32) {
+                const double zc = zs[col];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = fma(Lr[u][col], zc, p[u]);
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) p[u] += __shfl_xor_sync(0xffffffffu, p[u], o);
+                const int i = ty + 8 * u;
+                if (tx == 0 && i < w) tv[i] = double(c_new[int64_t(b) * n + k * CB + i]) - p[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Ivs[tid + 256 * u] = iv[u];
             __syncthreads();
             if (tid < w) {
-                const double* Iv = Iq + int64_t(rho) * CB;
                 double acc = 0.0;
-                for (int j = 0; j <= tid; ++j) acc = fma(Iv[tid * CB + j], tv[j], acc);
+                for (int j = 0; j <= tid; ++j) acc = fma(Ivs[tid * CB + j], tv[j], acc);
                 zs[c0 + tid] = acc;
                 z[int64_t(b) * bsz + c0 + tid] = acc;
             }
@@ -396,24 +419,41 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
     for (int rr = rounds - 1; rr >= 0; --rr) {
         for (int k = nsub - 1; k >= 0; --k) {
             const int rho = rr * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
-            const double* Iv = Iq + int64_t(rho) * CB;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Ivs[tid + 256 * u] = (tid + 256 * u) < w * CB ? Iq[int64_t(rho) * CB + tid + 256 * u] : 0.0;
+            __syncthreads();
             double yj = 0.0;
-            if (tid < w) {                                  // y_j = sum_{i >= j} Linv[i][j] rhs[i]
-                for (int i = tid; i < w; ++i) yj = fma(Iv[i * CB + tid], ys[c0 + i], yj);
-            }
+            if (tid < w)                                    // y_j = sum_{i >= j} Linv[i][j] rhs[i]
+                for (int i = tid; i < w; ++i) yj = fma(Ivs[i * CB + tid], ys[c0 + i], yj);
             __syncthreads();
             if (tid < w) ys[c0 + tid] = yj;
             __syncthreads();
-            const double* Lr = L + int64_t(rho) * ldl;      // rhs[col] -= sum_i L[row i of the block][col] y_i, col < c0
-            for (int col = tid; col < c0; col += 256) {
-                double a0 = 0.0, a1 = 0.0;
-                int i = 0;
-                for (; i + 1 < w; i += 2) {
-                    a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
-                    a1 = fma(Lr[int64_t(i + 1) * ldl + col], ys[c0 + i + 1], a1);
+            // rhs[col] -= sum_i L[row i of the block][col] y_i for col < c0: columns tid and tid + 256, eight rows at a time
+            const double* Lr = L + int64_t(rho) * ldl;
+            const int colA = tid, colB = tid + 256;
+            const bool okA = colA < c0, okB = colB < c0;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            for (int i = 0; i < w; i += 8) {
+                double va[8], vb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool in = i + u < w;
+                    va[u] = (okA && in) ? Lr[int64_t(i + u) * ldl + colA] : 0.0;
+                    vb[u] = (okB && in) ? Lr[int64_t(i + u) * ldl + colB] : 0.0;
                 }
-                if (i < w) a0 = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], a0);
-                ys[col] -= a0 + a1;
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const double y0 = i + u < w ? ys[c0 + i + u] : 0.0, y1 = i + u + 1 < w ? ys[c0 + i + u + 1] : 0.0;
+                    a0 = fma(va[u], y0, a0); a1 = fma(va[u + 1], y1, a1);
+                    b0 = fma(vb[u], y0, b0); b1 = fma(vb[u + 1], y1, b1);
+                }
+            }
+            if (okA) ys[colA] -= a0 + a1;
+            if (okB) ys[colB] -= b0 + b1;
+            for (int col = tid + 512; col < c0; col += 256) {     // m > 512 anchors: the plain loop
+                double acc = 0.0;
+                for (int i = 0; i < w; ++i) acc = fma(Lr[int64_t(i) * ldl + col], ys[c0 + i], acc);
+                ys[col] -= acc;
             }
             __syncthreads();
         }
@@ -421,30 +461,43 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
     if (s > 0) {                                            // the shared block: y_0 = L_1^-T rhs_0
         double yj = 0.0;
         if (tid < s) {
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int i = tid;
-            for (; i + 1 < s; i += 2) {
+            for (; i + 3 < s; i += 4) {
                 a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
                 a1 = fma(L1inv[int64_t(i + 1) * s + tid], ys[i + 1], a1);
+                a2 = fma(L1inv[int64_t(i + 2) * s + tid], ys[i + 2], a2);
+                a3 = fma(L1inv[int64_t(i + 3) * s + tid], ys[i + 3], a3);
             }
-            if (i < s) a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
-            yj = a0 + a1;
+            for (; i < s; ++i) a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
+            yj = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
         if (tid < s) ys[tid] = yj;
         __syncthreads();
     }
-    for (int t = tid; t < k_q; t += 256) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int i = 0;
-        for (; i + 3 < m; i += 4) {
-            const float v0 = __ldg(Rt + items[i] * k_q + t), v1 = __ldg(Rt + items[i + 1] * k_q + t);
-            const float v2 = __ldg(Rt + items[i + 2] * k_q + t), v3 = __ldg(Rt + items[i + 3] * k_q + t);
-            a0 = fma(ys[i], double(v0), a0); a1 = fma(ys[i + 1], double(v1), a1);
-            a2 = fma(ys[i + 2], double(v2), a2); a3 = fma(ys[i + 3], double(v3), a3);
+    // e = y^T M: columns t and t + 256 of the anchors' rows of R_anc^T, eight rows in flight
+    for (int t = tid; t < k_q; t += 512) {
+        const bool ok2 = t + 256 < k_q;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        for (int i = 0; i < m; i += 8) {
+            float va[8], vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = i + u < m;
+                const float* row = Rt + (in ? items[i + u] : 0) * k_q;
+                va[u] = in ? __ldg(row + t) : 0.f;
+                vb[u] = (in && ok2) ? __ldg(row + t + 256) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                const double y0 = i + u < m ? ys[i + u] : 0.0, y1 = i + u + 1 < m ? ys[i + u + 1] : 0.0;
+                a0 = fma(y0, double(va[u]), a0); a1 = fma(y1, double(va[u + 1]), a1);
+                b0 = fma(y0, double(vb[u]), b0); b1 = fma(y1, double(vb[u + 1]), b1);
+            }
         }
-        for (; i < m; ++i) a0 = fma(ys[i], double(__ldg(Rt + items[i] * k_q + t)), a0);
-        e_out[int64_t(b) * k_q + t] = float((a0 + a1) + (a2 + a3));
+        e_out[int64_t(b) * k_q + t] = float(a0 + a1);
+        if (ok2) e_out[int64_t(b) * k_q + t + 256] = float(b0 + b1);
     }
 }
 
@@ -557,7 +610,7 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
 static int backsolve_launch(const float* Rt, int k_q, const IncShared& sl, const char* sb, int s, const IncState& st, char* stb,
                             int n, int rounds_done, int new_round, const float* c_new, int n_queries, float* e_out, cudaStream_t stream) {
     const int m = s + (rounds_done + new_round) * n;
-    const size_t smem = sizeof(double) * (2 * size_t(m) + CB) + sizeof(int64_t) * size_t(m > 0 ? m : 1);
+    const size_t smem = sizeof(double) * (2 * size_t(m) + CB + CB * CB) + sizeof(int64_t) * size_t(m > 0 ? m : 1);
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(backsolve_e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     backsolve_e_kernel<<<n_queries, 256, smem, stream>>>(
         Rt, k_q, reinterpret_cast<const int64_t*>(sb + sl.off_anc), reinterpret_cast<const double*>(sb + sl.off_l1inv), s,
@@ -627,16 +680,27 @@ int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* share
         rc = dgemm_launch(g, true, n_queries, stream);
         if (rc != ANNCUR_OK) return rc;
     }
-    // c. the columns of the earlier per-query sub-blocks, in order: T_j -= X[:, 0:c0] L_j[:, 0:c0]^T, X_j = T_j L_jj^-T
+    // c. the columns of the earlier per-query rounds.  Per round block: everything to its left in ONE GEMM with full tiles
+    //    (T_blk -= X[:, 0:cb] L_blk[:, 0:cb]^T), then sub-block by sub-block the part inside the block (K = 32 k) and
+    //    X_k = T_k L_kk^-T.
     const int nsub = (n + CB - 1) / CB;
     for (int rr = 0; rr < r; ++rr) {
+        const int cb = s + rr * n;
+        if (cb > 0) {
+            DgArgs u{};
+            u.A = Lq + new_row0; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(rr) * n * st.ldl; u.ldb = st.ldl; u.bsB = st.bsLq;
+            u.Cin = T + cb; u.ldcin = st.ldl; u.bsCin = st.bsT; u.Cout = T + cb; u.ldc = st.ldl; u.bsC = st.bsT;
+            u.M = n; u.N = n; u.K = cb; u.sign = -1.0; u.diag_off = DG_ALL;
+            rc = dgemm_launch(u, false, n_queries, stream);
+            if (rc != ANNCUR_OK) return rc;
+        }
         for (int k = 0; k < nsub; ++k) {
             const int rho = rr * n + k * CB, w = n - k * CB < CB ? n - k * CB : CB, c0 = s + rho;
-            if (c0 > 0) {
+            if (k > 0) {
                 DgArgs u{};
-                u.A = Lq + new_row0; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(rho) * st.ldl; u.ldb = st.ldl; u.bsB = st.bsLq;
+                u.A = Lq + new_row0 + cb; u.lda = st.ldl; u.bsA = st.bsLq; u.B = Lq + int64_t(rho) * st.ldl + cb; u.ldb = st.ldl; u.bsB = st.bsLq;
                 u.Cin = T + c0; u.ldcin = st.ldl; u.bsCin = st.bsT; u.Cout = T + c0; u.ldc = st.ldl; u.bsC = st.bsT;
-                u.M = n; u.N = w; u.K = c0; u.sign = -1.0; u.diag_off = DG_ALL;
+                u.M = n; u.N = w; u.K = k * CB; u.sign = -1.0; u.diag_off = DG_ALL;
                 rc = dgemm_launch(u, false, n_queries, stream);
                 if (rc != ANNCUR_OK) return rc;
             }
