@@ -35,14 +35,16 @@ class AdaptiveIndex:
             self._shared[key] = engine.AdaptiveShared(self.Rt, first_anchors, rcond)
         return self._shared[key]
 
-    def topk(self, e, k):
+    def topk(self, e, k, n_rows_total=None):
         if self.sharded is not None:
+            if n_rows_total is not None:                       # e = this rank's block of query rows: the answer for the same rows
+                return self.sharded.search_owned(e, n_rows_total, k)
             return self.sharded.search(e, k)
         return engine.score_topk(e, self.packed, k)
 
 
 def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top_k, rcond=1e-15, *, rescore="fused",
-                    index=None, precision="f32r", solver="incremental"):
+                    index=None, precision="f32r", solver="incremental", n_rows_total=None):
     """Returns (anchors [B x T*k_per_round] int64 in selection order, idx [B x top_k] int64, exact scores [B x top_k]).
 
     ``rescore="fused"`` (default): per round one ``anncur_adaptive_solve`` (e_b for the whole batch), the fused tensor-core
@@ -52,7 +54,11 @@ def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top
     ``solver="incremental"`` (default, with the fused re-score): the per-query Cholesky factor is carried across rounds
     (``anncur_adaptive_begin`` / ``anncur_adaptive_extend``: a round pays for its NEW anchors only); ``solver="full"``: every
     round re-solves from scratch (``anncur_adaptive_solve``), also taken when a round adds more than
-    ANNCUR_ADAPTIVE_MAX_BLOCK anchors."""
+    ANNCUR_ADAPTIVE_MAX_BLOCK anchors.
+    ``n_rows_total`` (multi-GPU, with an item-sharded ``index``): ``exact_rows`` is THIS RANK'S block of a batch of
+    n_rows_total queries (``ShardedIndex.row_block``) -- the per-query solves are split over the ranks by query, the
+    re-score over the ranks by item, and one ``search_owned`` exchange per round (all-gather of the e blocks over NVLink,
+    local top-k per shard, candidates to the row's owner) brings every rank the candidates of its own queries."""
     R = engine._f32(R_anc)
     X = engine._f32(exact_rows, device=R.device)
     B = X.shape[0]
@@ -74,7 +80,7 @@ def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top
                 e = state.begin(torch.gather(X, 1, anchors)) if t == 0 else state.extend(nxt, torch.gather(X, 1, nxt))
             else:                                                                # K8a: per-query re-solve from scratch
                 e = engine.adaptive_solve(R, anchors, torch.gather(X, 1, anchors), rcond, Rt=index.Rt)
-            cv, ci = index.topk(e, k_per_round + m)                              # K3+K4 on the packed R_anc: the re-score
+            cv, ci = index.topk(e, k_per_round + m, n_rows_total)                # K3+K4 on the packed R_anc: the re-score
             _, nxt = engine.filter_excluded(cv, ci, anchors, k_per_round)        # the anchors leave the candidate lists
         else:
             c = torch.gather(X, 1, anchors)                                      # exact scores of the anchors so far

@@ -63,6 +63,11 @@ def _worker(rank, world, port, ret):
         a1, i1, v1 = adaptive_anncur(Ra, Xa, first, 4, 16, 10)
         a2, i2, v2 = adaptive_anncur(Ra, Xa, first, 4, 16, 10, index=AdaptiveIndex(Ra, sharded=ShardedIndex.from_full(Ra)))
         ok &= int(torch.equal(a1, a2) and torch.equal(i1, i2) and torch.equal(v1, v2))
+        # owned form: every rank solves ITS block of the queries, the re-score is item-sharded, search_owned per round
+        ixs = ShardedIndex.from_full(Ra)
+        q0, q1 = ixs.row_block(Xa.shape[0])
+        a3, i3, v3 = adaptive_anncur(Ra, Xa[q0:q1].contiguous(), first, 4, 16, 10, index=AdaptiveIndex(Ra, sharded=ixs), n_rows_total=Xa.shape[0])
+        ok &= int(torch.equal(a1[q0:q1], a3) and torch.equal(i1[q0:q1], i3) and torch.equal(v1[q0:q1], v3))
         out = torch.tensor([ok], device="cuda")
         dist.all_reduce(out, op=dist.ReduceOp.MIN)
         if rank == 0:
