@@ -19,11 +19,12 @@ class AdaptiveIndex:
     ``ShardedIndex`` over this rank's item slice: the re-score then runs on every rank's slice with one exchange per round
     (all ranks end with the same candidates, so the replicated solve stays in step)."""
 
-    def __init__(self, R_anc, precision="f32r", sharded=None):
+    def __init__(self, R_anc, precision="f32r", sharded=None, rank_budget=False):
         self.R = engine._f32(R_anc)
         self.k_q, self.N = self.R.shape
         self.Rt = engine.transpose(self.R)
         self.sharded = sharded
+        self.rank_budget = rank_budget                         # owned form: ship k/P + 6 sigma + 8 candidates per shard, certified (2 GPUs: no gain)
         self.packed = None if sharded is not None else engine.PackedItems(self.R, precision)
         self._shared = {}
 
@@ -38,7 +39,9 @@ class AdaptiveIndex:
     def topk(self, e, k, n_rows_total=None):
         if self.sharded is not None:
             if n_rows_total is not None:                       # e = this rank's block of query rows: the answer for the same rows
-                return self.sharded.search_owned(e, n_rows_total, k)
+                from .sharded import suggest_local_k
+                local_k = suggest_local_k(k, self.sharded.world_size) if self.rank_budget else None
+                return self.sharded.search_owned_verified(e, n_rows_total, k, local_k)
             return self.sharded.search(e, k)
         return engine.score_topk(e, self.packed, k)
 

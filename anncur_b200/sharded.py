@@ -333,6 +333,15 @@ class ShardedIndex:
             Q = torch.cat([allq[p * cap:p * cap + rows[p]] for p in range(self.world_size)], dim=0)
         return self.search_rowblock(Q, k, local_k)
 
+    def search_owned_verified(self, Q_block, n_rows_total, k, local_k=None):
+        """``search_owned`` with the rank-budgeted shortcut made safe (see ``search_rowblock_verified``): one small all-reduce
+        and a host read-back per call; a failed certificate anywhere recomputes the batch with local_k = k on every rank."""
+        out = self.search_owned(Q_block, n_rows_total, k, local_k)
+        if local_k is not None and local_k < k and self.exchange == "p2p" and self.world_size > 1:
+            if self.certificate_failures(reset=True) > 0:
+                out = self.search_owned(Q_block, n_rows_total, k, None)
+        return out
+
     def close(self):
         for ch in self._channels.values():
             ch.close()
