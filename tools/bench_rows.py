@@ -78,7 +78,7 @@ U = engine.pinv(C)
 t = gpu_ms(lambda: engine.pinv(C), warm=1, reps=3)
 Ch = C.cpu()
 emit("A1", f"U = pinv(C[{N_TRAIN}x{K_I}])  (fp64 normal equations: Gram + cooperative Cholesky + solves; Jacobi SVD fallback)", t, cpu_s(lambda: O.pinv_f32(Ch)), "full size, np.linalg.pinv",
-     bound="latency (tournament of column-pair rotations, ~10 sweeps x 499 rounds of small launches)")
+     bound="fp64 Gram + latency of the cooperative Cholesky panels (the Jacobi route, taken for rank-deficient / ill-conditioned inputs, is a tournament of column-pair rotations: 39 ms)")
 # A2 E = U R
 E = engine.gemm(U, R)
 t = gpu_ms(lambda: engine.gemm(U, R))
@@ -154,3 +154,15 @@ def cpu_adaptive():
 emit("A8", f"adaptive round: {Bq} queries x (pinv of {k_q}x{m} + re-score over {N} + top-125)  [not in the reference]", t,
      cpu_s(cpu_adaptive, reps=1) * (Bq / 4), "4 of 256 queries, numpy pinv per query (oracle restatement of SURVEY 8a-A8)",
      bound="fp64 Gram on the fp64 tensor cores + blocked fp64 Cholesky per query")
+
+# A8 whole procedure at BASELINE configs[2]: 4 rounds x 125 anchors, incremental solver + fused re-score
+from anncur_b200 import adaptive_anncur
+from anncur_b200.adaptive import AdaptiveIndex
+index = AdaptiveIndex(R_anc)
+first = torch.randperm(N, device=dev)[:125].sort().values
+t = gpu_ms(lambda: adaptive_anncur(R_anc, A_test, first, 4, 125, 100, index=index), warm=2, reps=3)
+An2 = A_test[:2].cpu().numpy()
+t_cpu = cpu_s(lambda: O.adaptive_anncur(Rn, An2, first.cpu().numpy(), 4, 125, 100), reps=1) * (B / 2)
+emit("A8", f"adaptive ANNCUR, whole procedure: {B} queries x 4 rounds x 125 anchors over {N} items (incremental fp64 solver + fused re-score)  [not in the reference]",
+     t, t_cpu, "2 of 4096 queries, oracle.adaptive_anncur (numpy fp64 pinv per query and round)",
+     queries_per_s=round(B / t * 1e3), bound="fp64 DMMA (Gram rows 28 %, block GEMMs 25 %), L2 round trips of the substitution kernel 17 %, re-score 18 %")
