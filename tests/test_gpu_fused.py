@@ -410,3 +410,62 @@ print("OK")
     env = dict(os.environ, ANNCUR_CTA_GROUP=group)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+# ---- randomised shapes: every kind against the oracle on shapes nobody picked by hand ---------------------------------------
+def _sweep_shapes(seed, n):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        B = int(rng.choice([1, 2, 5, 31, 64, 100, 129, 200, 257, 300]))
+        K = int(rng.integers(1, 260))
+        N = int(np.exp(rng.uniform(np.log(1), np.log(150_000))))
+        k = int(min(rng.choice([1, 2, 7, 10, 50, 100, 128, 129, 300, 700]), max(N + 3, 1)))     # k > N happens too (faiss padding)
+        out.append((B, K, N, k))
+    return out
+
+
+@pytest.mark.parametrize("kind,rel", [("f32r", 1e-5), ("f32x3", 1e-4)])
+def test_fused_random_shapes_match_oracle(eng, kind, rel):
+    """36 random (B, K, N, k) per kind, N from 1 to 150 000, on gaussian data and on a CUR-like low-rank index (scores with
+    a few dominant directions, as E = U R has); the same parity rules as everywhere else."""
+    for n, (B, K, N, k) in enumerate(_sweep_shapes(123 if kind == "f32r" else 321, 36)):
+        if n % 2 == 0:
+            Q, E = _rand((B, K), 1000 + n), _rand((K, N), 2000 + n)
+        else:
+            r = max(1, min(K, 8))
+            g = np.random.default_rng(3000 + n)
+            W = g.standard_normal((K, r), dtype=np.float32)
+            E = torch.from_numpy(W @ g.standard_normal((r, N), dtype=np.float32) / np.float32(np.sqrt(r)) + np.float32(0.05) * g.standard_normal((K, N), dtype=np.float32))
+            Q = torch.from_numpy(g.standard_normal((B, r), dtype=np.float32) @ W.T / np.float32(np.sqrt(r)) + np.float32(0.05) * g.standard_normal((B, K), dtype=np.float32))
+        try:
+            # tolerances are relative to the row's largest |score|: with a handful of items that "largest" can itself be a
+            # cancelled sum, so tiny item sets are held to north_star's 1e-4 instead of the kind's own 1e-5
+            _check(eng, Q, E, k, kind=kind, rel=rel if N >= 64 else 1e-4, offset=int(n % 3) * 1_000_003)
+        except AssertionError as exc:
+            raise AssertionError(f"shape B={B} K={K} N={N} k={k} (case {n}, {'gaussian' if n % 2 == 0 else 'low-rank'}): {exc}") from exc
+
+
+def test_fused_bf16_random_shapes_recall(eng):
+    """bf16 is reported as recall@k against the exact result (north_star): on random shapes the recall stays high, and the
+    returned values are the products of the bf16-ROUNDED operands accumulated in fp32 (error against those: fp32 summation
+    only, bounded per row by 1e-5 sum|q| max|e|; against the unrounded operands ~2^-8 of sqrt(K))."""
+    for n, (B, K, N, k) in enumerate(_sweep_shapes(77, 16)):
+        Q, E = _rand((B, K), 500 + n), _rand((K, N), 700 + n)
+        v, i = eng.score_topk(Q.cuda(), eng.PackedItems(E.cuda(), "bf16"), k)
+        v, i = v.cpu().numpy(), i.cpu().numpy()
+        dense = (Q.double() @ E.double()).numpy()
+        Qb, Eb = Q.bfloat16().double(), E.bfloat16().double()
+        dense_b = (Qb @ Eb).numpy()
+        kk = min(k, N)
+        ref = np.argsort(-dense, axis=1, kind="stable")[:, :kk]
+        recall = np.mean([len(set(i[r, :kk].tolist()) & set(ref[r].tolist())) / kk for r in range(B)])
+        assert recall > 0.9 or kk <= 2, (B, K, N, k, recall)
+        assert all(len(set(i[r, :kk].tolist())) == kk for r in range(B))
+        bound = 1e-5 * (Qb.abs().sum(1, keepdim=True) * Eb.abs().max()).numpy() + 1e-12
+        err = np.abs(v[:, :kk] - np.take_along_axis(dense_b, i[:, :kk], 1))
+        assert (err <= bound).all(), (B, K, N, k, float((err / bound).max()))
+        assert np.abs(v[:, :kk] - np.take_along_axis(dense, i[:, :kk], 1)).max() <= 2.0 ** -6 * np.sqrt(K) * 4, (B, K, N, k)
+        assert_sorted_desc(v[:, :kk])
+        if k > kk:
+            assert (i[:, kk:] == -1).all()
