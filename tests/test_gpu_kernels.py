@@ -569,3 +569,51 @@ def test_gemm_tc_and_recon_error_packed(eng):
         want_e2 = ((Q.double() @ E.cpu().double() - A.double()) ** 2).sum(1)
         want_n2 = (A.double() ** 2).sum(1)
         assert torch.allclose(e2.cpu(), want_e2, rtol=1e-4) and torch.allclose(n2.cpu(), want_n2, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- randomised eval-loop pieces
+def test_eval_loop_pieces_random_shapes_with_ties(eng):
+    """topk_rows, rerank_overlap and merge_topk on random shapes, half of them on INTEGER-valued scores (thousands of exact
+    ties): selection is bit-exact work, so values must be identical and, because the library breaks ties towards the lower
+    index, so must the indices (lexicographic order (-score, index) = a stable descending argsort)."""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        n = int(rng.choice([1, 3, 17, 40]))
+        N = int(np.exp(rng.uniform(np.log(2), np.log(120_000))))
+        k = int(min(rng.choice([1, 5, 10, 64, 100, 333, 1000]), N))
+        k_r = int(min(max(k, rng.choice([1, 10, 100, 500, 1000, 2000])), N))
+        if case % 2:
+            exact = rng.integers(-6, 7, size=(n, N)).astype(np.float32)
+            approx = exact + rng.integers(-2, 3, size=(n, N)).astype(np.float32)
+        else:
+            exact = rng.standard_normal((n, N)).astype(np.float32)
+            approx = exact + 0.3 * rng.standard_normal((n, N)).astype(np.float32)
+        order = np.lexsort((np.broadcast_to(np.arange(N), (n, N)), -exact.astype(np.float64)), axis=1)[:, :k]
+        v, i = eng.topk_rows(torch.from_numpy(exact).cuda(), k)
+        assert np.array_equal(i.cpu().numpy(), order), (case, n, N, k)
+        assert np.array_equal(v.cpu().numpy(), np.take_along_axis(exact, order, 1))
+        a_order = np.lexsort((np.broadcast_to(np.arange(N), (n, N)), -approx.astype(np.float64)), axis=1)[:, :k_r]
+        av, ai = eng.topk_rows(torch.from_numpy(approx).cuda(), k_r)
+        assert np.array_equal(ai.cpu().numpy(), a_order), (case, n, N, k_r)
+        # masked re-rank (..._w_fixed_train_test_splits.py:92-99): the k best retrieved items by EXACT score
+        got = np.take_along_axis(exact, a_order, 1)
+        rr = np.lexsort((a_order, -got.astype(np.float64)), axis=1)[:, :k]
+        want_i, want_v = np.take_along_axis(a_order, rr, 1), np.take_along_axis(got, rr, 1)
+        ks = sorted({1, min(10, k), k})
+        rr_i, rr_v, common = eng.rerank_overlap(torch.from_numpy(exact).cuda(), ai, i, ks)
+        assert np.array_equal(rr_v.cpu().numpy(), want_v) and np.array_equal(rr_i.cpu().numpy(), want_i), (case, n, N, k, k_r)
+        for j, kk in enumerate(ks):
+            want = [len(set(order[q, :kk].tolist()) & set(want_i[q, :kk].tolist())) for q in range(n)]
+            assert common[:, j].cpu().tolist() == want, (case, kk)
+        # shard merge: split the items into P shards, local top-k of each, merged = global top-k
+        P = int(rng.choice([2, 3, 8]))
+        bounds = [(p * N) // P for p in range(P + 1)]
+        if min(b1 - b0 for b0, b1 in zip(bounds[:-1], bounds[1:])) < 1:
+            continue
+        cv, ci = [], []
+        for p in range(P):
+            lv, li = eng.topk_rows(torch.from_numpy(np.ascontiguousarray(exact[:, bounds[p]:bounds[p + 1]])).cuda(), k, idx_offset=bounds[p])
+            cv.append(lv)
+            ci.append(li)
+        mv, mi = eng.merge_topk(torch.cat(cv, 1), torch.cat(ci, 1), k)
+        assert np.array_equal(mi.cpu().numpy(), order) and np.array_equal(mv.cpu().numpy(), np.take_along_axis(exact, order, 1)), (case, P)
