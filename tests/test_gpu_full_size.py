@@ -93,3 +93,39 @@ def test_c5_size_reconstruction_error_is_additive_over_item_shards(eng):
     A[:64] = Qm[:64] @ E
     e2, n2 = eng.recon_error_rows(Qm[:64], E, A[:64])
     assert float(torch.sqrt(e2.sum() / n2.sum())) < 1e-5
+
+
+def test_c3_size_adaptive_rounds_against_fp64_pinv(eng):
+    """BASELINE configs[2] at its own block sizes (k_q = 500 anchor queries, 4 rounds x 125 anchors, top-100) on N = 60 000
+    items, for a handful of queries the CPU can follow: every round's picks against the fp64 statement of that round on the
+    same anchor set (numpy pinv of the 500 x m matrix), exact outside the tie band tau = 1e-4 max|s|; and the batch answer
+    does not depend on which other queries share the batch (the solver's state is per query)."""
+    from anncur_b200 import adaptive_anncur
+    from anncur_b200.adaptive import AdaptiveIndex
+    from oracle import cur_oracle as O
+    k_q, N, B, T, kpr, top_k = 500, 60_000, 5, 4, 125, 100
+    A = O.synthetic_scores(k_q + 64, N, rank=64, noise=0.05, seed=21)
+    R, X = A[:k_q], A[k_q:]
+    first = np.sort(np.random.default_rng(3).choice(N, kpr, replace=False))
+    index = AdaptiveIndex(torch.from_numpy(R).cuda())
+    anc_all, idx_all, val_all = adaptive_anncur(torch.from_numpy(R).cuda(), torch.from_numpy(X).cuda(), first, T, kpr, top_k, index=index)
+    anc, idx, val = adaptive_anncur(torch.from_numpy(R).cuda(), torch.from_numpy(X[:B]).cuda(), first, T, kpr, top_k, index=index)
+    assert torch.equal(anc, anc_all[:B]) and torch.equal(idx, idx_all[:B]) and torch.equal(val, val_all[:B])
+    anc = anc.cpu().numpy()
+    R64 = R.astype(np.float64)
+    n_same = 0
+    for q in range(B):
+        for t in range(1, T):
+            cur, got = anc[q, :t * kpr], anc[q, t * kpr:(t + 1) * kpr]
+            e = X[q, cur].astype(np.float64) @ np.linalg.pinv(R64[:, cur])
+            sc = e @ R64
+            sc[cur] = -np.inf
+            order = np.argsort(-sc, kind="stable")
+            tau = 1e-4 * np.abs(sc[np.isfinite(sc)]).max()
+            assert len(set(got.tolist())) == kpr and not set(got.tolist()) & set(cur.tolist())
+            assert all(sc[j] >= sc[order[kpr - 1]] - tau for j in got), (q, t)
+            n_same += set(got.tolist()) == set(order[:kpr].tolist())
+    assert n_same >= 0.8 * B * (T - 1), n_same
+    exact_top = np.argsort(-X[:B].astype(np.float64), axis=1, kind="stable")[:, :top_k]
+    recall = np.mean([len(set(idx[q].cpu().tolist()) & set(exact_top[q].tolist())) / top_k for q in range(B)])
+    assert recall > 0.9, recall
