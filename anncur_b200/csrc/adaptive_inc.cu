@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, 2)
 dgemm_nt_kernel(const DgArgs p) {
     __shared__ __align__(16) double As[DG_T][DG_LD], Bs[DG_T][DG_LD];
     const int b = blockIdx.z;
-    const int i0 = blockIdx.y * DG_T, j0 = blockIdx.x * DG_T;
+    const int i0 = blockIdx.x * DG_T, j0 = blockIdx.y * DG_T;        // rows on grid.x: no 65535-tile limit on M
     if (int64_t(j0) > int64_t(i0) + DG_T - 1 + p.diag_off) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
@@ -168,7 +168,7 @@ dgemm_nt_kernel(const DgArgs p) {
 
 static int dgemm_launch(const DgArgs& a, bool gather, int batch, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return ANNCUR_OK;
-    dim3 grid(unsigned((a.N + DG_T - 1) / DG_T), unsigned((a.M + DG_T - 1) / DG_T), unsigned(batch));
+    dim3 grid(unsigned((a.M + DG_T - 1) / DG_T), unsigned((a.N + DG_T - 1) / DG_T), unsigned(batch));
     if (gather) dgemm_nt_kernel<true><<<grid, 256, 0, stream>>>(a);
     else dgemm_nt_kernel<false><<<grid, 256, 0, stream>>>(a);
     ANNCUR_LAUNCH_OK("dgemm_nt_kernel");
@@ -573,6 +573,7 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     if (shared_bytes < sl.total) { set_error("adaptive_prepare: shared blob too small: %zu < %zu", shared_bytes, sl.total); return ANNCUR_E_WORKSPACE; }
     if (s == 0) return ANNCUR_OK;
     if (workspace_bytes < adaptive_prepare_workspace_bytes(k_q, n_items, s)) { set_error("adaptive_prepare: workspace too small"); return ANNCUR_E_WORKSPACE; }
+    if (n_items >= (int64_t(1) << 31) - DG_T) { set_error("adaptive_prepare: n_items = %lld too large", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
     char* sb = reinterpret_cast<char*>(shared);
     int64_t* anc = reinterpret_cast<int64_t*>(sb + sl.off_anc);
     double* maxd = reinterpret_cast<double*>(sb + sl.off_maxd);
@@ -598,7 +599,6 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     DgArgs v{};
     v.Rt = Rt; v.ld_rt = k_q; v.idxA = nullptr; v.idxB = anc; v.bs_idxB = 0;
     v.Cout = V; v.ldc = s; v.bsC = 0; v.M = int(n_items); v.N = s; v.K = k_q; v.sign = 1.0; v.diag_off = DG_ALL; v.vec4 = vec4;
-    if (n_items > int64_t(65535) * DG_T) { set_error("adaptive_prepare: n_items = %lld too large", (long long)n_items); return ANNCUR_E_UNSUPPORTED; }
     rc = dgemm_launch(v, true, 1, stream);
     if (rc != ANNCUR_OK) return rc;
     DgArgs w{};

@@ -657,7 +657,9 @@ class AdaptiveState:
         dev = shared.Rt.device
         with torch.cuda.device(dev):
             nbytes = lib.anncur_adaptive_state_bytes(self.B, shared.k_q, shared.m_shared, self.n_new, self.m_max)
-            self.blob = WORKSPACE.get("adaptive_state", nbytes, dev)
+            # the state belongs to this object (two batches in flight on one stream must not share it); torch's caching
+            # allocator hands the block of the previous batch back without a cudaMalloc
+            self.blob = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
 
     def begin(self, c):
         lib, sh = _lib.load(), self.shared
