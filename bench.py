@@ -499,8 +499,11 @@ def run_c3(device, steps=3, B=4096, N=100_000, k_q=500, rounds=4, per_round=125,
     """BASELINE configs[2]: adaptive multi-round ANNCUR (NOT in the reference, parity unpinned): per query 4
     rounds of 125 anchor items chosen by re-solving e_q = c_q . pinv(R_anc[:, I_t]) and re-scoring all items; the exact-score
     matrix stands in for the cross-encoder calls and stays on the device.  A step = the whole procedure for one batch of B
-    queries.  world > 1: the queries' solves are split over the ranks by query block, the re-score by item shard, one
-    exchange per round (ShardedIndex.search_owned) -- strong scaling of the same batch."""
+    queries.  world > 1 (strong scaling of the same batch), two forms timed:
+      * queries split over the ranks by row block, every rank holds the whole R_anc (200 MB at this size) -- no collective on the
+        data path: the per-query solves are 4/5 of the work and queries are independent.  This is ``value``.
+      * the same split of the solves with the RE-SCORE item-sharded and one ShardedIndex.search_owned exchange per round (the form
+        SURVEY 8e words; it pays off when R_anc is too large to replicate) -- ``item_sharded_rescore``."""
     import torch
     import torch.distributed as dist
     from anncur_b200 import adaptive_anncur
@@ -513,49 +516,57 @@ def run_c3(device, steps=3, B=4096, N=100_000, k_q=500, rounds=4, per_round=125,
     R = torch.randn((k_q, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((k_q, N), generator=g, device=device)
     X = torch.randn((B, r), generator=g, device=device) @ Y.t() / math.sqrt(r) + NOISE * torch.randn((B, N), generator=g, device=device)
     first = torch.randperm(N, generator=g, device=device)[:per_round].sort().values
+    lo, hi = shard_bounds(B, world)[rank]
+    Xb = X[lo:hi] if world > 1 else X
+
+    def timed(index, total):
+        t0 = time.perf_counter()
+        adaptive_anncur(R, Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
+        torch.cuda.synchronize()
+        first_s = time.perf_counter() - t0            # includes anncur_adaptive_prepare (once per index + first anchors)
+        adaptive_anncur(R, Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0.record()
+        for _ in range(steps):
+            out = adaptive_anncur(R, Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, first_s, out
+
     t0 = time.perf_counter()
-    if world > 1:
-        lo, hi = shard_bounds(B, world)[rank]
-        index = AdaptiveIndex(R, sharded=ShardedIndex.from_full(R))
-        Xb, total = X[lo:hi], B
-    else:
-        index = AdaptiveIndex(R)                  # packed R_anc + its item-major copy: built once per index, outside the step
-        Xb, total = X, None
-    adaptive_anncur(R, Xb[:max(1, min(256, Xb.shape[0]))] if world == 1 else Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
+    index = AdaptiveIndex(R)                      # packed R_anc + its item-major copy: built once per index, outside the step
     torch.cuda.synchronize()
-    build_s = time.perf_counter() - t0            # packing, transposition, anncur_adaptive_prepare (first anchors) and the first call
-    adaptive_anncur(R, Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ev0.record()
-    for _ in range(steps):
-        anc, idx, val = adaptive_anncur(R, Xb, first, rounds, per_round, k, index=index, n_rows_total=total)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    build_s = time.perf_counter() - t0
+    ms, first_s, (anc, idx, val) = timed(index, None)
     n_chk = min(512, Xb.shape[0])
     exact = torch.topk(Xb[:n_chk], k, dim=1).indices
     recall = (idx[:n_chk].unsqueeze(2) == exact.unsqueeze(1)).any(2).float().mean().item()
     out = {"workload": f"c3: adaptive ANNCUR, N={N} items, k_q={k_q}, {rounds} rounds x {per_round} anchors, batch {B} queries/step, top-{k} by exact score",
            "value": B / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps, "ms_per_step": ms,
            "solver": "incremental (anncur_adaptive_begin / _extend: factor carried across rounds) + fused tensor-core re-score",
-           "index_build_and_first_call_s": build_s, "recall_at_k_vs_exact": recall,
+           "index_build_s": build_s, "first_call_s_incl_prepare": first_s, "recall_at_k_vs_exact": recall,
            "parity": "unpinned (no reference implementation; checked against our own CPU restatement)"}
     if world > 1:
-        out["parallelism"] = (f"queries' solves split over {world} ranks by row block, re-score item-sharded, one search_owned exchange "
-                              f"per round ({index.sharded.exchange}); strong scaling of one batch")
-        if rank == 0:                             # the sharded procedure must pick the single-GPU procedure's anchors
-            single = AdaptiveIndex(R)
-            anc1, idx1, _ = adaptive_anncur(R, Xb[:256], first, rounds, per_round, k, index=single)
-            out["anchors_equal_single_gpu_frac"] = float((anc[:256] == anc1).float().mean().item())
-            out["answer_equal_single_gpu_frac"] = float((idx[:256] == idx1).float().mean().item())
+        out["parallelism"] = (f"queries split over {world} ranks by row block ({hi - lo} per rank), R_anc replicated, no collective on the data path; "
+                              "strong scaling of one batch")
+        sharded = AdaptiveIndex(R, sharded=ShardedIndex.from_full(R))
+        ms2, _, (anc2, idx2, _) = timed(sharded, B)
+        out["item_sharded_rescore"] = {
+            "value": B / (ms2 * 1e-3), "ms_per_step": ms2,
+            "parallelism": f"solves split by query block, re-score item-sharded over {world} ranks, one search_owned exchange per round ({sharded.sharded.exchange})",
+            "anchors_equal_replicated_form_frac": float((anc2 == anc).float().mean().item()),
+            "answer_equal_replicated_form_frac": float((idx2 == idx).float().mean().item())}
+        sharded.sharded.close()
     else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         adaptive_anncur(R, X, first, rounds, per_round, k, index=index, solver="full")
         ev1.record()
