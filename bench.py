@@ -24,8 +24,9 @@ and asserts that the sharded answer equals the single-GPU answer on a row sample
 index, no collective (weak scaling; kept for comparison).
 
 ``value``  : device-resident throughput (queries already in HBM), CUDA events, max over ranks; N = 1 one stream in order, N > 1
-             two rotating streams (the exchange of batch j overlaps the kernels of batch j + 1; the in-order figure is printed
-             beside it as ``value_with_1_stream``).
+             one stream or two rotating streams (the exchange of batch j overlaps the kernels of batch j + 1), whichever an
+             untimed calibration pass finds faster on this box (``device_streams``); the other figure is printed beside it as
+             ``value_with_1_stream`` / ``value_with_2_streams``.
 ``e2e``    : the same through the host-facing call: N = 1 ``anncur_search_host`` (C ABI: pinned host Q -> H2D -> kernels ->
              D2H of values + indices every step); N > 1 ``ShardedIndex.search_owned``: every rank uploads ITS block of the
              batch, the blocks are all-gathered over NVLink, and every rank downloads the merged rows it owns.
@@ -628,7 +629,17 @@ def main():
     # N = 1: one stream, in order.  N > 1: the same steps issued over DEV_STREAMS rotating streams (each with its own exchange
     # channel), so that a rank waiting for the slowest sender of batch j already runs the kernels of batch j + 1 -- the GPUs of
     # a box drift apart by several % per step under their power caps, and an in-order loop pays the slowest rank every step.
-    dev_streams = DEV_STREAMS if index is not None else 1
+    # Whether that pays depends on the box (8 GPUs: +10 %; a 4-GPU box with a lower power cap: -12 %), so an untimed calibration
+    # pass picks 1 or DEV_STREAMS streams (max-over-ranks times, hence the same choice on every rank); the timed region below
+    # then runs exactly args.steps steps with that choice.
+    dev_streams, stream_calibration = 1, None
+    if index is not None:
+        n_cal = max(10, min(40, args.steps))
+        cal = {ns: h.time_device(n_cal, 3, streams=ns)[0] / n_cal for ns in (1, DEV_STREAMS)}
+        dev_streams = min(cal, key=cal.get)
+        stream_calibration = {f"ms_per_step_with_{ns}_stream{'s' if ns > 1 else ''}": v for ns, v in cal.items()}
+        if h.local_k is not None:
+            index.certificate_failures(reset=True)         # calibration rows are not part of the count reported below
     ms_total, clocks, fused_ms, fused_n, launches = h.time_device(args.steps, args.warmup, streams=dev_streams, sample_clocks=True, local_rank=local_rank)
     if index is not None and args.exchange == "p2p" and index.exchange != "p2p":
         args.exchange, h.local_k = "nccl", None           # peer memory was not available on this box: the line says what ran
@@ -843,6 +854,8 @@ def main():
 
     # ---- side measurements ---------------------------------------------------------------------------------
     line["device_streams"] = dev_streams
+    if stream_calibration is not None:
+        line["device_streams_calibration"] = stream_calibration
     if not args.no_extra:
         # the same steps over other stream counts (1 = strictly in order: every step pays the slowest rank of that step)
         for ns in [n for n in (1, 2, 3) if n != dev_streams]:
