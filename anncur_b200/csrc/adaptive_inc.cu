@@ -32,7 +32,7 @@ constexpr int DG_ALL = 1 << 29;                           // diag_off: "no trian
 
 struct DgArgs {
     // GATHER mode: row i of A = fp32 row idxA[i] of Rt (row length K, row stride ld_rt); idx == nullptr: row i itself
-    const float* Rt; int64_t ld_rt;
+    const float* Rt; int64_t ld_rt; int64_t n_rt;           // n_rt rows: an index outside [0, n_rt) reads as a zero row
     const int64_t* idxA; int64_t bs_idxA;
     const int64_t* idxB; int64_t bs_idxB;
     // fp64 mode
@@ -57,13 +57,15 @@ dgemm_nt_kernel(const DgArgs p) {
     const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
     const int fr = lane >> 2, fc = lane & 3;
     const int lrow = tid >> 2, lq = tid & 3;               // loader: one tile row of A and of B per thread, k = lq + 4u / 4lq + ..
-    const bool va = i0 + lrow < p.M, vb = j0 + lrow < p.N;
+    bool va = i0 + lrow < p.M, vb = j0 + lrow < p.N;
 
     const float* fa = nullptr; const float* fb = nullptr;
     const double* da = nullptr; const double* db = nullptr;
     if (GATHER) {
-        const int64_t ia = va ? (p.idxA ? p.idxA[int64_t(b) * p.bs_idxA + i0 + lrow] : int64_t(i0 + lrow)) : 0;
-        const int64_t ib = vb ? (p.idxB ? p.idxB[int64_t(b) * p.bs_idxB + j0 + lrow] : int64_t(j0 + lrow)) : 0;
+        int64_t ia = va ? (p.idxA ? p.idxA[int64_t(b) * p.bs_idxA + i0 + lrow] : int64_t(i0 + lrow)) : 0;
+        int64_t ib = vb ? (p.idxB ? p.idxB[int64_t(b) * p.bs_idxB + j0 + lrow] : int64_t(j0 + lrow)) : 0;
+        if (ia < 0 || ia >= p.n_rt) { va = false; ia = 0; }          // invalid anchor: a zero column (its pivot is dropped)
+        if (ib < 0 || ib >= p.n_rt) { vb = false; ib = 0; }
         fa = p.Rt + ia * p.ld_rt; fb = p.Rt + ib * p.ld_rt;
     } else {
         da = p.A + int64_t(b) * p.bsA + int64_t(va ? i0 + lrow : 0) * p.lda;
@@ -352,7 +354,7 @@ z_shared_kernel(const double* __restrict__ L1inv, int s, const double* __restric
 // The new anchors join the query's list, and the columns of their rows of L that belong to the shared anchors are gathered
 // from W_1^T (one warp per new anchor).
 __global__ void __launch_bounds__(256)
-append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_queries, int r_done,
+append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_queries, int r_done, int64_t n_items,
                       int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ W1t, int s,
                       double* __restrict__ Lq, int64_t bsLq, int ldl) {
     const int64_t w = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
@@ -360,9 +362,10 @@ append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_quer
     const int b = int(w / n), i = int(w % n);
     const int64_t item = new_anchors[w];
     if (lane_id() == 0) anc_q[int64_t(b) * bs_anc + int64_t(r_done) * n + i] = item;
-    const double* src = W1t + item * s;
+    const bool valid = item >= 0 && item < n_items;                  // invalid index (e.g. the -1 padding of a short list): zero row
+    const double* src = W1t + (valid ? item : 0) * s;
     double* dst = Lq + int64_t(b) * bsLq + (int64_t(r_done) * n + i) * ldl;
-    for (int t = lane_id(); t < s; t += 32) dst[t] = src[t];
+    for (int t = lane_id(); t < s; t += 32) dst[t] = valid ? src[t] : 0.0;
 }
 
 // Per query, after the round's rows of L are complete: the new blocks of z (forward substitution through the new rows, one
@@ -370,7 +373,7 @@ append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_quer
 // matrix-vector product), then e = (M y)^T.  Per-query rows come in rounds of n, each cut into sub-blocks of <= 32 columns
 // whose 32 x 32 inverses sit at Linvq + (local row) * 32; the shared block (s columns) has its s x s inverse L1inv.
 __global__ void __launch_bounds__(256)
-backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restrict__ shared_anc, const double* __restrict__ L1inv, int s,
+backsolve_e_kernel(const float* __restrict__ Rt, int k_q, int64_t n_items, const int64_t* __restrict__ shared_anc, const double* __restrict__ L1inv, int s,
                    const int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ Lq, int64_t bsLq, int ldl,
                    const double* __restrict__ Linvq, int64_t bsLinv, double* __restrict__ z, int64_t bsz, int n, int rounds_done,
                    int new_round, const float* __restrict__ c_new, float* __restrict__ e_out) {
@@ -389,7 +392,8 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
     const int m_old = s + rounds_done * n;
     for (int i = tid; i < m; i += 256) {
         zs[i] = i < m_old ? z[int64_t(b) * bsz + i] : 0.0;
-        items[i] = i < s ? shared_anc[i] : anc_q[int64_t(b) * bs_anc + (i - s)];
+        const int64_t it = i < s ? shared_anc[i] : anc_q[int64_t(b) * bs_anc + (i - s)];
+        items[i] = (it >= 0 && it < n_items) ? it : -1;                  // invalid anchors were zero columns: y_i = 0, row skipped
     }
     __syncthreads();
     const double* L = Lq + int64_t(b) * bsLq;
@@ -500,7 +504,7 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, const int64_t* __restr
             float va[8], vb[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const bool in = i + u < m;
+                const bool in = i + u < m && items[i + u] >= 0;
                 const float* row = Rt + (in ? items[i + u] : 0) * k_q;
                 va[u] = in ? __ldg(row + t) : 0.f;
                 vb[u] = (in && ok2) ? __ldg(row + t + 256) : 0.f;
@@ -601,7 +605,7 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     ANNCUR_CUDA_OK(cudaMemsetAsync(maxd, 0, sizeof(double), stream));
     const int vec4 = (k_q % 4 == 0) && (reinterpret_cast<uintptr_t>(Rt) % 16 == 0);
     DgArgs g{};
-    g.Rt = Rt; g.ld_rt = k_q; g.idxA = anc; g.bs_idxA = 0; g.idxB = anc; g.bs_idxB = 0;
+    g.Rt = Rt; g.ld_rt = k_q; g.n_rt = n_items; g.idxA = anc; g.bs_idxA = 0; g.idxB = anc; g.bs_idxB = 0;
     g.Cout = L1; g.ldc = s; g.bsC = 0; g.M = s; g.N = s; g.K = k_q; g.sign = 1.0; g.diag_off = 0; g.vec4 = vec4;
     rc = dgemm_launch(g, true, 1, stream);
     if (rc != ANNCUR_OK) return rc;
@@ -613,7 +617,7 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     ANNCUR_LAUNCH_OK("chol_inv_kernel");
     // V = R_anc^T M_1 (n_items x s), W_1^T = V L_1^-T
     DgArgs v{};
-    v.Rt = Rt; v.ld_rt = k_q; v.idxA = nullptr; v.idxB = anc; v.bs_idxB = 0;
+    v.Rt = Rt; v.ld_rt = k_q; v.n_rt = n_items; v.idxA = nullptr; v.idxB = anc; v.bs_idxB = 0;
     v.Cout = V; v.ldc = s; v.bsC = 0; v.M = int(n_items); v.N = s; v.K = k_q; v.sign = 1.0; v.diag_off = DG_ALL; v.vec4 = vec4;
     rc = dgemm_launch(v, true, 1, stream);
     if (rc != ANNCUR_OK) return rc;
@@ -623,13 +627,13 @@ int adaptive_prepare(const float* Rt, int k_q, int64_t n_items, const int64_t* s
     return dgemm_launch(w, false, 1, stream);
 }
 
-static int backsolve_launch(const float* Rt, int k_q, const IncShared& sl, const char* sb, int s, const IncState& st, char* stb,
+static int backsolve_launch(const float* Rt, int k_q, int64_t n_items, const IncShared& sl, const char* sb, int s, const IncState& st, char* stb,
                             int n, int rounds_done, int new_round, const float* c_new, int n_queries, float* e_out, cudaStream_t stream) {
     const int m = s + (rounds_done + new_round) * n;
     const size_t smem = sizeof(double) * (2 * size_t(m) + CB + CB * CB) + sizeof(int64_t) * size_t(m > 0 ? m : 1);
     ANNCUR_CUDA_OK(cudaFuncSetAttribute(backsolve_e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     backsolve_e_kernel<<<n_queries, 256, smem, stream>>>(
-        Rt, k_q, reinterpret_cast<const int64_t*>(sb + sl.off_anc), reinterpret_cast<const double*>(sb + sl.off_l1inv), s,
+        Rt, k_q, n_items, reinterpret_cast<const int64_t*>(sb + sl.off_anc), reinterpret_cast<const double*>(sb + sl.off_l1inv), s,
         reinterpret_cast<const int64_t*>(stb + st.off_anc), st.bs_anc, reinterpret_cast<const double*>(stb + st.off_lq), st.bsLq, st.ldl,
         reinterpret_cast<const double*>(stb + st.off_linv), st.bsLinv, reinterpret_cast<double*>(stb + st.off_z), st.bsz, n, rounds_done,
         new_round, c_new, e_out);
@@ -653,7 +657,7 @@ int adaptive_begin(const float* Rt, int k_q, int64_t n_items, const void* shared
         reinterpret_cast<double*>(stb + st.off_z), st.bsz, reinterpret_cast<double*>(stb + st.off_maxd));
     ANNCUR_LAUNCH_OK("z_shared_kernel");
     if (s == 0) { ANNCUR_CUDA_OK(cudaMemsetAsync(e_out, 0, sizeof(float) * size_t(n_queries) * k_q, stream)); return ANNCUR_OK; }
-    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n_new, 0, 0, nullptr, n_queries, e_out, stream);
+    return backsolve_launch(Rt, k_q, n_items, sl, sb, s, st, stb, n_new, 0, 0, nullptr, n_queries, e_out, stream);
 }
 
 // Round t + 1: every query gets n_new more anchors (m_cur = anchors so far = m_shared + r * n_new).
@@ -684,14 +688,14 @@ int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* share
     // a. anchors join the lists; shared columns of the new rows = gather from W_1^T
     {
         const int64_t warps = int64_t(n_queries) * n;
-        append_anchors_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, stream>>>(new_anchors, n, n_queries, r, anc_q, st.bs_anc, W1t, s,
+        append_anchors_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, stream>>>(new_anchors, n, n_queries, r, n_items, anc_q, st.bs_anc, W1t, s,
                                                                                     Lq, st.bsLq, st.ldl);
         ANNCUR_LAUNCH_OK("append_anchors_kernel");
     }
     // b. raw Gram rows of the new anchors against the per-query anchors (old, then new: lower triangle of the last block)
     {
         DgArgs g{};
-        g.Rt = Rt; g.ld_rt = k_q; g.idxA = anc_q + int64_t(r) * n; g.bs_idxA = st.bs_anc; g.idxB = anc_q; g.bs_idxB = st.bs_anc;
+        g.Rt = Rt; g.ld_rt = k_q; g.n_rt = n_items; g.idxA = anc_q + int64_t(r) * n; g.bs_idxA = st.bs_anc; g.idxB = anc_q; g.bs_idxB = st.bs_anc;
         g.Cout = T + s; g.ldc = st.ldl; g.bsC = st.bsT; g.M = n; g.N = (r + 1) * n; g.K = k_q; g.sign = 1.0; g.diag_off = r * n; g.vec4 = vec4;
         rc = dgemm_launch(g, true, n_queries, stream);
         if (rc != ANNCUR_OK) return rc;
@@ -761,7 +765,7 @@ int adaptive_extend(const float* Rt, int k_q, int64_t n_items, const void* share
         if (rc != ANNCUR_OK) return rc;
     }
     // f. new blocks of z, y = L^-T z, e = (M y)^T
-    return backsolve_launch(Rt, k_q, sl, sb, s, st, stb, n, r, 1, c_new, n_queries, e_out, stream);
+    return backsolve_launch(Rt, k_q, n_items, sl, sb, s, st, stb, n, r, 1, c_new, n_queries, e_out, stream);
 }
 
 }  // namespace anncur

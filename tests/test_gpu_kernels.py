@@ -378,6 +378,31 @@ def test_adaptive_incremental_solver_drops_dependent_anchors_like_the_full_solve
         assert np.allclose(e[q], want, atol=1e-4 * np.abs(want).max())
 
 
+def test_adaptive_incremental_solver_ignores_invalid_anchor_indices(eng):
+    """An index outside [0, N) among the new anchors (the -1 padding of a short candidate list) is a zero column: its pivot is
+    dropped and the solve equals the solve without it -- no out-of-range read."""
+    rng = np.random.default_rng(8)
+    k_q, N, B, s, n = 40, 500, 3, 6, 10
+    A = O.synthetic_scores(k_q + B, N, rank=8, noise=0.05, seed=19)
+    R, X = A[:k_q], A[k_q:]
+    Rt = eng.transpose(torch.from_numpy(R).cuda())
+    first = np.sort(rng.choice(N, s, replace=False))
+    rest = np.array([j for j in rng.permutation(N) if j not in set(first.tolist())])
+    new = np.stack([rest[q * n:(q + 1) * n] for q in range(B)]).astype(np.int64)
+    c_new = np.take_along_axis(X, new, 1)
+    new_bad = new.copy()
+    new_bad[0, 3], new_bad[2, 9], new_bad[2, 0] = -1, N + 7, -1
+    state = eng.AdaptiveState(eng.AdaptiveShared(Rt, torch.from_numpy(first), 1e-15), B, n, s + n)
+    state.begin(torch.from_numpy(X[:, first]).cuda())
+    e = state.extend(torch.from_numpy(new_bad).cuda(), torch.from_numpy(c_new).cuda()).cpu().numpy()
+    assert np.isfinite(e).all()
+    for q in range(B):
+        keep = [j for j in range(n) if 0 <= new_bad[q, j] < N]
+        cur = np.concatenate([first, new[q, keep]])
+        want = _np_pinv_e(R, cur, X[q, cur])
+        assert np.allclose(e[q], want, atol=2e-5 * np.abs(want).max()), q
+
+
 def test_adaptive_rounds_pick_exactly_outside_the_tie_band(eng):
     """Every round of the whole procedure (incremental solver + fused re-score + anchor filter) against the fp64 statement
     of that round ON THE SAME ANCHOR SET: each pick must score within tau = 1e-4 max|s| of the oracle's n-th best unmasked
