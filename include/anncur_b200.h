@@ -304,7 +304,8 @@ ANNCUR_API int anncur_filter_excluded(const float* cand_vals, const int64_t* can
  *   anncur_adaptive_extend  every later round: n_new more anchors per query (m_cur = anchors held before the call, =
  *                           m_shared + r n_new), their exact scores c_new, e_b for the grown set (n_queries x k_q fp32)
  * m_shared and n_new <= ANNCUR_ADAPTIVE_MAX_BLOCK, m_max = m_shared + (rounds) n_new <= k_q.  Same pivot rule as
- * anncur_adaptive_solve (pivots <= rcond^2 * largest Gram diagonal are dropped: that anchor's coordinate is 0). */
+ * anncur_adaptive_solve (pivots <= rcond^2 * largest Gram diagonal are dropped: that anchor's coordinate is 0).  An anchor
+ * index outside [0, n_items) -- the -1 padding of a short candidate list -- counts as a zero column (dropped the same way). */
 #define ANNCUR_ADAPTIVE_MAX_BLOCK 128
 ANNCUR_API size_t anncur_adaptive_shared_bytes(int k_q, int64_t n_items, int m_shared);
 ANNCUR_API size_t anncur_adaptive_prepare_workspace_bytes(int k_q, int64_t n_items, int m_shared);
