@@ -129,3 +129,35 @@ def test_c3_size_adaptive_rounds_against_fp64_pinv(eng):
     exact_top = np.argsort(-X[:B].astype(np.float64), axis=1, kind="stable")[:, :top_k]
     recall = np.mean([len(set(idx[q].cpu().tolist()) & set(exact_top[q].tolist())) / top_k for q in range(B)])
     assert recall > 0.9, recall
+
+
+@pytest.mark.parametrize("B,K,N,k,kind", [
+    (4225, 96, 20_000, 37, "f32r"),        # 34 query tiles: odd tile count for the CTA pairs, last tile holds one row
+    (8192, 500, 100_000, 100, "f32r"),     # two bench batches in one call
+    (5000, 1100, 30_000, 64, "f32r"),      # K > 1024
+    (4500, 300, 50_000, 200, "f32x3"),
+    (1, 500, 2_000_000, 100, "f32r"),      # one query, two million items (HBM-bound regime)
+    (6000, 64, 3_000, 1000, "f32r"),       # k_r = 1000 of a small item set: streamed from -inf
+])
+def test_large_batches_against_device_fp32_reference(eng, B, K, N, k, kind):
+    """Shapes the CPU oracle cannot follow in seconds, against torch's fp32 matmul (TF32 off) + topk on the device: returned
+    scores within the kind's tolerance of the dense scores of the returned items, every returned item a top-k item up to the
+    tie band 1e-4 max|s|, indices unique, best first."""
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    r = 24
+    W = torch.randn(K, r, device="cuda", generator=g)
+    E = W @ torch.randn(r, N, device="cuda", generator=g) / r ** 0.5 + 0.05 * torch.randn(K, N, device="cuda", generator=g)
+    Q = torch.randn(B, r, device="cuda", generator=g) @ W.t() / r ** 0.5 + 0.05 * torch.randn(B, K, device="cuda", generator=g)
+    v, i = eng.score_topk(Q, eng.PackedItems(E, kind), k)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for b0 in range(0, B, 2048):
+        dense = (Q[b0:b0 + 2048].double() @ E.double()) if K * N <= 40_000_000 else (Q[b0:b0 + 2048] @ E).double()
+        vv, ii = v[b0:b0 + 2048].double(), i[b0:b0 + 2048]
+        scale = dense.abs().amax(dim=1, keepdim=True)
+        got = torch.gather(dense, 1, ii)
+        assert float(((vv - got).abs() / scale).max()) <= (2e-5 if kind == "f32r" and K <= 700 else 1e-4)
+        kth = torch.topk(dense, k, dim=1).values[:, -1:]
+        assert bool((got >= kth - 1e-4 * scale).all())
+        assert bool((vv[:, :-1] >= vv[:, 1:]).all())
+        srt = torch.sort(ii, dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())
