@@ -123,9 +123,9 @@ __device__ __forceinline__ float rescore_long(const float* __restrict__ q, int k
 // Register budget 128: with less, ptxas sinks the 16 loads of a re-scoring batch down to their uses.
 template <int W> __device__ __forceinline__ void cta_sync() { if (W > 1) __syncthreads(); else __syncwarp(); }
 
-// CAP = candidates of one row held in shared memory (1024, or 4096 for large k)
+// CAP = candidates of one row held in shared memory (1024; 2048 / 4096 for large k)
 template <int U, int W, int CAP>
-__global__ void __launch_bounds__(W * 32, W == 1 ? (CAP > 1024 ? 6 : 16) : 4)
+__global__ void __launch_bounds__(W * 32, W == 1 ? (CAP > 2048 ? 6 : CAP > 1024 ? 11 : 16) : 4)
 refine_topk_kernel(const RefineParams p) {
     constexpr int kRefCap = CAP;
     extern __shared__ __align__(16) uint64_t ref_smem[];
@@ -332,7 +332,7 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
                          int64_t idx_offset, const float* Q, int ldq, int k_dim, const float* ET, int ld,
                          const float* row_inv_scale, float* out_vals, int64_t* out_idx, uint32_t* thr_shared,
                          uint32_t* mtile_flags, int m_tiles, int64_t n_items, int row_cap, cudaStream_t stream) {
-    if (row_cap != 1024 && row_cap != 4096) { set_error("refine_topk_keylists: row_cap %d is not 1024 or 4096", row_cap); return ANNCUR_E_INVALID; }
+    if (row_cap != 1024 && row_cap != 2048 && row_cap != 4096) { set_error("refine_topk_keylists: row_cap %d is not 1024, 2048 or 4096", row_cap); return ANNCUR_E_INVALID; }
     if (n_lists > kRefMaxLists) { set_error("refine_topk_keylists: %d lists per row > %d", n_lists, kRefMaxLists); return ANNCUR_E_UNSUPPORTED; }
     if (k > row_cap) { set_error("refine_topk_keylists: k = %d > %d", k, row_cap); return ANNCUR_E_UNSUPPORTED; }
     if (n_rows == 0) return ANNCUR_OK;
@@ -342,7 +342,6 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
                    row_inv_scale, out_vals, out_idx, thr_shared, mtile_flags, m_tiles};
     const bool wide = n_rows <= 4 * sm_count();               // few rows: 4 warps per row
     const int W = wide ? 4 : 1;
-    const bool big = row_cap > 1024;
     const size_t smem = (size_t(row_cap) + 2) * sizeof(uint64_t) + (256 + size_t(W) + 2 + size_t(row_cap) / 2 + size_t(n_lists) + 1) * sizeof(uint32_t);
     const int grid = n_rows < 32 * sm_count() ? n_rows : 32 * sm_count();
     const int ld4 = ld >> 2;
@@ -354,8 +353,8 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
     };
     auto pick = [&](auto u_tag) {
         constexpr int U = decltype(u_tag)::value;
-        if (wide) return big ? launch(refine_topk_kernel<U, 4, 4096>) : launch(refine_topk_kernel<U, 4, 1024>);
-        return big ? launch(refine_topk_kernel<U, 1, 4096>) : launch(refine_topk_kernel<U, 1, 1024>);
+        if (wide) return row_cap > 2048 ? launch(refine_topk_kernel<U, 4, 4096>) : row_cap > 1024 ? launch(refine_topk_kernel<U, 4, 2048>) : launch(refine_topk_kernel<U, 4, 1024>);
+        return row_cap > 2048 ? launch(refine_topk_kernel<U, 1, 4096>) : row_cap > 1024 ? launch(refine_topk_kernel<U, 1, 2048>) : launch(refine_topk_kernel<U, 1, 1024>);
     };
     if (ld4 <= 32) return pick(std::integral_constant<int, 1>{});
     if (ld4 <= 64) return pick(std::integral_constant<int, 2>{});

@@ -1624,10 +1624,10 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     // MAIN
     fp.mode = MODE_MAIN; fp.n_items = int(n_items); fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks;
     fp.close_compact = sampled ? 0 : 1;
-    // F32R keeps a row's candidates in shared memory while it re-scores them: 1024 (k up to ~200) or 4096 per row; past
+    // F32R keeps a row's candidates in shared memory while it re-scores them: 1024 (k up to ~200), 2048 or 4096 per row; past
     // that (cannot happen for k <= 1024) the call is served by the 3-pass launch
     const double expect_row = sampled ? 1.25 * pl.sample_rank * pl.sample_stride : 0.0;
-    const int row_cap = 1.8 * expect_row <= 1024.0 ? 1024 : 4096;
+    const int row_cap = 1.8 * expect_row <= 1024.0 ? 1024 : 1.8 * expect_row <= 2048.0 ? 2048 : 4096;
     // Re-scoring costs ~k x 2 KB of gathered reads per row (measured 1.9 us of kernel time per unit of k at B = 4096), the
     // two extra tensor passes ~4.6 ns per item: beyond k ~ N / 400 the 3-pass launch is the faster way to the same answer.
     if (refine && sampled && 1.5 * expect_row <= 4096.0 && int64_t(k) * 400 <= n_items) {

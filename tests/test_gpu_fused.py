@@ -69,6 +69,9 @@ def test_fused_f32x3_matches_oracle(eng, B, K, N, k):
     (20, 128, 60000, 500),
     (12, 64, 120000, 1000),     # k_r = 1000, the reference's largest retrieval size
     (260, 500, 100000, 1000),   # k_r = 1000 at the C2 index: sampled with the 2 j rule (stride 8), served by the 3-pass launch
+    (64, 200, 120000, 250),     # k = 250: the refine kernel holds 2048 candidates per row
+    (40, 128, 200000, 450),     # k = 450: 4096 candidates per row
+    (300, 96, 130000, 300),
 ])
 def test_fused_f32r_matches_oracle(eng, B, K, N, k):
     # plain fp32 dot products: 1e-5 of the row's max |score| up to K ~ 700; beyond, the fp32 summation error of ANY fp32
