@@ -1,0 +1,135 @@
+"""GPU: out-of-bounds WRITE detection without compute-sanitizer (closed on this pool, profiles/r2f_sanitizer_memcheck.log).
+
+Every output, workspace, packed index and solver state handed to the C ABI here is the interior of a larger allocation whose
+margins hold a byte pattern; after the call the margins must be untouched.  Buffers are sized exactly as the library's own
+*_bytes queries say, so a kernel that writes past its plan (a candidate list, a padded tile, a ragged tail) is caught."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PAD = 1 << 16           # bytes on either side
+PATTERN = 0xA5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from anncur_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+class Guarded:
+    """nbytes of device memory (256-byte aligned start) between two canary zones."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.full = torch.full((2 * PAD + self.nbytes + 256,), PATTERN, dtype=torch.uint8, device="cuda")
+        self.off = PAD + (-(self.full.data_ptr() + PAD)) % 256
+        self.bytes = self.full[self.off:self.off + self.nbytes]
+
+    def view(self, dtype, shape):
+        return self.bytes.view(dtype).view(shape)
+
+    def check(self, what):
+        torch.cuda.synchronize()
+        lo, hi = self.full[:self.off], self.full[self.off + self.nbytes:]
+        assert bool((lo == PATTERN).all()), f"{what}: write BEFORE the buffer"
+        assert bool((hi == PATTERN).all()), f"{what}: write PAST the buffer ({int((hi != PATTERN).sum())} bytes)"
+
+
+def _rand(shape, seed):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32)).cuda()
+
+
+@pytest.mark.parametrize("kind", ["f32r", "f32x3", "bf16"])
+@pytest.mark.parametrize("B,K,N,k", [(130, 70, 12345, 100), (1, 500, 70001, 100), (257, 64, 999, 37), (33, 129, 40000, 1000),
+                                     (4097, 500, 100003, 100)])
+def test_fused_search_stays_inside_its_buffers(eng, kind, B, K, N, k):
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    E, Q = _rand((K, N), 1), _rand((B, K), 2)
+    kd = eng.KINDS[kind]
+    g_pack = Guarded(lib.anncur_packed_items_bytes(N, K, kd))
+    scale = torch.ones(1, dtype=torch.float32, device="cuda")
+    _lib.check(lib.anncur_pack_items(eng._ptr(E), eng._ld(E), N, K, kd, eng._ptr(g_pack.bytes), eng._ptr(scale), eng._stream()))
+    g_pack.check(f"pack_items {kind}")
+    g_ws = Guarded(lib.anncur_score_topk_workspace_bytes(B, N, K, k, kd))
+    g_v, g_i = Guarded(4 * B * k), Guarded(8 * B * k)
+    for _ in range(2):                                       # twice: the second call starts from a used workspace
+        _lib.check(lib.anncur_score_topk(eng._ptr(Q), eng._ld(Q), B, eng._ptr(g_pack.bytes), eng._ptr(scale), N, K, kd, k, 0,
+                                         eng._ptr(g_v.bytes), eng._ptr(g_i.bytes), eng._ptr(g_ws.bytes), g_ws.nbytes, eng._stream()))
+    for g, what in ((g_ws, "workspace"), (g_v, "values"), (g_i, "indices"), (g_pack, "packed index")):
+        g.check(f"score_topk {kind} B={B} K={K} N={N} k={k}: {what}")
+    idx = g_i.view(torch.int64, (B, k))
+    kk = min(k, N)
+    assert int(idx[:, :kk].min()) >= 0 and int(idx[:, :kk].max()) < N
+    if kind != "bf16":                                       # dense epilogue on the same planes
+        g_d = Guarded(4 * B * N)
+        g_dws = Guarded(lib.anncur_score_dense_workspace_bytes(B, N, K, kd))
+        _lib.check(lib.anncur_score_dense(eng._ptr(Q), eng._ld(Q), B, eng._ptr(g_pack.bytes), eng._ptr(scale), N, K, kd,
+                                          eng._ptr(g_d.bytes), N, eng._ptr(g_dws.bytes), g_dws.nbytes, eng._stream()))
+        g_d.check("score_dense output")
+        g_dws.check("score_dense workspace")
+        ref = Q[: min(B, 64)].double() @ E.double()
+        got = g_d.view(torch.float32, (B, N))[: min(B, 64)].double()
+        assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+def test_adaptive_solver_stays_inside_its_state(eng):
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    k_q, N, B, s, n, rounds = 90, 3001, 37, 13, 29, 2       # ragged everything: sub-blocks of 29, odd leading dimensions
+    R, X = _rand((k_q, N), 3), _rand((B, N), 4)
+    Rt = eng.transpose(R)
+    rng = np.random.default_rng(5)
+    first = torch.from_numpy(np.sort(rng.choice(N, s, replace=False))).cuda()
+    g_sh = Guarded(lib.anncur_adaptive_shared_bytes(k_q, N, s))
+    g_pw = Guarded(lib.anncur_adaptive_prepare_workspace_bytes(k_q, N, s))
+    _lib.check(lib.anncur_adaptive_prepare(eng._ptr(Rt), k_q, N, eng._ptr(first), s, 1e-15, eng._ptr(g_sh.bytes), g_sh.nbytes,
+                                           eng._ptr(g_pw.bytes), g_pw.nbytes, eng._stream()))
+    g_sh.check("adaptive_prepare shared blob")
+    g_pw.check("adaptive_prepare workspace")
+    m_max = s + rounds * n
+    g_st = Guarded(lib.anncur_adaptive_state_bytes(B, k_q, s, n, m_max))
+    g_e = Guarded(4 * B * k_q)
+    c = torch.gather(X, 1, first.unsqueeze(0).expand(B, -1)).contiguous()
+    _lib.check(lib.anncur_adaptive_begin(eng._ptr(Rt), k_q, N, eng._ptr(g_sh.bytes), s, eng._ptr(c), B, n, m_max, eng._ptr(g_e.bytes),
+                                         eng._ptr(g_st.bytes), g_st.nbytes, eng._stream()))
+    m_cur = s
+    cur = first.unsqueeze(0).expand(B, -1)
+    for t in range(rounds):
+        new = torch.from_numpy(np.stack([rng.choice(N, n, replace=False) for _ in range(B)])).cuda()
+        c_new = torch.gather(X, 1, new).contiguous()
+        _lib.check(lib.anncur_adaptive_extend(eng._ptr(Rt), k_q, N, eng._ptr(g_sh.bytes), s, eng._ptr(new), eng._ptr(c_new), B, n, m_max,
+                                              m_cur, 1e-15, eng._ptr(g_e.bytes), eng._ptr(g_st.bytes), g_st.nbytes, eng._stream()))
+        m_cur += n
+        g_st.check(f"adaptive_extend round {t}: state")
+        g_e.check(f"adaptive_extend round {t}: e")
+        g_sh.check(f"adaptive_extend round {t}: shared blob")
+    assert bool(torch.isfinite(g_e.view(torch.float32, (B, k_q))).all())
+
+
+def test_filter_select_and_merge_stay_inside_their_outputs(eng):
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(6)
+    n, k_in, m, n_out = 301, 333, 77, 55
+    ci = torch.from_numpy(np.stack([rng.permutation(5000)[:k_in] for _ in range(n)])).cuda()
+    cv = torch.sort(torch.randn(n, k_in), dim=1, descending=True).values.cuda()
+    ex = torch.from_numpy(np.stack([rng.permutation(5000)[:m] for _ in range(n)])).cuda()
+    g_v, g_i = Guarded(4 * n * n_out), Guarded(8 * n * n_out)
+    _lib.check(lib.anncur_filter_excluded(eng._ptr(cv), eng._ptr(ci), n, k_in, eng._ptr(ex), m, n_out, eng._ptr(g_v.bytes), eng._ptr(g_i.bytes),
+                                          eng._stream()))
+    g_v.check("filter_excluded values")
+    g_i.check("filter_excluded indices")
+    S = _rand((19, 70001), 7)
+    for k in (1, 100, 2048):
+        g_v, g_i = Guarded(4 * 19 * k), Guarded(8 * 19 * k)
+        _lib.check(lib.anncur_topk_rows_f32(eng._ptr(S), eng._ld(S), 19, 70001, k, 0, eng._ptr(g_v.bytes), eng._ptr(g_i.bytes), eng._stream()))
+        g_v.check(f"topk_rows k={k} values")
+        g_i.check(f"topk_rows k={k} indices")
+        assert torch.equal(g_v.view(torch.float32, (19, k)), torch.topk(S, k, dim=1).values)
