@@ -133,3 +133,47 @@ def test_filter_select_and_merge_stay_inside_their_outputs(eng):
         g_v.check(f"topk_rows k={k} values")
         g_i.check(f"topk_rows k={k} indices")
         assert torch.equal(g_v.view(torch.float32, (19, k)), torch.topk(S, k, dim=1).values)
+
+
+@pytest.mark.parametrize("m,n", [(333, 97), (97, 333), (2000, 500), (64, 64)])
+def test_pinv_stays_inside_its_buffers(eng, m, n):
+    """Both pinv routes (normal equations chosen on the device, Jacobi forced through cond_out) and the FFMA GEMM."""
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    A = _rand((m, n), 11)
+    for want_cond in (False, True):
+        g_out, g_ws, g_cond = Guarded(4 * n * m), Guarded(lib.anncur_pinv_workspace_bytes(m, n)), Guarded(16)
+        _lib.check(lib.anncur_pinv_f32(eng._ptr(A), m, n, eng._ld(A), 1e-15, eng._ptr(g_out.bytes), m,
+                                       eng._ptr(g_cond.bytes) if want_cond else C.c_void_p(0), eng._ptr(g_ws.bytes), g_ws.nbytes, eng._stream()))
+        for g, what in ((g_out, "output"), (g_ws, "workspace"), (g_cond, "cond")):
+            g.check(f"pinv {m}x{n} (cond_out={want_cond}): {what}")
+        P = g_out.view(torch.float32, (n, m)).double()
+        assert float((A.double() @ P @ A.double() - A.double()).abs().max()) < 1e-3 * float(A.abs().max())
+    B = _rand((n, 131), 12)
+    g_c = Guarded(4 * m * 131)
+    _lib.check(lib.anncur_gemm_f32(eng._ptr(A), eng._ld(A), eng._ptr(B), eng._ld(B), eng._ptr(g_c.bytes), 131, m, 131, n, eng._stream()))
+    g_c.check("gemm_f32 output")
+
+
+def test_rerank_overlap_and_key_merge_stay_inside_their_outputs(eng):
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    n, N, k_r, k = 23, 7001, 777, 100
+    exact = _rand((n, N), 13)
+    _, retr = eng.topk_rows(exact + 0.3 * _rand((n, N), 14), k_r)
+    _, ex_i = eng.topk_rows(exact, k)
+    ks = (C.c_int * 3)(1, 10, 100)
+    g_i, g_v, g_c = Guarded(8 * n * k), Guarded(4 * n * k), Guarded(4 * n * 3)
+    _lib.check(lib.anncur_rerank_overlap(eng._ptr(exact), eng._ld(exact), n, N, eng._ptr(retr), k_r, eng._ptr(ex_i), k, ks, 3,
+                                         eng._ptr(g_i.bytes), eng._ptr(g_v.bytes), eng._ptr(g_c.bytes), eng._stream()))
+    for g, what in ((g_i, "indices"), (g_v, "values"), (g_c, "overlap counts")):
+        g.check(f"rerank_overlap: {what}")
+    P = 5
+    keys = torch.stack([eng.topk_to_keys(*eng.topk_rows(exact[:, p * 1400:(p + 1) * 1400].contiguous(), k, idx_offset=p * 1400)) for p in range(P)]).contiguous()
+    g_mv, g_mi, g_ws = Guarded(4 * n * k), Guarded(8 * n * k), Guarded(lib.anncur_merge_topk_keys_workspace_bytes(n))
+    _lib.check(lib.anncur_merge_topk_keys(eng._ptr(keys), P, n, k, k, eng._ptr(g_mv.bytes), eng._ptr(g_mi.bytes), eng._ptr(g_ws.bytes), g_ws.nbytes,
+                                          eng._stream()))
+    for g, what in ((g_mv, "values"), (g_mi, "indices"), (g_ws, "workspace")):
+        g.check(f"merge_topk_keys: {what}")
+    ref = torch.topk(exact[:, :7000], k, dim=1)
+    assert torch.equal(g_mv.view(torch.float32, (n, k)), ref.values)
