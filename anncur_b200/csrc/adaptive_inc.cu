@@ -11,10 +11,14 @@
 //     y   = L_t^-T z_t            e = (M y)^T
 //  * the columns of X that belong to the SHARED first anchors are a gather: X_a = W_1[:, new], W_1 = L_1^-1 M_1^T R_anc
 //    (m_1 x N, built once per index by anncur_adaptive_prepare);
-//  * the inverse of every n x n diagonal block is kept, so every other step is a batched fp64 GEMM C -= A B^T on the
-//    fp64 tensor cores (DMMA 8x8x4) -- one generic kernel, operands either fp64 panels or fp32 rows of R_anc^T gathered by
-//    item index -- plus ONE small per-query kernel (Cholesky + triangular inverse of the n x n Schur complement, n <= 128);
-//  * per query and round: 45 MFLOP in total instead of 241.
+//  * the n x n diagonal block is factorised right-looking in SUB-BLOCKS of <= 32 columns and the 32 x 32 inverse of every
+//    diagonal sub-block is kept, so every other step -- block substitution against earlier rounds, Schur complements,
+//    panel and trailing updates -- is a batched fp64 GEMM C -= A B^T on the fp64 tensor cores (DMMA 8x8x4): one generic
+//    kernel, operands either fp64 panels or fp32 rows of R_anc^T gathered by item index;
+//  * two small per-query kernels complete a round: a warp-level Cholesky + triangular inverse of a 32 x 32 sub-block
+//    (registers + shared-memory broadcasts), and the substitutions z, y and e = (M y)^T;
+//  * per query and round: 45 MFLOP in total instead of 241.  The CTA-per-query Cholesky + inverse of a whole block
+//    (chol_inv_kernel, n <= 128) is used once, for the shared anchors.
 // Pivots at or below rcond^2 * (largest Gram diagonal) are dropped exactly as in adaptive.cu (that anchor's coordinate of y
 // is 0): zero pivot, zero column of L, zero row and column of the block inverse.
 #include "common.cuh"
