@@ -910,6 +910,43 @@ def main():
                                           + ": torch.matmul + torch.topk fp32",
                                 "gpu_vs_cpu_check": {"index_agreement": same, "max_rel_score_err_sorted_lists": rel}}
         del E_host
+
+    # ---- the HBM-bound regime of the same index: small batches stream E once per call (north_star: "HBM GB/s ... for small-batch
+    #      streaming of E") -- device-resident, one stream, the MAIN launch timed by the library's own events ----------------
+    if world == 1 and not args.no_extra and args.precision in ("f32r", "bf16", "f32x3"):
+        try:
+            line["small_batch"] = []
+            hbm_peak = float(peaks.get("hbm_gbs", 0.0)) or None
+            plane_bytes = (4.0 if args.precision == "f32x3" else 2.0) * k_i * N          # what MAIN streams (algorithmic: unpadded k_i)
+            for b_small in (1, 64):
+                qs = [bt[:b_small].contiguous() for bt in batches[:2]]
+                ov = torch.empty((b_small, k), dtype=torch.float32, device=device)
+                oi = torch.empty((b_small, k), dtype=torch.int64, device=device)
+                for j in range(5):
+                    engine.score_topk(qs[j % 2], packed, k, idx_offset=lo, out=(ov, oi))
+                torch.cuda.synchronize()
+                engine.profile_enable(True)
+                engine.profile_read()
+                n_sb = 200
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for j in range(n_sb):
+                    engine.score_topk(qs[j % 2], packed, k, idx_offset=lo, out=(ov, oi))
+                e1.record()
+                torch.cuda.synchronize()
+                main_ms, main_n = engine.profile_read()
+                engine.profile_enable(False)
+                step_ms = e0.elapsed_time(e1) / n_sb
+                main_ms = main_ms / max(main_n, 1)
+                line["small_batch"].append({
+                    "batch": b_small, "value": b_small / (step_ms * 1e-3), "unit": "queries/s", "ms_per_step": step_ms,
+                    "main_kernel_ms": main_ms, "bound": "hbm", "algorithmic_bytes_main": plane_bytes,
+                    "hbm_gbs_main": plane_bytes / (main_ms * 1e-3) / 1e9, "hbm_gbs_step": plane_bytes / (step_ms * 1e-3) / 1e9,
+                    "hbm_gbs_peak": hbm_peak,
+                    "frac_main": (plane_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                    "frac_step": (plane_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None})
+        except Exception as exc:
+            line["small_batch"] = {"error": f"{type(exc).__name__}: {exc}"}
     h.close()
 
     # ---- the other BASELINE configs, device-resident figure only ---------------------------------------------
