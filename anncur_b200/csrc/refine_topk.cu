@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "warp_select.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace anncur {
@@ -125,7 +126,7 @@ template <int W> __device__ __forceinline__ void cta_sync() { if (W > 1) __synct
 
 // CAP = candidates of one row held in shared memory (1024; 2048 / 4096 for large k)
 template <int U, int W, int CAP>
-__global__ void __launch_bounds__(W * 32, W == 1 ? (CAP > 2048 ? 6 : CAP > 1024 ? 11 : 16) : 4)
+__global__ void __launch_bounds__(W * 32, W == 1 ? (CAP > 2048 ? 6 : CAP > 1024 ? 11 : 16) : W == 4 ? 4 : 2)
 refine_topk_kernel(const RefineParams p) {
     constexpr int kRefCap = CAP;
     extern __shared__ __align__(16) uint64_t ref_smem[];
@@ -341,7 +342,9 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
     RefineParams p{cand, counts, n_lists, cap, n_rows, k, n_sort, n_items, idx_offset, Q, ldq, k_dim, ET, ld,
                    row_inv_scale, out_vals, out_idx, thr_shared, mtile_flags, m_tiles};
     const bool wide = n_rows <= 4 * sm_count();               // few rows: 4 warps per row
-    const int W = wide ? 4 : 1;
+    static const int forced_w = [] { const char* e = getenv("ANNCUR_REFINE_WARPS"); return e ? atoi(e) : 0; }();
+    const bool wide8 = forced_w == 8 || (forced_w == 0 && n_rows <= sm_count());   // a row per SM at most: 8 warps per row
+    const int W = wide8 ? 8 : wide ? 4 : 1;
     const size_t smem = (size_t(row_cap) + 2) * sizeof(uint64_t) + (256 + size_t(W) + 2 + size_t(row_cap) / 2 + size_t(n_lists) + 1) * sizeof(uint32_t);
     const int grid = n_rows < 32 * sm_count() ? n_rows : 32 * sm_count();
     const int ld4 = ld >> 2;
@@ -353,6 +356,7 @@ int refine_topk_keylists(const uint64_t* cand, const uint32_t* counts, int n_lis
     };
     auto pick = [&](auto u_tag) {
         constexpr int U = decltype(u_tag)::value;
+        if (wide8) return row_cap > 2048 ? launch(refine_topk_kernel<U, 8, 4096>) : row_cap > 1024 ? launch(refine_topk_kernel<U, 8, 2048>) : launch(refine_topk_kernel<U, 8, 1024>);
         if (wide) return row_cap > 2048 ? launch(refine_topk_kernel<U, 4, 4096>) : row_cap > 1024 ? launch(refine_topk_kernel<U, 4, 2048>) : launch(refine_topk_kernel<U, 4, 1024>);
         return row_cap > 2048 ? launch(refine_topk_kernel<U, 1, 4096>) : row_cap > 1024 ? launch(refine_topk_kernel<U, 1, 2048>) : launch(refine_topk_kernel<U, 1, 1024>);
     };
