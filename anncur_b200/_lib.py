@@ -60,6 +60,8 @@ PROTOTYPES = {
     "anncur_adaptive_solve": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _sz, _vp]),
     "anncur_transpose_f32": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),
     "anncur_filter_excluded": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "anncur_score_topk_excluding_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i, _i]),
+    "anncur_score_topk_excluding": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "anncur_adaptive_shared_bytes": (_sz, [_i, _i64, _i]),
     "anncur_adaptive_prepare_workspace_bytes": (_sz, [_i, _i64, _i]),
     "anncur_adaptive_prepare": (_i, [_vp, _i, _i64, _vp, _i, _d, _vp, _sz, _vp, _sz, _vp]),

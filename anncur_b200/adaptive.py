@@ -83,8 +83,11 @@ def adaptive_anncur(R_anc, exact_rows, first_anchors, n_rounds, k_per_round, top
                 e = state.begin(torch.gather(X, 1, anchors)) if t == 0 else state.extend(nxt, torch.gather(X, 1, nxt))
             else:                                                                # K8a: per-query re-solve from scratch
                 e = engine.adaptive_solve(R, anchors, torch.gather(X, 1, anchors), rcond, Rt=index.Rt)
-            cv, ci = index.topk(e, k_per_round + m, n_rows_total)                # K3+K4 on the packed R_anc: the re-score
-            _, nxt = engine.filter_excluded(cv, ci, anchors, k_per_round)        # the anchors leave the candidate lists
+            if index.sharded is None:                                            # K3+K4 on the packed R_anc, anchors masked: one call
+                _, nxt = engine.score_topk_excluding(e, index.packed, k_per_round, anchors)
+            else:
+                cv, ci = index.topk(e, k_per_round + m, n_rows_total)            # sharded: the exchange carries k + m candidates
+                _, nxt = engine.filter_excluded(cv, ci, anchors, k_per_round)    # the anchors leave the candidate lists
         else:
             c = torch.gather(X, 1, anchors)                                      # exact scores of the anchors so far
             nxt, _ = engine.adaptive_round(R, anchors, c, k_per_round, rcond)    # K8: re-solve + masked re-score + pick

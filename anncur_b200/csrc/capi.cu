@@ -121,6 +121,40 @@ int anncur_score_topk(const float* Q, int ldq, int n_queries, const void* packed
                             out_idx, workspace, workspace_bytes, cudaStream_t(stream));
 }
 
+// Masked search ("optional mask / excluded-index list per row"): top-k of every row among the items NOT in the row's
+// excluded list.  Composition of the two kernels above it: the fused search for k + m_excl candidates (a row's m_excl excluded
+// items can displace at most m_excl of them) into the head of the workspace, then the order-keeping filter.
+static size_t excl_lists_bytes(int n_queries, int k_all) {
+    return align_up(sizeof(float) * size_t(n_queries) * k_all, 256) + align_up(sizeof(int64_t) * size_t(n_queries) * k_all, 256);
+}
+size_t anncur_score_topk_excluding_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int m_excl, int kind) {
+    if (n_queries <= 0 || k < 1 || m_excl < 0) return 256;
+    return excl_lists_bytes(n_queries, k + m_excl) + score_topk_workspace_bytes(n_queries, n_items, k_dim, k + m_excl, kind);
+}
+int anncur_score_topk_excluding(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                                int64_t n_items, int k_dim, int kind, int k, const int64_t* excluded, int m_excl,
+                                int64_t idx_offset, float* out_vals, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    ANNCUR_REQUIRE(n_queries >= 0 && n_items >= 0 && k_dim >= 0 && m_excl >= 0 && k >= 1, "score_topk_excluding: bad shape");
+    if (n_queries == 0) return ANNCUR_OK;
+    if (m_excl == 0)
+        return anncur_score_topk(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, k, idx_offset, out_vals, out_idx,
+                                 workspace, workspace_bytes, stream);
+    const int k_all = k + m_excl;
+    ANNCUR_REQUIRE(k_all <= ANNCUR_MAX_K_FUSED, "score_topk_excluding: k + m_excl = %d > %d", k_all, ANNCUR_MAX_K_FUSED);
+    ANNCUR_REQUIRE(out_vals && out_idx && excluded && workspace, "score_topk_excluding: null pointer");
+    const size_t head = excl_lists_bytes(n_queries, k_all);
+    ANNCUR_REQUIRE(workspace_bytes >= anncur_score_topk_excluding_workspace_bytes(n_queries, n_items, k_dim, k, m_excl, kind),
+                   "score_topk_excluding: workspace too small");
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* cand_v = reinterpret_cast<float*>(ws);
+    int64_t* cand_i = reinterpret_cast<int64_t*>(ws + align_up(sizeof(float) * size_t(n_queries) * k_all, 256));
+    int rc = anncur_score_topk(Q, ldq, n_queries, packed_items, e_scale, n_items, k_dim, kind, k_all, idx_offset, cand_v, cand_i,
+                               ws + head, workspace_bytes - head, stream);
+    if (rc != ANNCUR_OK) return rc;
+    return filter_excluded(cand_v, cand_i, n_queries, k_all, excluded, m_excl, k, out_vals, out_idx, cudaStream_t(stream));
+}
+
 size_t anncur_score_dense_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int kind) {
     return score_dense_workspace_bytes(n_queries, n_items, k_dim, kind);
 }

@@ -625,6 +625,27 @@ def filter_excluded(cand_vals, cand_idx, excluded, n_out):
     return vals, idx
 
 
+def score_topk_excluding(Q, packed, k, excluded, idx_offset=0):
+    """Top-k of every row among the items NOT in the row's ``excluded`` list (B x m int64, global indices) -- the masked
+    re-score of the adaptive rounds as one call (anncur_score_topk_excluding)."""
+    lib = _lib.load()
+    Q = _f32(Q, device=packed.device)
+    B = int(Q.shape[0])
+    excluded = excluded.to(device=Q.device, dtype=torch.int64).contiguous()
+    assert excluded.dim() == 2 and excluded.shape[0] == B
+    m = int(excluded.shape[1])
+    vals = torch.empty((B, k), dtype=torch.float32, device=Q.device)
+    idx = torch.empty((B, k), dtype=torch.int64, device=Q.device)
+    if B > 0:
+        with torch.cuda.device(Q.device):
+            nbytes = lib.anncur_score_topk_excluding_workspace_bytes(B, packed.n_items, packed.k_dim, int(k), m, packed.kind)
+            ws = WORKSPACE.get("score_topk_excluding", nbytes, Q.device)
+            _lib.check(lib.anncur_score_topk_excluding(_ptr(Q), _ld(Q), B, _ptr(packed.buf), _ptr(packed.scale), packed.n_items,
+                                                       packed.k_dim, packed.kind, int(k), _ptr(excluded), m, int(idx_offset),
+                                                       _ptr(vals), _ptr(idx), _ptr(ws), ws.numel(), _stream()))
+    return vals, idx
+
+
 class AdaptiveShared:
     """What anncur_adaptive_prepare builds once per (R_anc, shared first anchors): the Cholesky factor of the shared Gram
     matrix, its inverse and W_1^T (n_items x m_shared fp64) -- see include/anncur_b200.h."""

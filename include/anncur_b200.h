@@ -126,6 +126,17 @@ ANNCUR_API int anncur_score_topk(const float* Q, int ldq, int n_queries, const v
                       int64_t idx_offset, float* out_vals, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Masked search (the "excluded-index list per row" of the adaptive rounds): out[b] = the k best items of
+ * row b that are NOT among excluded[b][0 .. m_excl) (GLOBAL indices, i.e. including idx_offset; order free; entries < 0 are
+ * ignored), best first, padded with (-FLT_MAX, -1).  Exact: the fused search runs for k + m_excl candidates -- the excluded
+ * items of a row can displace at most m_excl of them -- and anncur_filter_excluded keeps the first k that survive.
+ * k + m_excl <= ANNCUR_MAX_K_FUSED. */
+ANNCUR_API size_t anncur_score_topk_excluding_workspace_bytes(int n_queries, int64_t n_items, int k_dim, int k, int m_excl, int kind);
+ANNCUR_API int anncur_score_topk_excluding(const float* Q, int ldq, int n_queries, const void* packed_items, const float* e_scale,
+                                int64_t n_items, int k_dim, int kind, int k, const int64_t* excluded, int m_excl,
+                                int64_t idx_offset, float* out_vals, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* ---- dense products on the tensor-core pipeline ---------------------------------------------------
  * out[B x N] = Q . E with the fp32-grade 3-pass arithmetic on a packed index of kind F32X3 or F32R: the tcgen05 form of
  * CURApprox.get_complete_row / get_rows / get (eval/matrix_approx_zeshel.py:71-119) and of the item-embedding build

@@ -472,3 +472,32 @@ def test_fused_bf16_random_shapes_recall(eng):
         assert_sorted_desc(v[:, :kk])
         if k > kk:
             assert (i[:, kk:] == -1).all()
+
+
+@pytest.mark.parametrize("B,K,N,k,m,kind", [(70, 64, 9000, 12, 24, "f32r"), (33, 200, 60000, 125, 375, "f32r"), (5, 40, 300, 100, 150, "f32r"),
+                                            (130, 96, 20000, 50, 1, "f32x3"), (9, 32, 5000, 10, 0, "f32r")])
+def test_masked_search_matches_oracle(eng, B, K, N, k, m, kind):
+    """anncur_score_topk_excluding: the k best items of a row that are not in the row's excluded list (the masked re-score of
+    the adaptive rounds) against the dense scores with the excluded items set to -inf."""
+    Q, E = _rand((B, K), 70 + B), _rand((K, N), 80 + k)
+    rng = np.random.default_rng(B + m)
+    dense = (Q.double() @ E.double()).numpy()
+    order = np.argsort(-dense, axis=1, kind="stable")
+    # half of the excluded items come from the row's own top (they would otherwise win), half are random; one padding entry
+    excl = np.zeros((B, 0), dtype=np.int64)
+    if m > 0:
+        excl = np.stack([np.concatenate([order[r, :m // 2], rng.choice(order[r, m // 2:], m - m // 2, replace=False)]) for r in range(B)]).astype(np.int64)
+    if m > 2:
+        excl[:, -1] = -1
+    v, i = eng.score_topk_excluding(Q.cuda(), eng.PackedItems(E.cuda(), kind), k, torch.from_numpy(excl))
+    v, i = v.cpu().numpy(), i.cpu().numpy()
+    masked = dense.copy()
+    for r in range(B):
+        masked[r, excl[r][excl[r] >= 0]] = -np.inf
+    ref = np.argsort(-masked, axis=1, kind="stable")[:, :k]
+    finite = np.where(np.isfinite(masked), masked, 0.0)
+    for r in range(B):
+        assert not set(i[r].tolist()) & set(excl[r][excl[r] >= 0].tolist())
+    assert_topk_sets_match(i, ref, full_scores=np.where(np.isfinite(masked), masked, -1e30), rel=1e-5 if kind == "f32r" else 1e-4)
+    assert_scores_close(v, np.take_along_axis(finite, i, 1), rel=1e-5 if kind == "f32r" else 1e-4)
+    assert_sorted_desc(v)
