@@ -177,3 +177,21 @@ def test_rerank_overlap_and_key_merge_stay_inside_their_outputs(eng):
         g.check(f"merge_topk_keys: {what}")
     ref = torch.topk(exact[:, :7000], k, dim=1)
     assert torch.equal(g_mv.view(torch.float32, (n, k)), ref.values)
+
+
+def test_masked_search_stays_inside_its_buffers(eng):
+    from anncur_b200 import _lib
+    lib = _lib.load()
+    B, K, N, k, m = 131, 70, 30001, 125, 375
+    E, Q = _rand((K, N), 21), _rand((B, K), 22)
+    packed = eng.PackedItems(E, "f32r")
+    excl = torch.from_numpy(np.stack([np.random.default_rng(r).choice(N, m, replace=False) for r in range(B)])).cuda()
+    g_ws = Guarded(lib.anncur_score_topk_excluding_workspace_bytes(B, N, K, k, m, packed.kind))
+    g_v, g_i = Guarded(4 * B * k), Guarded(8 * B * k)
+    _lib.check(lib.anncur_score_topk_excluding(eng._ptr(Q), eng._ld(Q), B, eng._ptr(packed.buf), eng._ptr(packed.scale), N, K, packed.kind, k,
+                                               eng._ptr(excl), m, 0, eng._ptr(g_v.bytes), eng._ptr(g_i.bytes), eng._ptr(g_ws.bytes), g_ws.nbytes,
+                                               eng._stream()))
+    for g, what in ((g_ws, "workspace"), (g_v, "values"), (g_i, "indices")):
+        g.check(f"score_topk_excluding: {what}")
+    idx = g_i.view(torch.int64, (B, k))
+    assert not bool((idx.unsqueeze(2) == excl.unsqueeze(1)).any())
