@@ -134,6 +134,7 @@ struct FusedParams {
                              // marked (top bit of its count) and the row goes to REDO
     int* error_flag;
     unsigned long long wait_timeout;   // mbarrier watchdog in SM cycles, 0 = off (see WAIT_TIMEOUT_CYCLES)
+    unsigned wait_sleep_ns;            // back-off between polls of the long waits (epilogue: accumulator ready; producer: stage free)
     // EPI_DENSE: out[row][col] = score; EPI_ERR: err2[row] += (score - exact[row][col])^2, norm2[row] += exact[row][col]^2
     const float* row_inv_scale;     // accumulator (scaled units) * row_inv_scale[row] = score
     float* dense_out;  int64_t ldo;
@@ -163,11 +164,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-struct WaitCtx { int* error_flag; unsigned long long timeout; };
+struct WaitCtx { int* error_flag; unsigned long long timeout; unsigned sleep_ns; };
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (w.timeout != 0ull && clock64() - t0 > w.timeout) {
+            if (w.error_flag) atomicExch(w.error_flag, 1);
+            __trap();
+        }
+    }
+}
+// The waits that are LONG by construction (the epilogue warps wait most of a tile's MMA time for the accumulator, the
+// producer for a free stage) can back off between polls (ANNCUR_WAIT_SLEEP_NS, default 0 = plain polling).  Measured as a way
+// to save power in the tensor-bound, power-capped MAIN kernel -- two thirds of its issued instructions are these polls --
+// and found neutral (20 / 100 / 400 ns: +-0.5 % at N = 1M and at C2, profiles/r2x_wait_sleep.txt): mbarrier.try_wait already
+// suspends the thread in hardware.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, const WaitCtx& w) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (w.sleep_ns != 0u) __nanosleep(w.sleep_ns);
         if (w.timeout != 0ull && clock64() - t0 > w.timeout) {
             if (w.error_flag) atomicExch(w.error_flag, 1);
             __trap();
@@ -357,7 +374,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
-    const WaitCtx wctx{p.error_flag, p.wait_timeout};
+    const WaitCtx wctx{p.error_flag, p.wait_timeout, p.wait_sleep_ns};
 
     // REDO launch without a flagged row (the normal case): nothing to do, leave before any TMEM / barrier set-up
     if (p.mtile_flags != nullptr && __ldg(p.mtile_flags + p.m_tiles) == 0u) return;
@@ -423,7 +440,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     const int item0 = tile * BLOCK_N + int(cta_rank) * (BLOCK_N / CG);     // this CTA's share of the item tile
                     for (int kb0 = 0; kb0 < p.num_kb; kb0 += Cfg::kKbPerStage) {
                         const int n_sub = p.num_kb - kb0 < Cfg::kKbPerStage ? p.num_kb - kb0 : Cfg::kKbPerStage;
-                        mbar_wait(empty_bar(stage), phase ^ 1u, wctx);
+                        mbar_wait_relaxed(empty_bar(stage), phase ^ 1u, wctx);
                         if (leader) mbar_expect_tx(full_bar(stage), uint32_t(CG * n_sub * Cfg::kSubBytes));
                         for (int u = 0; u < n_sub; ++u) {
                             const int kb = kb0 + u;
@@ -688,7 +705,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                     thr = INFINITY;
                     if (row_ok && overflow == 0u) thr = fmaxf(thr_own, ordered_to_float(__ldcg(p.thr_shared + row)));
                 }
-                mbar_wait(tfull_bar(buf), acc_phase, wctx);
+                mbar_wait_relaxed(tfull_bar(buf), acc_phase, wctx);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf) * BLOCK_N;
                 uint32_t ra[32], rb[32];
@@ -1272,6 +1289,10 @@ int binomial_tail_rank(int n, double p, double eps) {
 
 static int cta_group_for(int m_tiles);
 
+static unsigned wait_sleep_ns() {
+    static const unsigned v = [] { const char* e = getenv("ANNCUR_WAIT_SLEEP_NS"); return e ? unsigned(atoi(e)) : 0u; }();
+    return v;
+}
 static unsigned long long wait_timeout_cycles() {
     static unsigned long long v = [] {
         const char* e = getenv("ANNCUR_WAIT_TIMEOUT_CYCLES");
@@ -1595,6 +1616,7 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     fp.n_queries = n_queries; fp.num_kb = pl.num_kb; fp.k = k; fp.m_tiles = pl.m_tiles;
     fp.cand = cand; fp.counts = counts; fp.thr_shared = thr; fp.error_flag = err; fp.smax = smax; fp.n_smax = pl.n_smax;
     fp.wait_timeout = wait_timeout_cycles();
+    fp.wait_sleep_ns = wait_sleep_ns();
     // query high-plane variant of the last k-block (F32R only): +b at num_kb - 1, -b at num_kb, plain scores at num_kb + 1
     const int akb_upper = pl.num_kb - 1, akb_lower = refine ? pl.num_kb : pl.num_kb - 1, akb_plain = refine ? pl.num_kb + 1 : pl.num_kb - 1;
     fp.a_last_kb = akb_plain;
@@ -1737,6 +1759,7 @@ static int run_dense(int epi, int bound_sign, const float* Q, int ldq, int n_que
     fp.mode = MODE_MAIN; fp.n_queries = n_queries; fp.n_items = int(n_items); fp.num_kb = pl.num_kb; fp.k = 1;
     fp.m_tiles = pl.m_tiles; fp.n_tiles = pl.n_tiles; fp.n_chunks = pl.n_chunks; fp.error_flag = err;
     fp.wait_timeout = wait_timeout_cycles();
+    fp.wait_sleep_ns = wait_sleep_ns();
     fp.a_last_kb = kind == ANNCUR_KIND_F32R ? pl.num_kb + 1 : pl.num_kb - 1;     // plain scores: bound slot = 0
     fp.row_inv_scale = inv_scale; fp.dense_out = out; fp.ldo = ldo; fp.exact = exact; fp.lda = lda; fp.err2 = err2; fp.norm2 = norm2;
     fp.dense_vec_ok = (out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo & 3) == 0) ? 1 : 0;
