@@ -633,6 +633,12 @@ def main():
     # pass picks 1 or DEV_STREAMS streams (max-over-ranks times, hence the same choice on every rank); the timed region below
     # then runs exactly args.steps steps with that choice.
     dev_streams, stream_calibration = 1, None
+    settle_steps = 0
+    if index is None:
+        # the first loop after the index build runs through a power / clock transient of the capped GPU (observed: 1215 MHz
+        # in the first loop, 1320-1400 MHz in every later one); an untimed pass lets the clocks settle before W + K
+        settle_steps = max(10, min(100, args.steps))
+        h.time_device(settle_steps, 3, streams=1)
     if index is not None:
         n_cal = max(10, min(40, args.steps))
         cal = {ns: h.time_device(n_cal, 3, streams=ns)[0] / n_cal for ns in (1, DEV_STREAMS)}
@@ -854,6 +860,7 @@ def main():
 
     # ---- side measurements ---------------------------------------------------------------------------------
     line["device_streams"] = dev_streams
+    line["settle_steps_before_warmup"] = settle_steps
     if stream_calibration is not None:
         line["device_streams_calibration"] = stream_calibration
     if not args.no_extra:
