@@ -932,8 +932,13 @@ def main():
                 for j in range(5):
                     engine.score_topk(qs[j % 2], packed, k, idx_offset=lo, out=(ov, oi))
                 torch.cuda.synchronize()
-                engine.profile_enable(True)
-                engine.profile_read()
+                engine.profile_enable(True)                      # MAIN launch time from a short profiled pass (the library creates an
+                engine.profile_read()                            # event pair per launch while profiling: kept out of the timed loop)
+                for j in range(50):
+                    engine.score_topk(qs[j % 2], packed, k, idx_offset=lo, out=(ov, oi))
+                torch.cuda.synchronize()
+                main_ms, main_n = engine.profile_read()
+                engine.profile_enable(False)
                 n_sb = 200
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -941,8 +946,6 @@ def main():
                     engine.score_topk(qs[j % 2], packed, k, idx_offset=lo, out=(ov, oi))
                 e1.record()
                 torch.cuda.synchronize()
-                main_ms, main_n = engine.profile_read()
-                engine.profile_enable(False)
                 step_ms = e0.elapsed_time(e1) / n_sb
                 main_ms = main_ms / max(main_n, 1)
                 # the same call replayed as ONE CUDA graph (engine.GraphedSearch: no launch gaps between its seven kernels)
