@@ -1491,7 +1491,16 @@ static int launch_fused(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
     const int smem = Cfg::kStages * Cfg::kStageBytes + 1024 /*align slack*/ + 8 * (2 * Cfg::kStages + 4) + 16 + NUM_EPI_WARPS * 256 * 4 +
                      (EPI == EPI_DENSE ? NUM_EPI_WARPS * DENSE_TBUF_FLOATS * 4 : 0);
     auto kernel = fused_score_topk_kernel<PASSES, BF16, CPL, CG, EPI>;
-    ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    {   // once per instantiation and device (the value is a compile-time constant): a call issues three of these launches,
+        // and at small batches the host side of a call is what the GPU waits for between its short kernels
+        static bool attr_set[64] = {};
+        int dev = 0;
+        ANNCUR_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            ANNCUR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+    }
     // persistent: one CTA (pair) per SM (pair), never more CTAs than work items
     const long long units = 1ll * ((fp.m_tiles + CG - 1) / CG) * fp.n_chunks;
     const long long max_units = sm_count() / CG;
