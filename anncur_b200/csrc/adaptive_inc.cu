@@ -50,33 +50,39 @@ struct DgArgs {
     int vec4;                                              // GATHER: rows are 16-byte aligned and K % 4 == 0
 };
 
-template <bool GATHER>
-__global__ void __launch_bounds__(256, 2)
+// TN = 64: 256 threads, 8 warps (2 x 4).  TN = 32 (fp64 operands only): the narrow launches of the block algorithms (N <= 32:
+// a 32-wide sub-block) on 64 x 32 tiles with 128 threads, 4 warps (2 x 2) -- no half-empty tile, twice the CTAs per SM.
+template <bool GATHER, int TN>
+__global__ void __launch_bounds__(TN == 64 ? 256 : 128, TN == 64 ? 2 : 4)
 dgemm_nt_kernel(const DgArgs p) {
-    __shared__ __align__(16) double As[DG_T][DG_LD], Bs[DG_T][DG_LD];
+    static_assert(TN == 64 || (TN == 32 && !GATHER), "tile width");
+    constexpr int NT = TN == 64 ? 256 : 128;               // threads
+    constexpr int TA = NT / DG_T, KA = DG_K / TA;          // loader threads per row of A, k values per thread (8 or 16)
+    __shared__ __align__(16) double As[DG_T][DG_LD], Bs[TN][DG_LD];
     const int b = blockIdx.z;
-    const int i0 = blockIdx.x * DG_T, j0 = blockIdx.y * DG_T;        // rows on grid.x: no 65535-tile limit on M
+    const int i0 = blockIdx.x * DG_T, j0 = blockIdx.y * TN;          // rows on grid.x: no 65535-tile limit on M
     if (int64_t(j0) > int64_t(i0) + DG_T - 1 + p.diag_off) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
+    const int wr = TN == 64 ? (warp >> 2) * 32 : (warp >> 1) * 32, wc = TN == 64 ? (warp & 3) * 16 : (warp & 1) * 16;
     const int fr = lane >> 2, fc = lane & 3;
-    const int lrow = tid >> 2, lq = tid & 3;               // loader: one tile row of A and of B per thread, k = lq + 4u / 4lq + ..
-    bool va = i0 + lrow < p.M, vb = j0 + lrow < p.N;
+    const int lrow = tid / TA, lq = tid % TA;              // loader, A: tile row lrow, k = lq + TA u
+    const int lrowb = tid >> 2, lqb = tid & 3;             // loader, B: tile row lrowb (< TN), k = lqb + 4 u
+    bool va = i0 + lrow < p.M, vb = j0 + lrowb < p.N;
 
     const float* fa = nullptr; const float* fb = nullptr;
     const double* da = nullptr; const double* db = nullptr;
     if (GATHER) {
         int64_t ia = va ? (p.idxA ? p.idxA[int64_t(b) * p.bs_idxA + i0 + lrow] : int64_t(i0 + lrow)) : 0;
-        int64_t ib = vb ? (p.idxB ? p.idxB[int64_t(b) * p.bs_idxB + j0 + lrow] : int64_t(j0 + lrow)) : 0;
+        int64_t ib = vb ? (p.idxB ? p.idxB[int64_t(b) * p.bs_idxB + j0 + lrowb] : int64_t(j0 + lrowb)) : 0;
         if (ia < 0 || ia >= p.n_rt) { va = false; ia = 0; }          // invalid anchor: a zero column (its pivot is dropped)
         if (ib < 0 || ib >= p.n_rt) { vb = false; ib = 0; }
         fa = p.Rt + ia * p.ld_rt; fb = p.Rt + ib * p.ld_rt;
     } else {
         da = p.A + int64_t(b) * p.bsA + int64_t(va ? i0 + lrow : 0) * p.lda;
-        db = p.B + int64_t(b) * p.bsB + int64_t(vb ? j0 + lrow : 0) * p.ldb;
+        db = p.B + int64_t(b) * p.bsB + int64_t(vb ? j0 + lrowb : 0) * p.ldb;
     }
     float4 ga[2], gb[2];                                   // GATHER stage registers: k = 4 lq + {0, 16} .. +3
-    double ra[8], rb[8];                                   // fp64 stage registers:   k = lq + 4 u
+    double ra[KA], rb[8];                                  // fp64 stage registers:   k = lq + TA u (A), lqb + 4 u (B)
     auto load_stage = [&](int k0) {
         if (GATHER) {
 #pragma unroll
@@ -96,9 +102,13 @@ dgemm_nt_kernel(const DgArgs p) {
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = k0 + lq + 4 * u;
+            for (int u = 0; u < KA; ++u) {
+                const int k = k0 + lq + TA * u;
                 ra[u] = (va && k < p.K) ? da[k] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + lqb + 4 * u;
                 rb[u] = (vb && k < p.K) ? db[k] : 0.0;
             }
         }
@@ -114,7 +124,9 @@ dgemm_nt_kernel(const DgArgs p) {
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { As[lrow][lq + 4 * u] = ra[u]; Bs[lrow][lq + 4 * u] = rb[u]; }
+            for (int u = 0; u < KA; ++u) As[lrow][lq + TA * u] = ra[u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Bs[lrowb][lqb + 4 * u] = rb[u];
         }
     };
 
@@ -174,9 +186,12 @@ dgemm_nt_kernel(const DgArgs p) {
 
 static int dgemm_launch(const DgArgs& a, bool gather, int batch, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return ANNCUR_OK;
-    dim3 grid(unsigned((a.M + DG_T - 1) / DG_T), unsigned((a.N + DG_T - 1) / DG_T), unsigned(batch));
-    if (gather) dgemm_nt_kernel<true><<<grid, 256, 0, stream>>>(a);
-    else dgemm_nt_kernel<false><<<grid, 256, 0, stream>>>(a);
+    const bool narrow = !gather && a.N <= 32;
+    const int tn = narrow ? 32 : DG_T;
+    dim3 grid(unsigned((a.M + DG_T - 1) / DG_T), unsigned((a.N + tn - 1) / tn), unsigned(batch));
+    if (gather) dgemm_nt_kernel<true, 64><<<grid, 256, 0, stream>>>(a);
+    else if (narrow) dgemm_nt_kernel<false, 32><<<grid, 128, 0, stream>>>(a);
+    else dgemm_nt_kernel<false, 64><<<grid, 256, 0, stream>>>(a);
     ANNCUR_LAUNCH_OK("dgemm_nt_kernel");
     return ANNCUR_OK;
 }
