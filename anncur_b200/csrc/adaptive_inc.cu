@@ -429,11 +429,20 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, int64_t n_items, const
             const double* Lr[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) Lr[u] = L + int64_t(rho + (ty + 8 * u < w ? ty + 8 * u : 0)) * ldl;
-            for (int col = tx; col < c0; col += 32) {
+            double p2[4] = {0.0, 0.0, 0.0, 0.0};
+            int col = tx;
+            for (; col + 32 < c0; col += 64) {              // eight loads in flight per lane
+                const double zc = zs[col], zd = zs[col + 32];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { p[u] = fma(Lr[u][col], zc, p[u]); p2[u] = fma(Lr[u][col + 32], zd, p2[u]); }
+            }
+            if (col < c0) {
                 const double zc = zs[col];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) p[u] = fma(Lr[u][col], zc, p[u]);
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] += p2[u];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -515,7 +524,30 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, int64_t n_items, const
         if (tid < s) ys[tid] = yj;
         __syncthreads();
     }
-    // e = y^T M: columns t and t + 256 of the anchors' rows of R_anc^T, eight rows in flight
+    // e = y^T M.  k_q even and 8-byte aligned rows: one 64-bit load per row brings columns 2t, 2t + 1, sixteen rows in flight
+    // (the loop is a chain of L2 / DRAM round trips: 24 instead of 47 at m = 375); otherwise columns t and t + 256, eight rows.
+    if ((k_q & 1) == 0 && (reinterpret_cast<uintptr_t>(Rt) & 7) == 0) {
+        for (int t = tid; 2 * t < k_q; t += 256) {
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            for (int i = 0; i < m; i += 16) {
+                float2 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const bool in = i + u < m && items[i + u] >= 0;
+                    const float2* row = reinterpret_cast<const float2*>(Rt + (in ? items[i + u] : 0) * k_q);
+                    v[u] = in ? __ldg(row + t) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u += 2) {
+                    const double y0 = i + u < m ? ys[i + u] : 0.0, y1 = i + u + 1 < m ? ys[i + u + 1] : 0.0;
+                    a0 = fma(y0, double(v[u].x), a0); a1 = fma(y1, double(v[u + 1].x), a1);
+                    b0 = fma(y0, double(v[u].y), b0); b1 = fma(y1, double(v[u + 1].y), b1);
+                }
+            }
+            *reinterpret_cast<float2*>(e_out + int64_t(b) * k_q + 2 * t) = make_float2(float(a0 + a1), float(b0 + b1));
+        }
+        return;
+    }
     for (int t = tid; t < k_q; t += 512) {
         const bool ok2 = t + 256 < k_q;
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
