@@ -511,13 +511,26 @@ backsolve_e_kernel(const float* __restrict__ Rt, int k_q, int64_t n_items, const
         if (tid < s) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int i = tid;
-            for (; i + 3 < s; i += 4) {
-                a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
-                a1 = fma(L1inv[int64_t(i + 1) * s + tid], ys[i + 1], a1);
-                a2 = fma(L1inv[int64_t(i + 2) * s + tid], ys[i + 2], a2);
-                a3 = fma(L1inv[int64_t(i + 3) * s + tid], ys[i + 3], a3);
+            for (; i + 15 < s; i += 16) {                   // sixteen loads in flight
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldg(L1inv + int64_t(i + u) * s + tid);
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 = fma(v[u], ys[i + u], a0); a1 = fma(v[u + 1], ys[i + u + 1], a1);
+                    a2 = fma(v[u + 2], ys[i + u + 2], a2); a3 = fma(v[u + 3], ys[i + u + 3], a3);
+                }
             }
-            for (; i < s; ++i) a0 = fma(L1inv[int64_t(i) * s + tid], ys[i], a0);
+            {                                               // tail: up to 15 rows, predicated, all loads issued together
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = i + u < s ? __ldg(L1inv + int64_t(i + u) * s + tid) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 = fma(v[u], i + u < s ? ys[i + u] : 0.0, a0); a1 = fma(v[u + 1], i + u + 1 < s ? ys[i + u + 1] : 0.0, a1);
+                    a2 = fma(v[u + 2], i + u + 2 < s ? ys[i + u + 2] : 0.0, a2); a3 = fma(v[u + 3], i + u + 3 < s ? ys[i + u + 3] : 0.0, a3);
+                }
+            }
             yj = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
