@@ -1661,7 +1661,11 @@ int score_topk_fused(const float* Q, int ldq, int n_queries, const void* packed_
     const int row_cap = 1.8 * expect_row <= 1024.0 ? 1024 : 1.8 * expect_row <= 2048.0 ? 2048 : 4096;
     // Re-scoring costs ~k x 2 KB of gathered reads per row (measured 1.9 us of kernel time per unit of k at B = 4096), the
     // two extra tensor passes ~4.6 ns per item: beyond k ~ N / 400 the 3-pass launch is the faster way to the same answer.
-    if (refine && sampled && 1.5 * expect_row <= 4096.0 && int64_t(k) * 400 <= n_items) {
+    // (ANNCUR_F32R_K_RATIO overrides the 400 for experiments.  Measured with the 2048 / 4096-candidate refine variants at
+    // N = 100k, B = 4096: ratio 250 serves k = 375 by filter + refine in 0.97 instead of 1.02 ms, ratio 190 serves k = 500 in 1.10
+    // instead of 1.01 ms -- the crossover stays where it was.)
+    static const int64_t k_ratio = [] { const char* e = getenv("ANNCUR_F32R_K_RATIO"); return e ? int64_t(atoi(e)) : int64_t(400); }();
+    if (refine && sampled && 1.5 * expect_row <= 4096.0 && int64_t(k) * k_ratio <= n_items) {
         // one f16 pass of upper bounds, then the exact re-scoring of the candidates (refine_topk.cu)
         fp.a_last_kb = akb_upper; fp.filter = 1;
         rc = cg == 2 ? dispatch_cap<1, false, 2>(pl.cap, a0, a0, b0, b0, fp, true, stream)
