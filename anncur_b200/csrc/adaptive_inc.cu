@@ -53,7 +53,7 @@ struct DgArgs {
 // TN = 64: 256 threads, 8 warps (2 x 4).  TN = 32 (fp64 operands only): the narrow launches of the block algorithms (N <= 32:
 // a 32-wide sub-block) on 64 x 32 tiles with 128 threads, 4 warps (2 x 2) -- no half-empty tile, twice the CTAs per SM.
 template <bool GATHER, int TN>
-__global__ void __launch_bounds__(TN == 64 ? 256 : 128, TN == 64 ? 2 : 4)
+__global__ void __launch_bounds__(TN == 64 ? 256 : 128, TN == 64 ? (GATHER ? 3 : 2) : 4)
 dgemm_nt_kernel(const DgArgs p) {
     static_assert(TN == 64 || (TN == 32 && !GATHER), "tile width");
     constexpr int NT = TN == 64 ? 256 : 128;               // threads
