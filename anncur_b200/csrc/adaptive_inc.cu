@@ -391,7 +391,7 @@ append_anchors_kernel(const int64_t* __restrict__ new_anchors, int n, int n_quer
 // sub-block of <= 32 after the other), then y = L^-T z by blocks in reverse (the block inverses make every step a transposed
 // matrix-vector product), then e = (M y)^T.  Per-query rows come in rounds of n, each cut into sub-blocks of <= 32 columns
 // whose 32 x 32 inverses sit at Linvq + (local row) * 32; the shared block (s columns) has its s x s inverse L1inv.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 backsolve_e_kernel(const float* __restrict__ Rt, int k_q, int64_t n_items, const int64_t* __restrict__ shared_anc, const double* __restrict__ L1inv, int s,
                    const int64_t* __restrict__ anc_q, int64_t bs_anc, const double* __restrict__ Lq, int64_t bsLq, int ldl,
                    const double* __restrict__ Linvq, int64_t bsLinv, double* __restrict__ z, int64_t bsz, int n, int rounds_done,
